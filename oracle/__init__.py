@@ -1,0 +1,225 @@
+"""TEST INFRASTRUCTURE ONLY -- ctypes access to the CPU oracle.
+
+* ``solve`` / ``cell_to_node`` / ``interp`` : the plain-C restatement
+  (``oracle/fsm_oracle.c``), always available once ``make -C oracle`` ran.
+* ``RefGrid`` : the UNMODIFIED reference (``ttcr/Grid3Drnfs.h``, ``Grid3Drcfs.h``)
+  behind ``oracle/ref_shim.cpp``; available when ``oracle/_ref/libttcr_ref.so``
+  exists (built in the container where ``/root/reference`` is mounted; the
+  prebuilt ``.so`` travels to the GPU box).
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` /
+``--impl reference`` legs may import this package.  ``ttcr_b200`` never does.
+
+Array conventions are the reference's C++ ones: flat, x fastest,
+``n = (k*ny1 + j)*nx1 + i`` (``ttcr/Grid3Drn.h:2823``).  Helpers ``to_cxx`` /
+``from_cxx`` convert from / to numpy ``(nx, ny, nz)`` C-order arrays the way
+``src/ttcrpy/rgrid.pyx:559-566`` and ``:435`` do (flatten / reshape ``order='F'``).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = os.path.join(_HERE, "libfsm_oracle.so")
+_REF = os.path.join(_HERE, "_ref", "libttcr_ref.so")
+
+
+def build(quiet: bool = True) -> None:
+    """(Re)build the oracle libraries with ``make`` (compiling the checker, not using it)."""
+    subprocess.run(["make", "-C", _HERE] + (["-s"] if quiet else []), check=True,
+                   stdout=subprocess.DEVNULL if quiet else None)
+
+
+_lib = None
+_ref = None
+
+
+def _load():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB):
+            build()
+        _lib = C.CDLL(_LIB)
+    return _lib
+
+
+def have_ref() -> bool:
+    return os.path.exists(_REF)
+
+
+def _load_ref():
+    global _ref
+    if _ref is None:
+        if not have_ref():
+            raise RuntimeError("oracle/_ref/libttcr_ref.so not built (needs /root/reference)")
+        lib = C.CDLL(_REF)
+        lib.ttcr_ref_last_error.restype = C.c_char_p
+        lib.ttcr_ref_create.restype = C.c_void_p
+        lib.ttcr_ref_create.argtypes = [C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_double,
+                                        C.c_double, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int,
+                                        C.c_int, C.c_int, C.c_int]
+        lib.ttcr_ref_destroy.argtypes = [C.c_void_p]
+        lib.ttcr_ref_nnodes.restype = C.c_size_t
+        lib.ttcr_ref_nnodes.argtypes = [C.c_void_p]
+        dp = C.POINTER(C.c_double)
+        lib.ttcr_ref_set_slowness.argtypes = [C.c_void_p, dp, C.c_size_t]
+        lib.ttcr_ref_get_slowness.argtypes = [C.c_void_p, dp]
+        lib.ttcr_ref_raytrace.argtypes = [C.c_void_p, dp, dp, C.c_size_t, dp, C.c_size_t, dp, C.c_size_t, dp]
+        lib.ttcr_ref_raytrace_multi.argtypes = [C.c_void_p, C.c_size_t, dp, dp, dp, C.c_size_t, dp, dp]
+        lib.ttcr_ref_get_tt.argtypes = [C.c_void_p, dp, C.c_size_t]
+        lib.ttcr_ref_get_niter.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        _ref = lib
+    return _ref
+
+
+def to_cxx(a: np.ndarray) -> np.ndarray:
+    """numpy (nx,ny,nz) C-order -> flat x-fastest (rgrid.pyx:559)."""
+    return np.ascontiguousarray(np.asarray(a).flatten(order="F"))
+
+
+def from_cxx(v: np.ndarray, shape) -> np.ndarray:
+    """flat x-fastest -> numpy (nx,ny,nz) (rgrid.pyx:435)."""
+    return np.asarray(v).reshape(shape, order="F")
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+class RefGrid:
+    """The reference's own Grid3Drnfs / Grid3Drcfs (double or float)."""
+
+    def __init__(self, ncx, ncy, ncz, dx, xmin=0.0, ymin=0.0, zmin=0.0, eps=1e-5, maxit=50, weno=True,
+                 cell_slowness=False, dtype=np.float64, tt_from_rp=False, n_threads=1, translate_grid=False):
+        lib = _load_ref()
+        self._lib = lib
+        self.dtype = np.dtype(dtype)
+        self.shape = (ncx + 1, ncy + 1, ncz + 1)
+        self._h = lib.ttcr_ref_create(0 if self.dtype == np.float64 else 1, int(bool(cell_slowness)), ncx, ncy,
+                                      ncz, dx, xmin, ymin, zmin, eps, maxit, int(bool(weno)),
+                                      int(bool(tt_from_rp)), n_threads, int(bool(translate_grid)))
+        if not self._h:
+            raise RuntimeError(lib.ttcr_ref_last_error().decode())
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.ttcr_ref_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def _chk(self, rc):
+        if rc:
+            msg = self._lib.ttcr_ref_last_error().decode()
+            raise {1: RuntimeError, 2: ValueError, 3: ArithmeticError}.get(rc, RuntimeError)(msg)
+
+    def set_slowness(self, s_flat):
+        s = np.ascontiguousarray(s_flat, dtype=np.float64).ravel()
+        self._chk(self._lib.ttcr_ref_set_slowness(self._h, _dp(s), s.size))
+
+    def get_slowness(self):
+        out = np.empty(self._lib.ttcr_ref_nnodes(self._h))
+        self._chk(self._lib.ttcr_ref_get_slowness(self._h, _dp(out)))
+        return out
+
+    def raytrace(self, tx, t0, rx, thread_no=0):
+        """returns (tt at rx, seconds)"""
+        tx = np.ascontiguousarray(tx, dtype=np.float64).reshape(-1, 3)
+        t0 = np.ascontiguousarray(np.broadcast_to(np.asarray(t0, dtype=np.float64), (tx.shape[0],)))
+        rx = np.ascontiguousarray(rx, dtype=np.float64).reshape(-1, 3)
+        tt = np.empty(rx.shape[0])
+        sec = C.c_double()
+        self._chk(self._lib.ttcr_ref_raytrace(self._h, _dp(tx), _dp(t0), tx.shape[0], _dp(rx), rx.shape[0],
+                                              _dp(tt), thread_no, C.byref(sec)))
+        return tt, sec.value
+
+    def raytrace_multi(self, tx, t0, rx):
+        """one Tx point per source; same receivers for all; the reference's own thread fan-out."""
+        tx = np.ascontiguousarray(tx, dtype=np.float64).reshape(-1, 3)
+        t0 = np.ascontiguousarray(np.broadcast_to(np.asarray(t0, dtype=np.float64), (tx.shape[0],)))
+        rx = np.ascontiguousarray(rx, dtype=np.float64).reshape(-1, 3)
+        tt = np.empty((tx.shape[0], rx.shape[0]))
+        sec = C.c_double()
+        self._chk(self._lib.ttcr_ref_raytrace_multi(self._h, tx.shape[0], _dp(tx), _dp(t0), _dp(rx),
+                                                    rx.shape[0], _dp(tt), C.byref(sec)))
+        return tt, sec.value
+
+    def get_tt(self, thread_no=0):
+        out = np.empty(self._lib.ttcr_ref_nnodes(self._h))
+        self._chk(self._lib.ttcr_ref_get_tt(self._h, _dp(out), thread_no))
+        return out.astype(self.dtype)
+
+    def niter(self):
+        a, b = C.c_int(), C.c_int()
+        self._chk(self._lib.ttcr_ref_get_niter(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+
+def _sfx(dtype):
+    dtype = np.dtype(dtype)
+    if dtype == np.float64:
+        return "_d", C.c_double
+    if dtype == np.float32:
+        return "_f", C.c_float
+    raise ValueError(dtype)
+
+
+def cell_to_node(s_cell_flat, ncx, ncy, ncz, dtype=np.float64):
+    """Grid3Drcfs::setSlowness (Grid3Drcfs.h:88-171) on flat x-fastest arrays."""
+    sfx, ct = _sfx(dtype)
+    lib = _load()
+    sc = np.ascontiguousarray(s_cell_flat, dtype=dtype).ravel()
+    if sc.size != ncx * ncy * ncz:
+        raise ValueError("Error: slowness vectors of incompatible size.")
+    sn = np.empty((ncx + 1) * (ncy + 1) * (ncz + 1), dtype=dtype)
+    f = getattr(lib, "fsmo_cell_to_node" + sfx)
+    f.restype = None
+    f.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_void_p]
+    f(sc.ctypes.data, ncx, ncy, ncz, sn.ctypes.data)
+    return sn
+
+
+def solve(ncx, ncy, ncz, dx, s_node_flat, tx, t0=0.0, xmin=0.0, ymin=0.0, zmin=0.0, eps=1e-5, maxit=50,
+          weno=False, dtype=np.float64, order=0):
+    """Grid3Drnfs::raytrace (Grid3Drnfs.h:84-155) on flat arrays.
+
+    returns (tt flat x-fastest, niter, niterw).  ``order=1`` visits nodes by diagonal level.
+    """
+    sfx, ct = _sfx(dtype)
+    lib = _load()
+    s = np.ascontiguousarray(s_node_flat, dtype=dtype).ravel()
+    n = (ncx + 1) * (ncy + 1) * (ncz + 1)
+    if s.size != n:
+        raise ValueError("Error: slowness vectors of incompatible size.")
+    tx = np.ascontiguousarray(np.asarray(tx, dtype=dtype).reshape(-1, 3))
+    t0 = np.ascontiguousarray(np.broadcast_to(np.asarray(t0, dtype=dtype), (tx.shape[0],)))
+    tt = np.empty(n, dtype=dtype)
+    ni, nw = C.c_int(), C.c_int()
+    f = getattr(lib, "fsmo_solve" + sfx)
+    f.restype = C.c_int
+    f.argtypes = [C.c_size_t] * 3 + [ct] * 5 + [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                             C.c_size_t, C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                             C.c_int]
+    rc = f(ncx, ncy, ncz, dx, xmin, ymin, zmin, eps, maxit, int(bool(weno)), s.ctypes.data, tx.ctypes.data,
+           t0.ctypes.data, tx.shape[0], tt.ctypes.data, C.byref(ni), C.byref(nw), order)
+    if rc:
+        raise RuntimeError("Error: Point outside grid.")
+    return tt, ni.value, nw.value
+
+
+def interp(ncx, ncy, ncz, dx, tt_flat, rx, xmin=0.0, ymin=0.0, zmin=0.0, dtype=np.float64):
+    """Grid3Drn::getTraveltime (Grid3Drn.h:794-930) at receiver points."""
+    sfx, ct = _sfx(dtype)
+    lib = _load()
+    tt = np.ascontiguousarray(tt_flat, dtype=dtype).ravel()
+    rx = np.ascontiguousarray(np.asarray(rx, dtype=dtype).reshape(-1, 3))
+    out = np.empty(rx.shape[0], dtype=dtype)
+    f = getattr(lib, "fsmo_interp" + sfx)
+    f.restype = None
+    f.argtypes = [C.c_size_t] * 3 + [ct] * 4 + [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+    f(ncx, ncy, ncz, dx, xmin, ymin, zmin, tt.ctypes.data, rx.ctypes.data, rx.shape[0], out.ctypes.data)
+    return out
