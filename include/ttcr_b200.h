@@ -1,0 +1,145 @@
+/*
+ * ttcr_b200 -- C ABI of the B200-native 3D rectilinear fast-sweeping (FSM) eikonal solver.
+ *
+ * This is the drop-in boundary for ONE hot path of groupeLIAMG/ttcr: the classes
+ * Grid3Drnfs / Grid3Drcfs (and their OpenCL twins) behind ttcrpy.rgrid.Grid3d.  The
+ * reference has no C ABI: its boundary is the abstract C++ class ttcr::Grid3D<T1,T2>
+ * (ttcr/Grid3D.h:44-466) as declared for Cython in src/ttcrpy/rgrid.pxd:30-106.  Every
+ * entry point below names the reference member it replaces.  A header-only adapter that
+ * subclasses ttcr::Grid3D<T1,T2> and forwards to this ABI is in
+ * include/Grid3Drfs_B200.h; the Cython / ctypes bindings are shown in INTEGRATION.md.
+ *
+ * Conventions
+ *  - All pointers are HOST pointers owned by the caller; the library copies in and out
+ *    (same ownership rule as the reference: std::vector by value/reference, rgrid.pyx:153).
+ *    The library owns all device memory behind the handle.
+ *  - Element type of every `const void*` / `void*` array is the grid dtype chosen at
+ *    creation (TTCR_B200_F64 -> double, TTCR_B200_F32 -> float).
+ *  - nx, ny, nz are CELL counts (reference constructor, ttcr/Grid3Drnfs.h:39-50); node
+ *    counts are nx+1, ny+1, nz+1.
+ *  - `order` selects the memory order of full-grid arrays:
+ *      TTCR_B200_ORDER_X_FASTEST : n = (k*(ny+1)+j)*(nx+1)+i, the reference C++ order
+ *                                  (ttcr/Grid3Drn.h:2823; cells: (k*ny+j)*nx+i, :404)
+ *      TTCR_B200_ORDER_Z_FASTEST : n = (i*(ny+1)+j)*(nz+1)+k, numpy C order of an
+ *                                  (nx+1,ny+1,nz+1) array -- lets the Python surface skip
+ *                                  the order='F' flatten of rgrid.pyx:559-566 / :435.
+ *  - Every function returns a status code; ttcr_b200_last_error() gives the message.
+ *    The status codes map 1:1 onto the C++ exception types the reference throws, so the
+ *    adapter can rethrow them and Cython's `except +` behaviour is unchanged.
+ *  - Thread safety: concurrent ttcr_b200_raytrace() calls on one handle are allowed for
+ *    DISTINCT slots (slot == the reference's threadNo; per-slot traveltime field and CUDA
+ *    stream).  Slowness must not change during solves.
+ */
+#ifndef TTCR_B200_H
+#define TTCR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ttcr_b200_grid ttcr_b200_grid;
+
+enum {
+    TTCR_B200_OK = 0,
+    TTCR_B200_ERR_RUNTIME = 1, /* std::runtime_error: point outside grid (Grid3Drn.h:784-786) */
+    TTCR_B200_ERR_LENGTH = 2,  /* std::length_error: slowness size mismatch (Grid3Drn.h:82-85) */
+    TTCR_B200_ERR_LOGIC = 3,   /* std::logic_error (Grid3Drnfs.h:111-113) */
+    TTCR_B200_ERR_INVALID = 4, /* std::invalid_argument: bad handle / argument */
+    TTCR_B200_ERR_CUDA = 5,    /* CUDA failure (no CPU fallback: the call fails) */
+    TTCR_B200_ERR_UNSUPPORTED = 6
+};
+
+enum { TTCR_B200_F64 = 0, TTCR_B200_F32 = 1 };
+enum { TTCR_B200_ORDER_X_FASTEST = 0, TTCR_B200_ORDER_Z_FASTEST = 1 };
+
+/* Per-slot statistics of the last solve (extension; reference exposes only get_niter /
+ * get_niterw, Grid3Drnfs.h:56-57, and the OpenCL profile printout, Grid3Drn_OpenCL.h:204-229). */
+typedef struct {
+    int niter;            /* first-order iterations (groups of 8 directional sweeps) */
+    int niterw;           /* WENO iterations */
+    double solve_ms;      /* device time, CUDA events: reinit + initFSM + sweeps + reductions */
+    double sweep_ms;      /* device time of the sweep kernels only */
+    long long launches;   /* kernels launched by the solve */
+    long long sweep_launches;
+    double last_change;   /* L1 change of the last iteration */
+    int kernel;           /* sweep kernel actually used (TTCR_B200_KERNEL_*) */
+} ttcr_b200_stats;
+
+enum { TTCR_B200_KERNEL_AUTO = 0, TTCR_B200_KERNEL_PLANE = 1, TTCR_B200_KERNEL_TILE = 2 };
+
+/* Replaces: new Grid3Drnfs<T,uint32_t>(nx,ny,nz,dx,xmin,ymin,zmin,eps,maxit,weno,ttrp,intVel,nt,
+ * translateOrigin) (Grid3Drnfs.h:39-50, rgrid.pyx:256-261) and the Grid3Drcfs twin
+ * (Grid3Drcfs.h:40-52, rgrid.pyx:221-227) when cell_slowness != 0.
+ * n_slots == the reference's nt (one traveltime field per slot).  device: CUDA ordinal, or -1
+ * for the current device. */
+int ttcr_b200_create(ttcr_b200_grid** out, uint32_t nx, uint32_t ny, uint32_t nz, double dx,
+                     double xmin, double ymin, double zmin, double eps, int maxit, int weno,
+                     int tt_from_rp, int interp_vel, size_t n_slots, int translate_origin,
+                     int cell_slowness, int dtype, int device);
+
+/* Replaces: delete grid (rgrid.pyx:284-285). */
+void ttcr_b200_destroy(ttcr_b200_grid* g);
+
+/* Message of the last error on this handle (or of the last failed create if g == NULL). */
+const char* ttcr_b200_last_error(const ttcr_b200_grid* g);
+
+/* Replaces: Grid3Drn::setSlowness (Grid3Drn.h:82-89, n == nodes) or Grid3Drcfs::setSlowness
+ * (Grid3Drcfs.h:88-171, n == cells; 8/4/2/1-cell average onto nodes, on the device).
+ * TTCR_B200_ERR_LENGTH on size mismatch. */
+int ttcr_b200_set_slowness(ttcr_b200_grid* g, const void* s, size_t n, int order);
+
+/* Replaces: Grid3Drn::getSlowness (Grid3Drn.h:90-97): NODE slowness, (nx+1)(ny+1)(nz+1) values. */
+int ttcr_b200_get_slowness(ttcr_b200_grid* g, void* out, int order);
+
+/* Replaces: Grid3D::raytrace(Tx,t0,Rx,traveltimes,threadNo) (Grid3D.h:115-119, :470-502) ->
+ * Grid3Drnfs::raytrace (Grid3Drnfs.h:84-155).  tx_xyz: ntx x 3, rx_xyz: nrx x 3 (row major),
+ * t0: ntx, tt_out: nrx (may be NULL when nrx == 0).  All Tx points belong to ONE source.
+ * Receiver traveltimes are Grid3Drn::getTraveltime (trilinear, Grid3Drn.h:794-930).
+ * TTCR_B200_ERR_RUNTIME if a point is outside the grid (checkPts, Grid3Drn.h:771-790). */
+int ttcr_b200_raytrace(ttcr_b200_grid* g, const void* tx_xyz, const void* t0, size_t ntx,
+                       const void* rx_xyz, size_t nrx, void* tt_out, size_t slot);
+
+/* Replaces: Grid3D::raytrace(vector<vector<sxyz>>&Tx, vector<vector<T>>&t0, vector<vector<sxyz>>&Rx,
+ * vector<vector<T>>&tt) (Grid3D.h:172-175, :810-853).  Source s owns Tx points
+ * [tx_off[s], tx_off[s+1]) and receivers [rx_off[s], rx_off[s+1]); tt_out is indexed like rx.
+ * Sources are dealt round-robin to the slots, each slot on its own CUDA stream (the
+ * reference's one-source-per-thread fan-out).  niter/niterw (may be NULL): per source. */
+int ttcr_b200_raytrace_multi(ttcr_b200_grid* g, size_t nsrc, const size_t* tx_off, const void* tx_xyz,
+                             const void* t0, const size_t* rx_off, const void* rx_xyz, void* tt_out,
+                             int* niter, int* niterw);
+
+/* Replaces: Grid3Drn::getTT(tt, threadNo) (Grid3Drn.h:102-108): the full traveltime field. */
+int ttcr_b200_get_tt(ttcr_b200_grid* g, void* out, size_t slot, int order);
+
+/* Replaces: Grid3Drnfs::get_niter / get_niterw (Grid3Drnfs.h:56-57), per slot. */
+int ttcr_b200_get_niter(ttcr_b200_grid* g, size_t slot, int* niter, int* niterw);
+
+/* Replaces: Grid3D::setTraveltimeFromRaypath / setUsePool (Grid3D.h:287,302-309) and tuning knobs.
+ * keys: "tt_from_rp" (0/1), "kernel" (TTCR_B200_KERNEL_*), "tile_rows" (flag chunk, rows),
+ *       "ctas_per_sm", "use_pool" (accepted, ignored). */
+int ttcr_b200_set_option(ttcr_b200_grid* g, const char* key, double value);
+
+/* Replaces: Grid3D::getNthreads (Grid3D.h:309). */
+size_t ttcr_b200_n_slots(const ttcr_b200_grid* g);
+
+/* Extension.  Solve only: sources already described by host Tx (tiny), slowness resident on the
+ * device; the field stays on the device (no receiver extraction, no field copy).  This is the
+ * region the Mnodes/s metric is defined on. */
+int ttcr_b200_solve(ttcr_b200_grid* g, const void* tx_xyz, const void* t0, size_t ntx, size_t slot);
+
+/* Extension: statistics of the last solve on a slot. */
+int ttcr_b200_get_stats(ttcr_b200_grid* g, size_t slot, ttcr_b200_stats* out);
+
+/* Extension: device memory held by the handle, in bytes. */
+size_t ttcr_b200_device_bytes(const ttcr_b200_grid* g);
+
+/* Library version string. */
+const char* ttcr_b200_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TTCR_B200_H */

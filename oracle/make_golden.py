@@ -1,0 +1,117 @@
+"""TEST INFRASTRUCTURE: generate tests/golden/*.npz from the UNMODIFIED reference.
+
+Run in the container where /root/reference is mounted:
+
+    make -C oracle && python oracle/make_golden.py
+
+Every file holds the inputs (grid, slowness, sources, receivers) and what the reference's own
+Grid3Drnfs / Grid3Drcfs (through oracle/_ref/libttcr_ref.so) produced for them: the full
+traveltime field, receiver traveltimes, niter / niterw.  The two `ref_*` cases use the
+reference's own test fixtures (tests/files/gradient_medium.vtr, layers_medium.vtr, src.dat,
+rcv.dat) and also store the analytic solution at the receivers
+(sol_analytique_*_tt.vtr), so the reference's acceptance criterion (mean relative error
+< 0.01, tests/test_grid3d.cpp:68-96,181,199) can be re-checked anywhere.
+Arrays are stored in numpy (nx,ny,nz) C order.
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+import oracle as O  # noqa: E402
+from ttcr_b200.vtr import read_vtr  # noqa: E402
+
+REF = "/root/reference/tests/files"
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def run_ref(x, y, z, slowness, cell, src, t0, rcv, weno, dtype, eps=1e-5, maxit=50, translate=False):
+    ncx, ncy, ncz = x.size - 1, y.size - 1, z.size - 1
+    dx = float(np.asarray(x, dtype=dtype)[1] - np.asarray(x, dtype=dtype)[0])
+    g = O.RefGrid(ncx, ncy, ncz, dx, float(x[0]), float(y[0]), float(z[0]), eps=eps, maxit=maxit, weno=weno,
+                  cell_slowness=cell, dtype=dtype, translate_grid=translate)
+    g.set_slowness(O.to_cxx(slowness))
+    tt_rcv, _ = g.raytrace(src, t0, rcv)
+    field = O.from_cxx(g.get_tt(), (x.size, y.size, z.size))
+    node_s = O.from_cxx(g.get_slowness(), (x.size, y.size, z.size))
+    ni, nw = g.niter()
+    g.close()
+    out = dict(tt_grid=np.ascontiguousarray(field), tt_rcv=tt_rcv.astype(dtype), niter=ni, niterw=nw)
+    if cell:
+        out["node_slowness"] = np.ascontiguousarray(node_s.astype(dtype))
+    return out
+
+
+def save(name, **kw):
+    os.makedirs(OUT, exist_ok=True)
+    path = os.path.join(OUT, name + ".npz")
+    np.savez_compressed(path, **kw)
+    print(f"{name}: niter={kw.get('niter')} niterw={kw.get('niterw')} {os.path.getsize(path) / 1024:.0f} KiB")
+
+
+def reference_fixtures():
+    src = np.loadtxt(os.path.join(REF, "src.dat"), skiprows=1).reshape(1, 4)
+    rcv = np.loadtxt(os.path.join(REF, "rcv.dat"), skiprows=1)
+    for tag, model, key, cell, sol in (("gradient", "gradient_medium.vtr", "point_data", False, "sol_analytique_gradient_tt.vtr"),
+                                       ("layers", "layers_medium.vtr", "cell_data", True, "sol_analytique_couches_tt.vtr")):
+        m = read_vtr(os.path.join(REF, model))
+        x, y, z = m["x"], m["y"], m["z"]
+        dim = (x.size - 1, y.size - 1, z.size - 1) if cell else (x.size, y.size, z.size)
+        slowness = np.ascontiguousarray(m[key]["Slowness"].reshape(dim, order="F"))
+        a = read_vtr(os.path.join(REF, sol))
+        at = a["point_data"]["Travel Time"].reshape((a["x"].size, a["y"].size, a["z"].size), order="F")
+        # rcv.dat points are integer lattice points of the analytic grid (z = 0 face)
+        ia = np.rint((rcv[:, 0] - a["x"][0]) / (a["x"][1] - a["x"][0])).astype(int)
+        ja = np.rint((rcv[:, 1] - a["y"][0]) / (a["y"][1] - a["y"][0])).astype(int)
+        ka = np.rint((rcv[:, 2] - a["z"][0]) / (a["z"][1] - a["z"][0])).astype(int)
+        analytic = at[ia, ja, ka]
+        for dtype in (np.float64, np.float32):
+            for weno in (1, 0):
+                r = run_ref(x, y, z, slowness, cell, src[:, 1:4], src[:, 0], rcv, weno, dtype)
+                err = np.mean(np.abs(r["tt_rcv"][1:] - analytic[1:]) / analytic[1:])
+                assert (not weno) or err < 0.01, err   # the reference's criterion is on weno3=1 runs
+                if dtype == np.float32:
+                    r["tt_grid"] = r["tt_grid"].astype(np.float32)
+                save(f"ref_{tag}_medium_{'w' if weno else 'f'}_{np.dtype(dtype).name}", x=x, y=y, z=z,
+                     slowness=slowness, cell_slowness=cell, src=src, rcv=rcv, weno=weno, eps=1e-5, maxit=50,
+                     analytic_rcv=analytic, ref_mean_rel_err=err, **r)
+
+
+def synthetic():
+    rng = np.random.default_rng(12345)
+    cases = []
+    # (name, n nodes per axis (nx,ny,nz), cell, sources (t0,x,y,z), weno, translate, origin)
+    cases.append(("syn_het21_corner", (21, 21, 21), False, [[0, 0, 0, 0]], 0.0))
+    cases.append(("syn_het21_offnode", (21, 21, 21), False, [[0.5, 3.3, 7.1, 12.9]], 0.0))
+    cases.append(("syn_het_ragged", (15, 21, 34), False, [[0, 6.0, 10.0, 4.0]], 0.0))
+    cases.append(("syn_het_multitx", (19, 17, 33), False, [[0.1, 2.0, 2.0, 2.0], [0.0, 15.5, 11.2, 3.9], [0.3, 18.0, 16.0, 32.0]], 0.0))
+    cases.append(("syn_cells_ragged", (18, 14, 35), True, [[0, 10.0, 8.0, 17.0]], 0.0))
+    cases.append(("syn_translate", (17, 17, 17), False, [[0, 1005.0, 2010.0, -495.0]], 1000.0))
+    for name, (nx, ny, nz), cell, srcs, org in cases:
+        h = 1.0
+        x = org + h * np.arange(nx)
+        y = 2 * org + h * np.arange(ny)
+        z = -0.5 * org + h * np.arange(nz)
+        dim = (nx - 1, ny - 1, nz - 1) if cell else (nx, ny, nz)
+        X, Y, Z = np.meshgrid(np.arange(dim[0]) * h, np.arange(dim[1]) * h, np.arange(dim[2]) * h, indexing="ij")
+        slowness = (1 + 0.3 * np.sin(0.7 * X) * np.cos(0.9 * Y)) / (1 + 0.1 * Z) * np.exp(0.05 * rng.standard_normal(dim))
+        src = np.array(srcs, dtype=np.float64)
+        rcv = np.column_stack([rng.uniform(x[0], x[-1], 40), rng.uniform(y[0], y[-1], 40), rng.uniform(z[0], z[-1], 40)])
+        rcv[:5] = np.column_stack([x[[0, -1, 3, 5, 7]], y[[0, -1, 3, 6, 2]], z[[0, -1, 9, 1, 4]]])   # on-node receivers
+        rcv[5, 0] = x[4]; rcv[6, 1] = y[2]; rcv[7, 2] = z[8]                                      # on-face receivers
+        rcv[8, :2] = (x[3], y[3]); rcv[9, 1:] = (y[1], z[1]); rcv[10, ::2] = (x[2], z[2])          # on-edge receivers
+        for dtype in (np.float64, np.float32):
+            for weno in (0, 1):
+                r = run_ref(x, y, z, slowness, cell, src[:, 1:4], src[:, 0], rcv, weno, dtype, translate=(org != 0.0))
+                save(f"{name}_{'w' if weno else 'f'}_{np.dtype(dtype).name}", x=x, y=y, z=z, slowness=slowness,
+                     cell_slowness=cell, src=src, rcv=rcv, weno=weno, eps=1e-5, maxit=50, translate=(org != 0.0), **r)
+
+
+if __name__ == "__main__":
+    if not O.have_ref():
+        sys.exit("oracle/_ref/libttcr_ref.so missing: run `make -C oracle` where /root/reference exists")
+    reference_fixtures()
+    synthetic()

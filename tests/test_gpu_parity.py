@@ -1,0 +1,172 @@
+"""GPU parity tests: the CUDA path (through the C ABI / the Grid3d mirror) against
+ (1) the fields the unmodified reference produced (tests/golden), and
+ (2) the CPU oracle on seeded inputs,
+ fp64: bit-exact; fp32: max relative difference <= 1e-4 (BASELINE.json north_star tolerance).
+"""
+import numpy as np
+import pytest
+
+from conftest import golden_names, load_golden
+
+pytestmark = pytest.mark.gpu
+
+RTOL32 = 1e-4   # north_star: travel times within 1e-4 relative of the reference CPU Grid3Drnfs
+
+
+def rel_err(a, ref, floor):
+    a = np.asarray(a, dtype=np.float64)
+    ref = np.asarray(ref, dtype=np.float64)
+    return float(np.max(np.abs(a - ref) / np.maximum(np.abs(ref), floor)))
+
+
+def make_grid(g, kernel=None, n_threads=1):
+    from ttcr_b200 import Grid3d
+    grid = Grid3d(g["x"], g["y"], g["z"], n_threads=n_threads, cell_slowness=g["cell_slowness"], method="FSM",
+                  tt_from_rp=False, eps=g["eps"], maxit=g["maxit"], weno=g["weno"], translate_grid=g["translate"],
+                  dtype=g["dtype"])
+    if kernel is not None:
+        grid.set_option("kernel", kernel)
+    return grid
+
+
+@pytest.mark.parametrize("kernel", [1, 2])
+@pytest.mark.parametrize("name", golden_names())
+def test_golden(name, kernel):
+    g = load_golden(name)
+    grid = make_grid(g, kernel)
+    tt = grid.raytrace(g["src"], g["rcv"], g["slowness"], aggregate_src=True)
+    field = grid.get_grid_traveltimes()
+    ni, nw = grid.get_niter()
+    dx = float(g["x"][1] - g["x"][0])
+    floor = dx * float(np.min(g["slowness"]))
+    if g["dtype"] == np.float64:
+        assert np.array_equal(field, g["tt_grid"]), f"max rel {rel_err(field, g['tt_grid'], floor):.3e}"
+        assert np.array_equal(tt, g["tt_rcv"])
+        assert (ni, nw) == (g["niter"], g["niterw"])
+    else:
+        assert rel_err(field, g["tt_grid"], floor) <= RTOL32
+        assert rel_err(tt, g["tt_rcv"], floor) <= RTOL32
+        assert ni == g["niter"] and abs(nw - g["niterw"]) <= 1
+    if g["cell_slowness"]:
+        assert np.array_equal(grid.get_slowness(), g["node_slowness"])
+    if "analytic_rcv" in g and g["weno"]:
+        err = np.mean(np.abs(tt[1:] - g["analytic_rcv"][1:]) / g["analytic_rcv"][1:])
+        assert err < 0.01   # the reference's own acceptance test (tests/test_grid3d.cpp:181,199)
+
+
+def _model(n, seed):
+    rng = np.random.default_rng(seed)
+    x = np.linspace(0.0, 20.0, n)
+    X, Y, Z = np.meshgrid(x, x, x, indexing="ij")
+    s = (1 + 0.3 * np.sin(0.7 * X) * np.cos(0.9 * Y)) / (1 + 0.1 * Z) * np.exp(0.02 * rng.standard_normal((n, n, n)))
+    return x, s
+
+
+@pytest.mark.parametrize("kernel", [1, 2])
+@pytest.mark.parametrize("dtype,weno,n", [(np.float32, 0, 64), (np.float32, 1, 64), (np.float64, 0, 48),
+                                          (np.float64, 1, 40), (np.float32, 0, 97)])
+def test_against_oracle_seeded(oracle, kernel, dtype, weno, n):
+    """config 1 scale (64^3 node slowness, 1 source) and neighbours, vs the CPU oracle on the same inputs"""
+    from ttcr_b200 import Grid3d
+    x, s = _model(n, 100 + n)
+    src = np.array([[x[n // 3], x[n // 2], x[n // 5]]])
+    grid = Grid3d(x, x, x, cell_slowness=0, tt_from_rp=False, weno=weno, dtype=dtype)
+    grid.set_option("kernel", kernel)
+    grid.raytrace(src, src, s)
+    field = grid.get_grid_traveltimes()
+    xt = x.astype(dtype)
+    dx = float(xt[1] - xt[0])
+    ref, ni, nw = oracle.solve(n - 1, n - 1, n - 1, dx, oracle.to_cxx(s.astype(dtype)), src.astype(dtype), 0.0, weno=weno,
+                               dtype=dtype)
+    ref = oracle.from_cxx(ref, (n, n, n))
+    if dtype == np.float64:
+        assert np.array_equal(field, ref)
+        assert grid.get_niter() == (ni, nw)
+    else:
+        assert rel_err(field, ref, dx * s.min()) <= RTOL32
+        assert grid.get_niter()[0] == ni
+
+
+def test_plane_and_tile_kernels_agree_bitwise():
+    """both sweep kernels execute the same Gauss-Seidel DAG with the same arithmetic"""
+    from ttcr_b200 import Grid3d
+    n = (70, 45, 83)
+    rng = np.random.default_rng(3)
+    s = rng.uniform(0.3, 1.0, n)
+    x, y, z = (np.arange(m) * 0.25 for m in n)
+    src = np.array([[0.1, 3.0, 2.0, 11.1]])
+    out = []
+    for kernel in (1, 2):
+        grid = Grid3d(x, y, z, cell_slowness=0, tt_from_rp=False, weno=1, dtype=np.float32)
+        grid.set_option("kernel", kernel)
+        grid.raytrace(src, src[:, 1:], s)
+        out.append((grid.get_grid_traveltimes(), grid.get_niter()))
+    assert np.array_equal(out[0][0], out[1][0])
+    assert out[0][1] == out[1][1]
+
+
+def test_homogeneous_analytic_config2_scaled():
+    """config 2 (homogeneous, centre source, t = s*dist), scaled to 128^3 for test time"""
+    from ttcr_b200 import Grid3d
+    n = 128
+    x = np.arange(n, dtype=np.float64)
+    s = np.full((n, n, n), 1.0 / 3.0)
+    src = np.array([[64.0, 64.0, 64.0]])
+    grid = Grid3d(x, x, x, cell_slowness=0, tt_from_rp=False, weno=1, dtype=np.float32)
+    grid.raytrace(src, src, s)
+    f = grid.get_grid_traveltimes().astype(np.float64)
+    X, Y, Z = np.meshgrid(x, x, x, indexing="ij")
+    exact = np.sqrt((X - 64) ** 2 + (Y - 64) ** 2 + (Z - 64) ** 2) / 3.0
+    m = exact > 3.0 / 3.0 * 2.5   # outside the frozen box
+    assert np.mean(np.abs(f[m] - exact[m]) / exact[m]) < 5e-3
+
+
+def test_multi_source_slots_and_idempotence():
+    from ttcr_b200 import Grid3d
+    n = 40
+    x, s = _model(n, 5)
+    rng = np.random.default_rng(11)
+    src = rng.uniform(0.5, 19.5, (6, 3))
+    rcv = rng.uniform(0.0, 20.0, (6, 3))
+    g1 = Grid3d(x, x, x, n_threads=1, cell_slowness=0, tt_from_rp=False, weno=0, dtype=np.float32)
+    g3 = Grid3d(x, x, x, n_threads=3, cell_slowness=0, tt_from_rp=False, weno=0, dtype=np.float32)
+    t1 = g1.raytrace(src, rcv, s)
+    t3 = g3.raytrace(src, rcv, s)
+    assert np.array_equal(t1, t3)
+    assert np.array_equal(t1, g1.raytrace(src, rcv))   # same call twice -> same answer
+    # single slot addressed explicitly
+    t = g3.raytrace(src[2:3], rcv[2:3], thread_no=2)
+    assert t[0] == t1[2]
+    assert np.all(np.isfinite(g3.get_grid_traveltimes(2)))
+
+
+def test_errors_match_reference_behaviour():
+    from ttcr_b200 import Grid3d
+    x = np.arange(9.0)
+    g = Grid3d(x, x, x, cell_slowness=0, tt_from_rp=False)
+    with pytest.raises(ValueError, match="wrong size"):
+        g.set_slowness(np.ones(10))
+    g.set_slowness(np.ones((9, 9, 9)))
+    with pytest.raises(ValueError, match="outside"):
+        g.raytrace(np.array([[9.5, 0, 0]]), np.array([[1.0, 1, 1]]))
+    with pytest.raises(ValueError, match="Thread number"):
+        g.get_grid_traveltimes(3)
+    g2 = Grid3d(x, x, x, cell_slowness=0, tt_from_rp=True)
+    g2.set_slowness(np.ones((9, 9, 9)))
+    with pytest.raises(NotImplementedError):
+        g2.raytrace(np.array([[1.0, 1, 1]]), np.array([[2.0, 2, 2]]))
+    g3 = Grid3d(x, x, x, cell_slowness=0, tt_from_rp=False)
+    with pytest.raises(RuntimeError, match="slowness"):
+        g3.raytrace(np.array([[1.0, 1, 1]]), np.array([[2.0, 2, 2]]))
+
+
+def test_builder_from_vtr(tmp_path):
+    from ttcr_b200 import Grid3d, write_vtr
+    g = load_golden("syn_cells_ragged_w_float64")
+    fn = str(tmp_path / "m.vtr")
+    write_vtr(fn, g["x"], g["y"], g["z"], cell_data={"Slowness": g["slowness"].flatten(order="F")})
+    grid = Grid3d.builder(fn, tt_from_rp=0, weno=1)
+    assert grid.cell_slowness
+    tt = grid.raytrace(g["src"], g["rcv"])
+    assert np.array_equal(tt, g["tt_rcv"])
+    assert np.array_equal(grid.get_grid_traveltimes(), g["tt_grid"])

@@ -1,0 +1,95 @@
+"""CPU tests of the oracle (tests/ may use oracle/; the product may not).
+
+The plain-C restatement (oracle/fsm_oracle.c) must reproduce, bit for bit, the fields the
+UNMODIFIED reference produced (tests/golden/*.npz, written by oracle/make_golden.py through
+oracle/_ref) -- and the live reference when oracle/_ref is present.
+"""
+import numpy as np
+import pytest
+
+from conftest import golden_names, load_golden
+
+
+def _run_oracle(O, g, order=0):
+    dt = g["dtype"]
+    x, y, z = g["x"], g["y"], g["z"]
+    ncx, ncy, ncz = x.size - 1, y.size - 1, z.size - 1
+    xt = np.asarray(x, dtype=dt)
+    dx = float(xt[1] - xt[0])
+    org = np.array([x[0], y[0], z[0]], dtype=dt)
+    s = O.to_cxx(g["slowness"].astype(dt))
+    if g["cell_slowness"]:
+        s = O.cell_to_node(s, ncx, ncy, ncz, dtype=dt)
+    src = g["src"]
+    tx = src[:, 1:4].astype(dt)
+    rx = g["rcv"].astype(dt)
+    mins = org.copy()
+    if g["translate"]:   # Grid3D.h:478-485, Grid3Drn.h:362-369
+        tx = tx - org
+        rx = rx - org
+        mins = np.zeros(3, dtype=dt)
+    tt, ni, nw = O.solve(ncx, ncy, ncz, dx, s, tx, src[:, 0].astype(dt), float(mins[0]), float(mins[1]), float(mins[2]),
+                         eps=g["eps"], maxit=g["maxit"], weno=g["weno"], dtype=dt, order=order)
+    trx = O.interp(ncx, ncy, ncz, dx, tt, rx, float(mins[0]), float(mins[1]), float(mins[2]), dtype=dt)
+    return O.from_cxx(tt, (x.size, y.size, z.size)), trx, ni, nw, s
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_restatement_matches_reference_golden_bitwise(oracle, name):
+    g = load_golden(name)
+    tt, trx, ni, nw, s = _run_oracle(oracle, g)
+    assert (ni, nw) == (g["niter"], g["niterw"])
+    assert tt.dtype == g["tt_grid"].dtype
+    assert np.array_equal(tt, g["tt_grid"]), f"max |d| = {np.abs(tt - g['tt_grid']).max()}"
+    assert np.array_equal(trx, g["tt_rcv"])
+    if g["cell_slowness"]:
+        assert np.array_equal(oracle.from_cxx(s, tt.shape), g["node_slowness"])
+
+
+@pytest.mark.parametrize("name", golden_names("syn_het_ragged*") + golden_names("syn_cells*"))
+def test_plane_order_is_bit_identical_to_lexicographic(oracle, name):
+    """any topological order of the Gauss-Seidel DAG gives the same field (what the GPU kernels rely on)"""
+    g = load_golden(name)
+    tt, _, ni, nw, _ = _run_oracle(oracle, g, order=1)
+    assert (ni, nw) == (g["niter"], g["niterw"])
+    assert np.array_equal(tt, g["tt_grid"])
+
+
+@pytest.mark.parametrize("name", golden_names("ref_*_w_*"))
+def test_reference_acceptance_criterion(oracle, name):
+    """tests/test_grid3d.cpp:68-96,181,199: mean relative error vs analytic < 0.01 over rcv.dat[1:]"""
+    g = load_golden(name)
+    _, trx, _, _, _ = _run_oracle(oracle, g)
+    err = np.mean(np.abs(trx[1:] - g["analytic_rcv"][1:]) / g["analytic_rcv"][1:])
+    assert err < 0.01
+    assert abs(err - float(g["ref_mean_rel_err"])) < 1e-12
+
+
+def test_live_reference_if_present(oracle):
+    """where /root/reference was compiled (oracle/_ref), re-pin the restatement on a fresh random case"""
+    if not oracle.have_ref():
+        pytest.skip("oracle/_ref not built on this machine")
+    rng = np.random.default_rng(7)
+    n = (17, 23, 20)
+    s = rng.uniform(0.2, 1.0, n)
+    for dt in (np.float64, np.float32):
+        for weno in (0, 1):
+            g = oracle.RefGrid(n[0] - 1, n[1] - 1, n[2] - 1, 0.5, 1.0, -2.0, 3.0, weno=weno, dtype=dt)
+            g.set_slowness(oracle.to_cxx(s))
+            tx = np.array([[3.25, 1.0, 7.5], [1.0, -2.0, 3.0]])
+            g.raytrace(tx, [0.0, 0.25], np.zeros((0, 3)))
+            ref = g.get_tt()
+            tt, ni, nw = oracle.solve(n[0] - 1, n[1] - 1, n[2] - 1, 0.5, g.get_slowness().astype(dt), tx, [0.0, 0.25],
+                                      1.0, -2.0, 3.0, weno=weno, dtype=dt)
+            assert (ni, nw) == g.niter()
+            assert np.array_equal(tt, ref)
+
+
+def test_oracle_errors(oracle):
+    s = np.ones(27)
+    with pytest.raises(RuntimeError):
+        oracle.solve(2, 2, 2, 1.0, s, [[5.0, 0, 0]])
+    with pytest.raises(ValueError):
+        oracle.solve(2, 2, 2, 1.0, np.ones(26), [[0.0, 0, 0]])
+    with pytest.raises(ValueError):
+        oracle.cell_to_node(np.ones(7), 2, 2, 2)

@@ -1,0 +1,583 @@
+// Host side of libttcr_b200.so: the grid object behind the C ABI of include/ttcr_b200.h.
+//
+// Mirrors, for the FSM path only, what the reference spreads over Grid3D (Grid3D.h:470-502,
+// :810-853: origin translation, receiver extraction, source fan-out), Grid3Drn (setSlowness /
+// getTT / checkPts, Grid3Drn.h:82-108, :771-790) and the Grid3Drnfs / Grid3Drcfs drivers
+// (Grid3Drnfs.h:84-155, Grid3Drcfs.h:88-247).  There is no CPU solver in this library: if a CUDA
+// call fails the entry point returns TTCR_B200_ERR_CUDA.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <sstream>
+#include <stdexcept>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/ttcr_b200.h"
+#include "kernels.cuh"
+#include "sweep_tile.cuh"
+
+namespace ttcrb200 {
+
+struct Err : std::exception {
+    int code;
+    std::string msg;
+    Err(int c, std::string m) : code(c), msg(std::move(m)) {}
+    const char* what() const noexcept override { return msg.c_str(); }
+};
+
+#define CK(call)                                                                                      \
+    do {                                                                                              \
+        cudaError_t e_ = (call);                                                                      \
+        if (e_ != cudaSuccess) {                                                                      \
+            std::ostringstream os_;                                                                   \
+            os_ << "CUDA error: " << cudaGetErrorString(e_) << " at " << __FILE__ << ":" << __LINE__  \
+                << " (" #call ")";                                                                    \
+            throw Err(TTCR_B200_ERR_CUDA, os_.str());                                                 \
+        }                                                                                             \
+    } while (0)
+
+static inline unsigned nblocks(size_t n, unsigned threads = 256, unsigned cap = 148 * 16) {
+    size_t b = (n + threads - 1) / threads;
+    return (unsigned)std::min<size_t>(std::max<size_t>(b, 1), cap);
+}
+
+struct GridBase {
+    virtual ~GridBase() {}
+    virtual void set_slowness(const void* s, size_t n, int order) = 0;
+    virtual void get_slowness(void* out, int order) = 0;
+    virtual void solve(const void* tx, const void* t0, size_t ntx, size_t slot) = 0;
+    virtual void raytrace(const void* tx, const void* t0, size_t ntx, const void* rx, size_t nrx, void* tt,
+                          size_t slot) = 0;
+    virtual void raytrace_multi(size_t nsrc, const size_t* tx_off, const void* tx, const void* t0,
+                                const size_t* rx_off, const void* rx, void* tt, int* niter, int* niterw) = 0;
+    virtual void get_tt(void* out, size_t slot, int order) = 0;
+    virtual void stats(size_t slot, ttcr_b200_stats* out) = 0;
+    virtual void set_option(const std::string& key, double v) = 0;
+    virtual size_t n_slots() const = 0;
+    virtual size_t device_bytes() const = 0;
+};
+
+template <typename T>
+class Grid final : public GridBase {
+   public:
+    Grid(uint32_t ncx, uint32_t ncy, uint32_t ncz, double dx, double xmin, double ymin, double zmin, double eps,
+         int maxit, bool weno, bool ttrp, bool /*interp_vel*/, size_t nslots, bool translate, bool cell, int device)
+        : maxit_(maxit), weno_(weno), ttrp_(ttrp), cell_(cell), translate_(translate) {
+        if (ncx < 1 || ncy < 1 || ncz < 1) throw Err(TTCR_B200_ERR_INVALID, "grid must have at least one cell per axis");
+        if (nslots < 1) throw Err(TTCR_B200_ERR_INVALID, "n_slots must be >= 1");
+        if ((double)(ncx + 1) * (ncy + 1) * (ncz + 1) > 4294967295.0)
+            throw Err(TTCR_B200_ERR_INVALID, "grid has more nodes than a uint32_t index can address");
+        if (device < 0) CK(cudaGetDevice(&device));
+        dev_ = device;
+        CK(cudaSetDevice(dev_));
+        d_ = make_dims((int)ncx + 1, (int)ncy + 1, (int)ncz + 1);
+        // reference constructor arithmetic, in T (Grid3Drn.h:68-77, buildGridNodes :362-372)
+        g_.dx = T(dx);
+        g_.xmin = T(xmin); g_.ymin = T(ymin); g_.zmin = T(zmin);
+        g_.xmax = g_.xmin + T(ncx) * g_.dx;
+        g_.ymax = g_.ymin + T(ncy) * g_.dx;
+        g_.zmax = g_.zmin + T(ncz) * g_.dx;
+        g_.ncx = (int)ncx; g_.ncy = (int)ncy; g_.ncz = (int)ncz;
+        origin_[0] = origin_[1] = origin_[2] = T(0);
+        if (translate_) {
+            origin_[0] = g_.xmin; origin_[1] = g_.ymin; origin_[2] = g_.zmin;
+            g_.xmax -= g_.xmin; g_.ymax -= g_.ymin; g_.zmax -= g_.zmin;
+            g_.xmin = g_.ymin = g_.zmin = T(0);
+        }
+        // per-node tolerance -> L1 threshold, in T (Grid3Drnfs.h:49)
+        epsilon_ = T(eps);
+        epsilon_ *= static_cast<T>(d_.nodes());
+
+        const size_t ne = d_.elems();
+        for (int l = 0; l < 2; ++l) {
+            CK(cudaMalloc(&slo_[l], ne * sizeof(T)));
+            bytes_ += ne * sizeof(T);
+            CK(cudaMemset(slo_[l], 0, ne * sizeof(T)));
+        }
+        slots_.resize(nslots);
+        for (auto& s : slots_) {
+            CK(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+            CK(cudaEventCreate(&s.e0));
+            CK(cudaEventCreate(&s.e1));
+            for (int l = 0; l < 2; ++l) {
+                CK(cudaMalloc(&s.tt[l], ne * sizeof(T)));
+                CK(cudaMalloc(&s.mask[l], ne / 32 * sizeof(uint32_t)));
+                bytes_ += ne * sizeof(T) + ne / 8;
+                k_fill<T><<<nblocks(ne), 256, 0, s.stream>>>(s.tt[l], ne, Lim<T>::max());
+                CK(cudaMemsetAsync(s.mask[l], 0, ne / 8, s.stream));
+            }
+            CK(cudaMalloc(&s.d_change, sizeof(double)));
+            CK(cudaMallocHost(&s.h_change, sizeof(double)));
+            tile_alloc(s.tile, d_, bytes_);
+            CK(cudaStreamSynchronize(s.stream));
+        }
+        int sms = 0;
+        CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev_));
+        sm_count_ = sms;
+    }
+
+    ~Grid() override {
+        cudaSetDevice(dev_);
+        for (auto& s : slots_) {
+            cudaStreamSynchronize(s.stream);
+            for (int l = 0; l < 2; ++l) { cudaFree(s.tt[l]); cudaFree(s.mask[l]); }
+            cudaFree(s.d_change); cudaFreeHost(s.h_change);
+            cudaFree(s.d_pts); cudaFreeHost(s.h_pts);
+            tile_free(s.tile);
+            cudaEventDestroy(s.e0); cudaEventDestroy(s.e1);
+            cudaStreamDestroy(s.stream);
+        }
+        for (int l = 0; l < 2; ++l) cudaFree(slo_[l]);
+        cudaFree(lin_[0]); cudaFree(lin_[1]);
+    }
+
+    size_t n_slots() const override { return slots_.size(); }
+    size_t device_bytes() const override { return bytes_; }
+
+    // ---- model -------------------------------------------------------------------------------
+    void set_slowness(const void* s, size_t n, int order) override {
+        CK(cudaSetDevice(dev_));
+        const size_t want = cell_ ? (size_t)g_.ncx * g_.ncy * g_.ncz : d_.nodes();
+        if (n != want) throw Err(TTCR_B200_ERR_LENGTH, "Error: slowness vectors of incompatible size.");
+        if (order != 0 && order != 1) throw Err(TTCR_B200_ERR_INVALID, "bad order");
+        std::lock_guard<std::mutex> lk(lin_mu_);
+        ensure_lin();
+        cudaStream_t st = slots_[0].stream;
+        CK(cudaMemcpyAsync(lin_[0], s, n * sizeof(T), cudaMemcpyHostToDevice, st));
+        const T* nodes = lin_[0];
+        if (cell_) {
+            k_cell_to_node<T><<<nblocks(d_.nodes()), 256, 0, st>>>(lin_[0], lin_[1], order, g_.ncx, g_.ncy, g_.ncz);
+            nodes = lin_[1];
+        }
+        for (int l = 0; l < 2; ++l) k_import<T><<<nblocks(d_.elems()), 256, 0, st>>>(nodes, order, slo_[l], l, d_);
+        CK(cudaGetLastError());
+        CK(cudaStreamSynchronize(st));
+        have_slowness_ = true;
+    }
+
+    void get_slowness(void* out, int order) override {
+        CK(cudaSetDevice(dev_));
+        if (order != 0 && order != 1) throw Err(TTCR_B200_ERR_INVALID, "bad order");
+        std::lock_guard<std::mutex> lk(lin_mu_);
+        ensure_lin();
+        cudaStream_t st = slots_[0].stream;
+        k_export<T><<<nblocks(d_.nodes()), 256, 0, st>>>(slo_[0], 0, lin_[0], order, d_);
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(out, lin_[0], d_.nodes() * sizeof(T), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+    }
+
+    void get_tt(void* out, size_t slot, int order) override {
+        CK(cudaSetDevice(dev_));
+        Slot& s = slot_at(slot);
+        if (order != 0 && order != 1) throw Err(TTCR_B200_ERR_INVALID, "bad order");
+        std::lock_guard<std::mutex> lk(lin_mu_);
+        ensure_lin();
+        k_export<T><<<nblocks(d_.nodes()), 256, 0, s.stream>>>(s.tt[0], 0, lin_[0], order, d_);
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(out, lin_[0], d_.nodes() * sizeof(T), cudaMemcpyDeviceToHost, s.stream));
+        CK(cudaStreamSynchronize(s.stream));
+    }
+
+    // ---- solve -------------------------------------------------------------------------------
+    void solve(const void* tx, const void* t0, size_t ntx, size_t slot) override {
+        CK(cudaSetDevice(dev_));
+        Slot& s = slot_at(slot);
+        std::vector<T> vtx, vt0;
+        prepare_tx(tx, t0, ntx, vtx, vt0);
+        solve_device(s, vtx, vt0);
+    }
+
+    void raytrace(const void* tx, const void* t0, size_t ntx, const void* rx, size_t nrx, void* tt, size_t slot) override {
+        CK(cudaSetDevice(dev_));
+        Slot& s = slot_at(slot);
+        std::vector<T> vtx, vt0, vrx;
+        prepare_tx(tx, t0, ntx, vtx, vt0);
+        // checkPts(Rx) before any work, as Grid3Drnfs.h:89-90
+        vrx.assign((const T*)rx, (const T*)rx + 3 * nrx);
+        translate_pts(vrx);
+        check_pts(vrx);
+        if (nrx && ttrp_)
+            throw Err(TTCR_B200_ERR_UNSUPPORTED,
+                      "tt_from_rp=1 (traveltimes integrated along raypaths, Grid3Drn.h:1103-1243) is not part of the "
+                      "B200 FSM path yet; construct the grid with tt_from_rp=0");
+        solve_device(s, vtx, vt0);
+        if (nrx) {
+            ensure_pts(s, 4 * nrx);
+            std::memcpy(s.h_pts, vrx.data(), 3 * nrx * sizeof(T));
+            CK(cudaMemcpyAsync(s.d_pts, s.h_pts, 3 * nrx * sizeof(T), cudaMemcpyHostToDevice, s.stream));
+            T* d_out = s.d_pts + 3 * nrx;
+            k_interp<T><<<(unsigned)((nrx + 127) / 128), 128, 0, s.stream>>>(g_, d_, s.tt[0], s.d_pts, (int)nrx, d_out);
+            CK(cudaGetLastError());
+            CK(cudaMemcpyAsync(s.h_pts + 3 * nrx, d_out, nrx * sizeof(T), cudaMemcpyDeviceToHost, s.stream));
+            CK(cudaStreamSynchronize(s.stream));
+            std::memcpy(tt, s.h_pts + 3 * nrx, nrx * sizeof(T));
+        }
+    }
+
+    // Grid3D.h:810-853: sources dealt to the slots; one host thread per slot drives its stream.
+    void raytrace_multi(size_t nsrc, const size_t* tx_off, const void* tx, const void* t0, const size_t* rx_off,
+                        const void* rx, void* tt, int* niter, int* niterw) override {
+        const size_t nt = std::min(slots_.size(), nsrc);
+        if (nt == 0) return;
+        std::vector<std::string> errs(nt);
+        std::vector<int> codes(nt, 0);
+        auto work = [&](size_t t) {
+            try {
+                for (size_t sidx = t; sidx < nsrc; sidx += nt) {
+                    const size_t a = tx_off[sidx], b = tx_off[sidx + 1], ra = rx_off[sidx], rb = rx_off[sidx + 1];
+                    raytrace((const T*)tx + 3 * a, (const T*)t0 + a, b - a, (const T*)rx + 3 * ra, rb - ra,
+                             (T*)tt + ra, t);
+                    if (niter) niter[sidx] = slots_[t].st.niter;
+                    if (niterw) niterw[sidx] = slots_[t].st.niterw;
+                }
+            } catch (const Err& e) {
+                codes[t] = e.code; errs[t] = e.msg;
+            } catch (const std::exception& e) {
+                codes[t] = TTCR_B200_ERR_RUNTIME; errs[t] = e.what();
+            }
+        };
+        if (nt == 1) {
+            work(0);
+        } else {
+            std::vector<std::thread> th;
+            for (size_t t = 0; t < nt; ++t) th.emplace_back(work, t);
+            for (auto& x : th) x.join();
+        }
+        for (size_t t = 0; t < nt; ++t)
+            if (codes[t]) throw Err(codes[t], errs[t]);
+    }
+
+    void stats(size_t slot, ttcr_b200_stats* out) override { *out = slot_at(slot).st; }
+
+    void set_option(const std::string& key, double v) override {
+        if (key == "tt_from_rp") ttrp_ = v != 0;
+        else if (key == "kernel") {
+            if (v != TTCR_B200_KERNEL_AUTO && v != TTCR_B200_KERNEL_PLANE && v != TTCR_B200_KERNEL_TILE)
+                throw Err(TTCR_B200_ERR_INVALID, "unknown kernel id");
+            kernel_ = (int)v;
+        } else if (key == "tile_rows") tile_opt_.chunk = std::max(1, (int)v);
+        else if (key == "ctas_per_sm") tile_opt_.ctas_per_sm = std::max(0, (int)v);
+        else if (key == "tile_warps") tile_opt_.warps = std::max(1, std::min(16, (int)v));
+        else if (key == "spin_limit") tile_opt_.spin_limit = (long long)v;
+        else if (key == "use_pool") {}
+        else if (key == "maxit") maxit_ = (int)v;
+        else throw Err(TTCR_B200_ERR_INVALID, "unknown option '" + key + "'");
+    }
+
+   private:
+    struct Slot {
+        T* tt[2] = {nullptr, nullptr};          // traveltime field in layouts L1, L2 (padding = MAX)
+        uint32_t* mask[2] = {nullptr, nullptr}; // frozen bit per slot, both layouts
+        cudaStream_t stream = nullptr;
+        cudaEvent_t e0 = nullptr, e1 = nullptr;
+        double* d_change = nullptr;
+        double* h_change = nullptr;
+        T* d_pts = nullptr;   // small point buffer (Tx, t0, Rx, out)
+        T* h_pts = nullptr;
+        size_t pts_cap = 0;
+        TileState tile;
+        ttcr_b200_stats st{};
+    };
+
+    Slot& slot_at(size_t slot) {
+        if (slot >= slots_.size()) throw Err(TTCR_B200_ERR_INVALID, "Thread number is larger than number of threads");
+        return slots_[slot];
+    }
+
+    void ensure_lin() {
+        if (lin_[0]) return;
+        for (int l = 0; l < 2; ++l) {
+            CK(cudaMalloc(&lin_[l], d_.nodes() * sizeof(T)));
+            bytes_ += d_.nodes() * sizeof(T);
+        }
+    }
+
+    void ensure_pts(Slot& s, size_t n) {
+        if (n <= s.pts_cap) return;
+        CK(cudaStreamSynchronize(s.stream));
+        cudaFree(s.d_pts); cudaFreeHost(s.h_pts);
+        s.pts_cap = std::max<size_t>(n, 1024);
+        CK(cudaMalloc(&s.d_pts, s.pts_cap * sizeof(T)));
+        CK(cudaMallocHost(&s.h_pts, s.pts_cap * sizeof(T)));
+    }
+
+    void translate_pts(std::vector<T>& p) const {   // Grid3D.h:478-485
+        if (!translate_) return;
+        for (size_t n = 0; n < p.size(); n += 3) { p[n] -= origin_[0]; p[n + 1] -= origin_[1]; p[n + 2] -= origin_[2]; }
+    }
+
+    void check_pts(const std::vector<T>& p) const {   // Grid3Drn.h:771-790
+        for (size_t n = 0; n < p.size(); n += 3) {
+            if (p[n] < g_.xmin || p[n] > g_.xmax || p[n + 1] < g_.ymin || p[n + 1] > g_.ymax || p[n + 2] < g_.zmin ||
+                p[n + 2] > g_.zmax) {
+                std::ostringstream msg;
+                msg << "Error: Point (" << p[n] << " " << p[n + 1] << " " << p[n + 2] << ") outside grid.";
+                throw Err(TTCR_B200_ERR_RUNTIME, msg.str());
+            }
+        }
+    }
+
+    void prepare_tx(const void* tx, const void* t0, size_t ntx, std::vector<T>& vtx, std::vector<T>& vt0) const {
+        if (!have_slowness_) throw Err(TTCR_B200_ERR_LOGIC, "slowness has not been set");
+        if (ntx == 0) throw Err(TTCR_B200_ERR_INVALID, "source has no Tx point");
+        vtx.assign((const T*)tx, (const T*)tx + 3 * ntx);
+        vt0.assign((const T*)t0, (const T*)t0 + ntx);
+        translate_pts(vtx);
+        check_pts(vtx);
+    }
+
+    FrozenBox frozen_box(const std::vector<T>& vtx, int npts) const {
+        FrozenBox fb{INT32_MAX, -1, INT32_MAX, -1, INT32_MAX, -1};
+        auto upd = [&](double p, double mn, int nc, int& lo, int& hi) {
+            const int c = (int)std::floor((p - mn) / (double)g_.dx);
+            lo = std::min(lo, std::max(0, c - npts - 1));
+            hi = std::max(hi, std::min(nc, c + npts + 2));
+        };
+        for (size_t n = 0; n < vtx.size(); n += 3) {
+            upd(vtx[n], g_.xmin, g_.ncx, fb.ilo, fb.ihi);
+            upd(vtx[n + 1], g_.ymin, g_.ncy, fb.jlo, fb.jhi);
+            upd(vtx[n + 2], g_.zmin, g_.ncz, fb.klo, fb.khi);
+        }
+        return fb;
+    }
+
+    // one directional sweep (dir 0..7 in the reference order) on the layout the field is in
+    void launch_sweep(Slot& s, int dir, bool weno_stage, const FrozenBox& fb, int kernel) {
+        const SweepView w = make_view(d_, dir);
+        T* tt = s.tt[w.layout];
+        if (kernel == TTCR_B200_KERNEL_TILE) {
+            const int nl = tile_sweep<T>(s.tile, tile_opt_, sm_count_, w, d_, tt, slo_[w.layout], s.mask[w.layout], fb,
+                                        g_.dx, weno_stage, s.d_change, s.stream);
+            s.st.launches += nl; s.st.sweep_launches += nl;
+            return;
+        }
+        const dim3 block(32, 8);
+        const int np = w.nu + w.nm - 1;
+        for (int p = 0; p < np; ++p) {
+            const int u_lo = std::max(0, p - w.nm + 1), u_hi = std::min(w.nu - 1, p);
+            const dim3 grid(d_.kpad / 32, (u_hi - u_lo + 1 + 7) / 8);
+            if (weno_stage)
+                k_sweep_plane<T, true><<<grid, block, 0, s.stream>>>(w, d_, tt, slo_[w.layout], s.mask[w.layout], fb, p,
+                                                                    u_lo, u_hi, g_.dx, s.d_change);
+            else
+                k_sweep_plane<T, false><<<grid, block, 0, s.stream>>>(w, d_, tt, slo_[w.layout], s.mask[w.layout], fb, p,
+                                                                     u_lo, u_hi, g_.dx, s.d_change);
+        }
+        s.st.launches += np; s.st.sweep_launches += np;
+    }
+
+    int pick_kernel(bool weno_stage) const {
+        if (kernel_ != TTCR_B200_KERNEL_AUTO) {
+            if (kernel_ == TTCR_B200_KERNEL_TILE && !tile_supported<T>(weno_stage)) return TTCR_B200_KERNEL_PLANE;
+            return kernel_;
+        }
+        if (!tile_supported<T>(weno_stage)) return TTCR_B200_KERNEL_PLANE;
+        return TTCR_B200_KERNEL_TILE;
+    }
+
+    // Grid3Drnfs::raytrace body (Grid3Drnfs.h:92-154) on the device
+    void solve_device(Slot& s, const std::vector<T>& vtx, const std::vector<T>& vt0) {
+        const size_t ntx = vt0.size();
+        const int npts = weno_ ? 2 : 1;
+        const size_t ne = d_.elems();
+        s.st = ttcr_b200_stats{};
+        ensure_pts(s, 4 * ntx);
+        std::memcpy(s.h_pts, vtx.data(), 3 * ntx * sizeof(T));
+        std::memcpy(s.h_pts + 3 * ntx, vt0.data(), ntx * sizeof(T));
+        const FrozenBox fb = frozen_box(vtx, npts);
+
+        CK(cudaEventRecord(s.e0, s.stream));
+        CK(cudaMemcpyAsync(s.d_pts, s.h_pts, 4 * ntx * sizeof(T), cudaMemcpyHostToDevice, s.stream));
+        k_reinit_l1<T><<<nblocks(ne), 256, 0, s.stream>>>(s.tt[0], d_);
+        CK(cudaMemsetAsync(s.mask[0], 0, ne / 8, s.stream));
+        CK(cudaMemsetAsync(s.mask[1], 0, ne / 8, s.stream));
+        k_init_fsm<T><<<1, 32, 0, s.stream>>>(g_, d_, s.d_pts, s.d_pts + 3 * ntx, (int)ntx, npts, s.tt[0], slo_[0], s.mask[0],
+                                              s.mask[1]);
+        CK(cudaGetLastError());
+        s.st.launches += 4;
+
+        int cur = 0;   // layout the field currently lives in
+        float sweep_ms = 0.f;
+        for (int stage = 0; stage < (weno_ ? 2 : 1); ++stage) {
+            const bool wstage = stage == 1;
+            const int kernel = pick_kernel(wstage);
+            s.st.kernel = kernel;
+            int it = 0;
+            T change = Lim<T>::max();
+            while (change >= epsilon_ && it < maxit_) {
+                CK(cudaMemsetAsync(s.d_change, 0, sizeof(double), s.stream));
+                for (int dir = 0; dir < 8; ++dir) {
+                    const int want = make_view(d_, dir).layout;
+                    if (want != cur) {
+                        const dim3 grid((d_.nk + 31) / 32, (d_.nj + 31) / 32, d_.ni);
+                        k_relayout<T><<<grid, dim3(32, 8), 0, s.stream>>>(s.tt[cur], cur, s.tt[want], d_);
+                        s.st.launches += 1;
+                        cur = want;
+                    }
+                    launch_sweep(s, dir, wstage, fb, kernel);
+                }
+                CK(cudaGetLastError());
+                CK(cudaMemcpyAsync(s.h_change, s.d_change, sizeof(double), cudaMemcpyDeviceToHost, s.stream));
+                CK(cudaStreamSynchronize(s.stream));
+                tile_check(s.tile);
+                const double c = *s.h_change;
+                s.st.last_change = c;
+                // the reference accumulates `change` in T; an overflowing double sum maps to T's inf
+                change = c > (double)Lim<T>::max() ? std::numeric_limits<T>::infinity() : (T)c;
+                ++it;
+            }
+            if (wstage) s.st.niterw = it; else s.st.niter = it;
+        }
+        if (cur != 0) throw Err(TTCR_B200_ERR_LOGIC, "internal: field not in layout L1 after the last sweep");
+        CK(cudaEventRecord(s.e1, s.stream));
+        CK(cudaEventSynchronize(s.e1));
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, s.e0, s.e1));
+        s.st.solve_ms = ms;
+        s.st.sweep_ms = sweep_ms;
+    }
+
+    Dims d_{};
+    Geom<T> g_{};
+    T origin_[3];
+    T epsilon_;
+    int maxit_;
+    bool weno_, ttrp_, cell_, translate_;
+    bool have_slowness_ = false;
+    int dev_ = 0, sm_count_ = 148;
+    int kernel_ = TTCR_B200_KERNEL_AUTO;
+    TileOptions tile_opt_{};
+    T* slo_[2] = {nullptr, nullptr};   // node slowness in layouts L1, L2
+    T* lin_[2] = {nullptr, nullptr};   // linear staging buffers (host order)
+    std::mutex lin_mu_;
+    std::vector<Slot> slots_;
+    size_t bytes_ = 0;
+};
+
+}  // namespace ttcrb200
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+using namespace ttcrb200;
+
+struct ttcr_b200_grid {
+    GridBase* impl = nullptr;
+};
+
+static thread_local std::string g_last_error;
+
+template <typename F>
+static int guard(F&& f) {
+    try {
+        f();
+        return TTCR_B200_OK;
+    } catch (const Err& e) {
+        g_last_error = e.msg;
+        return e.code;
+    } catch (const std::bad_alloc&) {
+        g_last_error = "out of host memory";
+        return TTCR_B200_ERR_RUNTIME;
+    } catch (const std::exception& e) {
+        g_last_error = e.what();
+        return TTCR_B200_ERR_RUNTIME;
+    }
+}
+
+#define NEED(g)                                                    \
+    if (!(g) || !(g)->impl) {                                      \
+        g_last_error = "null ttcr_b200_grid handle";               \
+        return TTCR_B200_ERR_INVALID;                              \
+    }
+
+extern "C" {
+
+const char* ttcr_b200_version(void) { return "ttcr_b200 0.1 (sm_100a)"; }
+
+const char* ttcr_b200_last_error(const ttcr_b200_grid*) { return g_last_error.c_str(); }
+
+int ttcr_b200_create(ttcr_b200_grid** out, uint32_t nx, uint32_t ny, uint32_t nz, double dx, double xmin, double ymin,
+                     double zmin, double eps, int maxit, int weno, int tt_from_rp, int interp_vel, size_t n_slots,
+                     int translate_origin, int cell_slowness, int dtype, int device) {
+    if (!out) { g_last_error = "null output pointer"; return TTCR_B200_ERR_INVALID; }
+    *out = nullptr;
+    return guard([&] {
+        int ndev = 0;
+        cudaError_t e = cudaGetDeviceCount(&ndev);
+        if (e != cudaSuccess || ndev == 0)
+            throw Err(TTCR_B200_ERR_CUDA, std::string("no CUDA device available: ") + cudaGetErrorString(e) +
+                                              " (ttcr_b200 has no CPU path)");
+        GridBase* impl;
+        if (dtype == TTCR_B200_F64)
+            impl = new Grid<double>(nx, ny, nz, dx, xmin, ymin, zmin, eps, maxit, weno != 0, tt_from_rp != 0, interp_vel != 0,
+                                    n_slots, translate_origin != 0, cell_slowness != 0, device);
+        else if (dtype == TTCR_B200_F32)
+            impl = new Grid<float>(nx, ny, nz, dx, xmin, ymin, zmin, eps, maxit, weno != 0, tt_from_rp != 0, interp_vel != 0,
+                                   n_slots, translate_origin != 0, cell_slowness != 0, device);
+        else
+            throw Err(TTCR_B200_ERR_INVALID, "dtype must be TTCR_B200_F64 or TTCR_B200_F32");
+        *out = new ttcr_b200_grid{impl};
+    });
+}
+
+void ttcr_b200_destroy(ttcr_b200_grid* g) {
+    if (!g) return;
+    delete g->impl;
+    delete g;
+}
+
+int ttcr_b200_set_slowness(ttcr_b200_grid* g, const void* s, size_t n, int order) {
+    NEED(g);
+    return guard([&] { g->impl->set_slowness(s, n, order); });
+}
+int ttcr_b200_get_slowness(ttcr_b200_grid* g, void* out, int order) {
+    NEED(g);
+    return guard([&] { g->impl->get_slowness(out, order); });
+}
+int ttcr_b200_raytrace(ttcr_b200_grid* g, const void* tx, const void* t0, size_t ntx, const void* rx, size_t nrx, void* tt,
+                       size_t slot) {
+    NEED(g);
+    return guard([&] { g->impl->raytrace(tx, t0, ntx, rx, nrx, tt, slot); });
+}
+int ttcr_b200_raytrace_multi(ttcr_b200_grid* g, size_t nsrc, const size_t* tx_off, const void* tx, const void* t0,
+                             const size_t* rx_off, const void* rx, void* tt, int* niter, int* niterw) {
+    NEED(g);
+    return guard([&] { g->impl->raytrace_multi(nsrc, tx_off, tx, t0, rx_off, rx, tt, niter, niterw); });
+}
+int ttcr_b200_get_tt(ttcr_b200_grid* g, void* out, size_t slot, int order) {
+    NEED(g);
+    return guard([&] { g->impl->get_tt(out, slot, order); });
+}
+int ttcr_b200_get_niter(ttcr_b200_grid* g, size_t slot, int* niter, int* niterw) {
+    NEED(g);
+    return guard([&] {
+        ttcr_b200_stats st;
+        g->impl->stats(slot, &st);
+        if (niter) *niter = st.niter;
+        if (niterw) *niterw = st.niterw;
+    });
+}
+int ttcr_b200_set_option(ttcr_b200_grid* g, const char* key, double value) {
+    NEED(g);
+    return guard([&] { g->impl->set_option(key ? key : "", value); });
+}
+size_t ttcr_b200_n_slots(const ttcr_b200_grid* g) { return g && g->impl ? g->impl->n_slots() : 0; }
+int ttcr_b200_solve(ttcr_b200_grid* g, const void* tx, const void* t0, size_t ntx, size_t slot) {
+    NEED(g);
+    return guard([&] { g->impl->solve(tx, t0, ntx, slot); });
+}
+int ttcr_b200_get_stats(ttcr_b200_grid* g, size_t slot, ttcr_b200_stats* out) {
+    NEED(g);
+    if (!out) { g_last_error = "null output pointer"; return TTCR_B200_ERR_INVALID; }
+    return guard([&] { g->impl->stats(slot, out); });
+}
+size_t ttcr_b200_device_bytes(const ttcr_b200_grid* g) { return g && g->impl ? g->impl->device_bytes() : 0; }
+
+}  // extern "C"
