@@ -31,7 +31,8 @@ def check():
         x, y, z = (np.arange(m) * 0.25 for m in shape)
         s = rng.uniform(0.3, 1.0, shape)
         res = []
-        for kernel, opts in ((1, {}), (2, {}), (2, {"tile_warps": 4, "tile_rows": 2}), (2, {"tile_warps": 16, "tile_rows": 8, "ctas_per_sm": 1})):
+        for kernel, opts in ((1, {}), (2, {}), (2, {"tile_warps": 4, "tile_urows": 2, "tile_rows": 2}), (2, {"tile_urows": 1, "tile_rows": 8, "ctas_per_sm": 1}),
+                             (2, {"tile_urows": 2, "tile_depth": 8, "tile_rows": 1})):
             g = Grid3d(x, y, z, cell_slowness=0, tt_from_rp=False, weno=0, dtype=dtype)
             g.set_option("kernel", kernel)
             for k, v in opts.items():
@@ -58,12 +59,13 @@ def timing(sizes):
         g = Grid3d(x, x, x, cell_slowness=0, tt_from_rp=False, weno=0, dtype=np.float32)
         g.set_slowness(s)
         print(f"--- {n}^3 device bytes {g.device_bytes() / 2**30:.2f} GiB", flush=True)
-        combos = [dict(kernel=2, tile_warps=w, tile_rows=c, ctas_per_sm=o)
-                  for w, c, o in itertools.product((8, 16, 4), (4, 8), (0,))]
-        combos += [dict(kernel=2, tile_warps=8, tile_rows=4, ctas_per_sm=o) for o in (1, 2)]
+        combos = [dict(kernel=2, tile_warps=8, tile_urows=r, tile_rows=c, tile_depth=dd, ctas_per_sm=0)
+                  for r, c, dd in itertools.product((2, 1), (2, 4, 8), (4, 8))]
+        combos += [dict(kernel=2, tile_warps=4, tile_urows=r, tile_rows=4, tile_depth=4, ctas_per_sm=0) for r in (1, 2)]
+        combos += [dict(kernel=2, tile_warps=8, tile_urows=2, tile_rows=4, tile_depth=4, ctas_per_sm=o) for o in (1,)]
         if n <= 256:
             combos.append(dict(kernel=1))
-        for src in ([0.0, 0.0, 0.0], [x[n // 2]] * 3):
+        for src in ([0.0, 0.0, 0.0],):
             for c in combos:
                 for k, v in c.items():
                     g.set_option(k, v)
@@ -79,7 +81,22 @@ def timing(sizes):
                                       ms_per_sweep=round(best["solve_ms"] / nsw, 4), mnodes_s=round(mn), hbm_frac=round(frac, 4))), flush=True)
 
 
+def one(n, opts):
+    x, s = gradient(n)
+    g = Grid3d(x, x, x, cell_slowness=0, tt_from_rp=False, weno=0, dtype=np.float32)
+    g.set_slowness(s)
+    g.set_option("kernel", 2)
+    for kv in opts:
+        k, v = kv.split("=")
+        g.set_option(k, float(v))
+    st = g.solve(np.array([[0.0, 0.0, 0.0]]))
+    print(st)
+
+
 if __name__ == "__main__":
+    if sys.argv[1] == "one":
+        one(int(sys.argv[2]), sys.argv[3:])
+        sys.exit(0)
     if sys.argv[1] == "check":
         sys.exit(0 if check() else 1)
     timing([int(a) for a in sys.argv[2:]])

@@ -265,6 +265,8 @@ class Grid final : public GridBase {
         } else if (key == "tile_rows") tile_opt_.chunk = std::max(1, (int)v);
         else if (key == "ctas_per_sm") tile_opt_.ctas_per_sm = std::max(0, (int)v);
         else if (key == "tile_warps") tile_opt_.warps = std::max(1, std::min(16, (int)v));
+        else if (key == "tile_urows") tile_opt_.rows = std::max(1, std::min(4, (int)v));
+        else if (key == "tile_depth") tile_opt_.depth = (int)v;
         else if (key == "spin_limit") tile_opt_.spin_limit = (long long)v;
         else if (key == "use_pool") {}
         else if (key == "maxit") maxit_ = (int)v;

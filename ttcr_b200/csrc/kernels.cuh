@@ -35,9 +35,9 @@ __global__ void k_reinit_l1(T* __restrict__ tt, Dims d) {
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     for (; e < n; e += stride) {
         const int k = (int)(e % d.kpad);
-        const int q = (int)((e / d.kpad) % d.q);
+        const int q = (int)((e / d.kpad) % d.qs) - GUARD;
         const int j = q - k;
-        if (k < d.nk && j >= 0 && j < d.nj) tt[e] = Lim<T>::max();
+        if (q >= 0 && q < d.q && k < d.nk && j >= 0 && j < d.nj) tt[e] = Lim<T>::max();
     }
 }
 
@@ -56,10 +56,10 @@ __global__ void k_import(const T* __restrict__ lin, int order, T* __restrict__ d
     for (; e < n; e += stride) {
         const int k = (int)(e % d.kpad);
         const size_t row = e / d.kpad;
-        const int r = (int)(row % d.q);
-        const int i = (int)(row / d.q);
+        const int r = (int)(row % d.qs) - GUARD;
+        const int i = (int)(row / d.qs);
         const int j = layout ? r + k - (d.nk - 1) : r - k;
-        if (k < d.nk && j >= 0 && j < d.nj) dst[e] = lin[lin_index(d, order, i, j, k)];
+        if (r >= 0 && r < d.q && k < d.nk && j >= 0 && j < d.nj) dst[e] = lin[lin_index(d, order, i, j, k)];
     }
 }
 
@@ -97,7 +97,7 @@ __global__ void k_relayout(const T* __restrict__ src, int src_layout, T* __restr
             const int jl = src_layout ? rr + lane - 31 : rr - lane;
             const int j = j0 + jl;
             if (jl >= 0 && jl < 32 && j < d.nj && k < d.nk)
-                tile[jl][lane] = src[((size_t)i * d.q + (row0 + rr)) * d.kpad + k];
+                tile[jl][lane] = src[d.row(i, row0 + rr) + k];
         }
     }
     __syncthreads();
@@ -108,7 +108,7 @@ __global__ void k_relayout(const T* __restrict__ src, int src_layout, T* __restr
             const int jl = dl ? rr + lane - 31 : rr - lane;
             const int j = j0 + jl;
             if (jl >= 0 && jl < 32 && j < d.nj && k < d.nk)
-                dst[((size_t)i * d.q + (row0 + rr)) * d.kpad + k] = tile[jl][lane];
+                dst[d.row(i, row0 + rr) + k] = tile[jl][lane];
         }
     }
 }

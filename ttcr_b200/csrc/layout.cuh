@@ -11,10 +11,12 @@
 //   L1[i][q][k],  q = j + k              used by sweeps with sj == sk   (1,2,7,8)
 //   L2[i][r][k],  r = j - k + (nk-1)     used by sweeps with sj != sk   (3,4,5,6)
 //
-// Each has Q = nj + nk - 1 rows per i and rows padded to KPAD = roundup(nk, 32) lanes.
-// Slots that correspond to no node (j out of range, k >= nk) hold +MAX forever, which
-// makes the reference's one-sided face stencils (Grid3Drn.h:2906-2934) fall out of a plain
-// min().  With the reference's sweep order (+++,-++,+-+,--+,++-,-+-,+--,---; :2819-2898) the
+// Each has Q = nj + nk - 1 rows per i and rows padded to KPAD = roundup(nk, 32) lanes; every
+// i-plane additionally carries GUARD never-written rows before and after its Q rows, so that a
+// marching kernel can prefetch a few rows past either end without bounds checks.
+// Slots that correspond to no node (guard rows, j out of range, k >= nk) hold +MAX forever
+// (0 in the slowness arrays), which makes the reference's one-sided face stencils
+// (Grid3Drn.h:2906-2934) fall out of a plain min().  With the reference's sweep order (+++,-++,+-+,--+,++-,-+-,+--,---; :2819-2898) the
 // layout changes only twice per iteration (after sweep 2 and after sweep 6).
 //
 // A sweep is expressed in ORIENTED coordinates (u, m, v): u along i, m along the row axis,
@@ -29,15 +31,20 @@
 
 namespace ttcrb200 {
 
+constexpr int GUARD = 48;   // guard rows on each side of an i-plane (>= NW*R + 2*D + 2 of the tile kernel)
+
 struct Dims {
     int ni, nj, nk;   // node counts along x, y, z
     int kpad;         // lanes per row (multiple of 32)
-    int q;            // rows per i: nj + nk - 1
-    __host__ __device__ size_t rows() const { return (size_t)ni * q; }
+    int q;            // node rows per i: nj + nk - 1
+    int qs;           // allocated rows per i: q + 2*GUARD
+    __host__ __device__ size_t rows() const { return (size_t)ni * qs; }
     __host__ __device__ size_t elems() const { return rows() * kpad; }
     __host__ __device__ size_t nodes() const { return (size_t)ni * nj * nk; }
-    __host__ __device__ size_t l1(int i, int j, int k) const { return ((size_t)i * q + (j + k)) * kpad + k; }
-    __host__ __device__ size_t l2(int i, int j, int k) const { return ((size_t)i * q + (j - k + nk - 1)) * kpad + k; }
+    // element offset of node row r (0 <= r < q) of plane i
+    __host__ __device__ size_t row(int i, int r) const { return ((size_t)i * qs + GUARD + r) * kpad; }
+    __host__ __device__ size_t l1(int i, int j, int k) const { return row(i, j + k) + k; }
+    __host__ __device__ size_t l2(int i, int j, int k) const { return row(i, j - k + nk - 1) + k; }
     __host__ __device__ size_t at(int layout, int i, int j, int k) const { return layout ? l2(i, j, k) : l1(i, j, k); }
 };
 
@@ -46,6 +53,7 @@ inline Dims make_dims(int ni, int nj, int nk) {
     d.ni = ni; d.nj = nj; d.nk = nk;
     d.kpad = (nk + 31) / 32 * 32;
     d.q = nj + nk - 1;
+    d.qs = d.q + 2 * GUARD;
     return d;
 }
 
@@ -66,12 +74,12 @@ inline SweepView make_view(const Dims& d, int dir) {
     SweepView w;
     w.ri = dir & 1; w.rj = (dir >> 1) & 1; w.rk = (dir >> 2) & 1;
     w.layout = (w.rj == w.rk) ? 0 : 1;
-    const long long rowlen = d.kpad, plane = (long long)d.q * d.kpad;
+    const long long rowlen = d.kpad, plane = (long long)d.qs * d.kpad;
     w.su = w.ri ? -plane : plane;
     w.sm = w.rj ? -rowlen : rowlen;
     w.sv = w.rk ? -1 : 1;
-    w.base = (w.ri ? (long long)(d.ni - 1) * plane : 0) + (w.rj ? (long long)(d.q - 1) * rowlen : 0) +
-             (w.rk ? (long long)(d.kpad - 1) : 0);
+    w.base = (w.ri ? (long long)(d.ni - 1) * plane : 0) + (long long)GUARD * rowlen +
+             (w.rj ? (long long)(d.q - 1) * rowlen : 0) + (w.rk ? (long long)(d.kpad - 1) : 0);
     w.nu = d.ni; w.nm = d.q;
     w.vlo = w.rk ? d.kpad - d.nk : 0;
     w.vhi = w.vlo + d.nk;
