@@ -1,0 +1,326 @@
+#!/usr/bin/env python
+"""bench.py -- the headline benchmark of the B200 FSM path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--n NODES]
+
+Workload (config.workload): BASELINE.json configs[2] -- ttcrpy.rgrid.Grid3d 512^3 nodes, fp32, node
+slowness s(z) = 1/(1+0.1 z) on a 20^3 domain (the reference's gradient model, tests/files/mk_models3d.py),
+one source at the corner node, first-order FSM (weno=0), eps=1e-5, maxit=50.  One STEP = one complete
+solve of one source (reinit + initFSM + 8-direction sweeps until converged + convergence reductions).
+
+metric  Mnodes/s = grid nodes x directional sweeps / solve time / 1e6          
+value   inputs (slowness, source) resident in HBM; device time from CUDA events (ttcr_b200_solve)
+e2e     same metric through the public API Grid3d.raytrace(src, rcv, slowness): slowness from PINNED
+        host memory every step (H2D), receiver traveltimes back to the host (D2H), wall clock
+roofline  dominant kernel = the directional-sweep kernel; 12 algorithmic bytes per node per launch
+cpu_baseline  the reference's own CPU FSM (oracle/_ref, built from /root/reference) on a bounded sample
+
+With N > 1 (torchrun, one rank per GPU) every rank solves its own source of the same model (weak
+scaling, source-parallel; no collective in the timed region; the model is broadcast once over NCCL).
+--impl reference times the reference's own CPU implementation (rank 0 only).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "Mnodes/s (grid nodes x sweep-iters / s) on 512^3 FSM"
+UNIT = "Mnodes/s"
+BYTES_PER_NODE_SWEEP = 12.0   # tt read + tt write + slowness read, fp32
+CPU_SAMPLE_N = 192            # nodes per side of the bounded CPU sample
+
+
+def gradient_model(n, dtype=np.float32):
+    x = np.linspace(0.0, 20.0, n)
+    s = np.broadcast_to((1.0 / (1.0 + 0.1 * x))[None, None, :], (n, n, n))
+    return x, np.ascontiguousarray(s, dtype=dtype)
+
+
+def receivers(x):
+    # the reference's rcv.dat pattern: a 21 x 21 lattice on the z = 0 face
+    g = np.linspace(x[0], x[-1], 21)
+    X, Y = np.meshgrid(g, g, indexing="ij")
+    return np.column_stack([X.ravel(), Y.ravel(), np.zeros(X.size)])
+
+
+def source_for_rank(x, rank):
+    if rank == 0:
+        return np.array([[0.0, 0.0, 0.0]])
+    # config 5 pattern: points +-1/4 L around the centre
+    c, q = 0.5 * (x[0] + x[-1]), 0.25 * (x[-1] - x[0])
+    b = rank - 1
+    return np.array([[c + q * (1 if b & 1 else -1), c + q * (1 if b & 2 else -1), c + q * (1 if b & 4 else -1)]])
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except OSError:
+            pass
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        for line in self.f.read().splitlines():
+            c = [t.strip() for t in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1])); mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        self.f.close()
+        os.unlink(self.f.name)
+        if sm:
+            out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(np.max(mx)), "reasons": sorted(reasons),
+                   "samples": len(sm)}
+        return out
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_reference(n, steps, warmup, dtype=np.float32):
+    """The reference's own CPU FSM on an n^3 sample of the workload.  Returns (Mnodes/s, s/step, kind, niter)."""
+    import oracle as O
+    x, s = gradient_model(n, dtype)
+    xt = x.astype(dtype)
+    dx = float(xt[1] - xt[0])
+    src = np.array([[0.0, 0.0, 0.0]])
+    times, niter = [], 0
+    if O.have_ref():
+        kind = "reference"
+        g = O.RefGrid(n - 1, n - 1, n - 1, dx, weno=False, dtype=dtype, eps=1e-5, maxit=50)
+        g.set_slowness(O.to_cxx(s))
+        for k in range(warmup + steps):
+            _, sec = g.raytrace(src, 0.0, np.zeros((0, 3)))
+            if k >= warmup:
+                times.append(sec)
+        niter = g.niter()[0]
+        g.close()
+    else:
+        kind = "port"
+        sf = O.to_cxx(s)
+        for k in range(warmup + steps):
+            t = time.perf_counter()
+            _, niter, _ = O.solve(n - 1, n - 1, n - 1, dx, sf, src, 0.0, weno=False, dtype=dtype)
+            if k >= warmup:
+                times.append(time.perf_counter() - t)
+    sec = float(np.mean(times))
+    return n ** 3 * 8 * niter / sec / 1e6, sec, kind, niter
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    n = CPU_SAMPLE_N
+    t0 = time.perf_counter()
+    v, sec, kind, niter = cpu_reference(n, args.steps, args.warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args.n, extra={"sample": f"{n}^3"}),
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": 1, "kind": kind,
+                         "sample": f"{n}^3-node sample of the workload (same model, source, eps), Grid3Drnfs<float>, "
+                                   f"{niter} iterations, 1 thread: the reference has no intra-source parallelism"},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "wall_s": time.perf_counter() - t0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(n, extra=None):
+    c = {"workload": f"ttcrpy.rgrid.Grid3d {n}^3 nodes, linear-gradient node slowness s=1/(1+0.1z), 1 source per GPU "
+                     f"(rank 0: corner node), first-order FSM (weno=0), eps=1e-5, fp32 (BASELINE.json configs[2])",
+         "nodes": n ** 3, "l2": "inputs larger than L2 (tt + slowness = 1 GiB+ per sweep at 512^3 vs 126 MB L2)",
+         "parallelism": "source-parallel, one grid replica per GPU"}
+    if extra:
+        c.update(extra)
+    return c
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=512, help="nodes per side (512 = the headline workload)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--opt", action="append", default=[], help="library option key=value (development)")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    from ttcr_b200 import Grid3d
+    from ttcr_b200.distributed import broadcast_slowness
+
+    if not torch.cuda.is_available():
+        sys.exit("bench.py: no CUDA device (ttcr_b200 has no CPU path)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    n = args.n
+    warm = max(args.warmup, 3) if args.warmup > 0 else 0
+    x, s_host = gradient_model(n) if rank == 0 else (np.linspace(0.0, 20.0, n), None)
+    g = Grid3d(x, x, x, n_threads=1, cell_slowness=0, method="FSM", tt_from_rp=0, eps=1e-5, maxit=50, weno=0,
+               dtype=np.float32, device=local_rank)
+    for kv in args.opt:
+        k, v = kv.split("=")
+        g.set_option(k, float(v))
+    # the model: generated on rank 0, broadcast once over NCCL (device to device), outside the timed region
+    broadcast_slowness(g, s_host)
+    src = source_for_rank(x, rank)
+    rcv = receivers(x)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident arm -----------------------------------------------------------------------
+    for _ in range(warm):
+        g.solve(src)
+    barrier()
+    clocks = ClockSampler(local_rank)
+    t_wall = time.perf_counter()
+    dev_ms = sweep_ms = 0.0
+    sweeps = launches = sweep_launches = 0
+    st = None
+    for _ in range(args.steps):
+        st = g.solve(src)
+        dev_ms += st["solve_ms"]; sweep_ms += st["sweep_ms"]
+        sweeps += st["sweeps"]; launches += st["launches"]; sweep_launches += st["sweep_launches"]
+    barrier()
+    wall_ms = (time.perf_counter() - t_wall) * 1e3
+    clk = clocks.stop()
+
+    # ---- end-to-end arm: public API, pinned host slowness in, receiver traveltimes out ---------------
+    if rank == 0:
+        s_pinned = torch.from_numpy(s_host).pin_memory()
+    else:
+        s_pinned = torch.from_numpy(g.get_slowness()).pin_memory()
+    s_np = s_pinned.numpy()
+    src4 = np.concatenate([[0.0], src[0]]).reshape(1, 4)
+    for _ in range(min(warm, 2)):
+        g.raytrace(src4, rcv, s_np)
+    barrier()
+    t_e2e = time.perf_counter()
+    e2e_sweeps = 0
+    for _ in range(args.steps):
+        tt = g.raytrace(src4, rcv, s_np)
+        e2e_sweeps += g.get_stats()["sweeps"]
+    barrier()
+    e2e_ms = (time.perf_counter() - t_e2e) * 1e3
+    h2d = int(s_np.nbytes + src4.astype(np.float32).nbytes + rcv.astype(np.float32).nbytes)
+    d2h = int(tt.astype(np.float32).nbytes)
+
+    # ---- reduce over ranks: whole-job node-sweeps, max time ------------------------------------------
+    nodes = float(n) ** 3
+    mine = torch.tensor([nodes * sweeps, dev_ms, wall_ms, nodes * e2e_sweeps, e2e_ms, sweep_ms, float(sweeps),
+                         float(launches)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        tot = mine.clone(); dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+        mx = mine.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+    else:
+        tot, mx = mine, mine
+    tot, mx = tot.cpu().numpy(), mx.cpu().numpy()
+    value = tot[0] / (mx[1] * 1e-3) / 1e6
+    e2e_value = tot[3] / (mx[4] * 1e-3) / 1e6
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        per_launch_ms = sweep_ms / max(sweeps, 1)
+        achieved = BYTES_PER_NODE_SWEEP * nodes / (per_launch_ms * 1e-3) / 1e9
+        traffic = None
+        tj = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+        if os.path.exists(tj):
+            with open(tj) as f:
+                traffic = json.load(f).get(f"{n}")
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warm,
+            "ms_per_step": mx[1] / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": workload_config(n),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": mx[4] / args.steps,
+                    "call": "Grid3d.raytrace(src, rcv, slowness): slowness from pinned host memory, 441 receiver times back"},
+            "gpu_launches": int(tot[7]),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "kernel": "k_sweep_tile (one launch = one directional sweep)",
+                         "algorithmic_bytes_per_launch": BYTES_PER_NODE_SWEEP * nodes,
+                         "avg_launch_ms": per_launch_ms, "peak_source": peak_src},
+            "clocks": clk,
+            "detail": {"niter": st["niter"], "sweeps_per_step": st["sweeps"], "solve_ms_last": st["solve_ms"],
+                       "sweep_ms_per_step": sweep_ms / args.steps, "wall_ms_per_step": mx[2] / args.steps,
+                       "mnode_iters_per_s": value / 8.0, "kernel": st["kernel"],
+                       "device_bytes": g.device_bytes(), "launches_per_step": launches / args.steps},
+        }
+        if not args.no_cpu_baseline:
+            try:
+                v, sec, kind, niter = cpu_reference(CPU_SAMPLE_N, 2, 0)
+                line["cpu_baseline"] = {
+                    "value": v, "unit": UNIT, "cores": 1, "kind": kind,
+                    "sample": f"{CPU_SAMPLE_N}^3-node sample of the workload (same model, source, eps), "
+                              f"Grid3Drnfs<float>, {niter} iterations, {sec:.1f} s per solve, 1 thread: the reference "
+                              f"has no intra-source parallelism"}
+            except Exception as e:   # the baseline is a reported number, never a reason to lose the bench line
+                line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 1, "kind": "unavailable", "sample": str(e)}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

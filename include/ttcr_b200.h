@@ -61,9 +61,10 @@ typedef struct {
     int niter;            /* first-order iterations (groups of 8 directional sweeps) */
     int niterw;           /* WENO iterations */
     double solve_ms;      /* device time, CUDA events: reinit + initFSM + sweeps + reductions */
-    double sweep_ms;      /* device time of the sweep kernels only */
+    double sweep_ms;      /* device time of the sweep kernels only (CUDA events around each directional sweep) */
     long long launches;   /* kernels launched by the solve */
-    long long sweep_launches;
+    long long sweep_launches; /* of which sweep kernels */
+    int sweeps;           /* directional sweeps executed: 8 * (niter + niterw) */
     double last_change;   /* L1 change of the last iteration */
     int kernel;           /* sweep kernel actually used (TTCR_B200_KERNEL_*) */
 } ttcr_b200_stats;
@@ -91,6 +92,12 @@ const char* ttcr_b200_last_error(const ttcr_b200_grid* g);
  * TTCR_B200_ERR_LENGTH on size mismatch. */
 int ttcr_b200_set_slowness(ttcr_b200_grid* g, const void* s, size_t n, int order);
 
+/* Extension: same as ttcr_b200_set_slowness but `s_dev` is a DEVICE pointer on the grid's device
+ * (e.g. the landing buffer of an NCCL broadcast; the reference's OpenCL upload,
+ * Grid3Drn_OpenCL.h:675-703, has no such path).  Synchronous with respect to the caller's prior
+ * work on that buffer only if the caller has synchronised; the call itself returns when done. */
+int ttcr_b200_set_slowness_device(ttcr_b200_grid* g, const void* s_dev, size_t n, int order);
+
 /* Replaces: Grid3Drn::getSlowness (Grid3Drn.h:90-97): NODE slowness, (nx+1)(ny+1)(nz+1) values. */
 int ttcr_b200_get_slowness(ttcr_b200_grid* g, void* out, int order);
 
@@ -113,6 +120,9 @@ int ttcr_b200_raytrace_multi(ttcr_b200_grid* g, size_t nsrc, const size_t* tx_of
 
 /* Replaces: Grid3Drn::getTT(tt, threadNo) (Grid3Drn.h:102-108): the full traveltime field. */
 int ttcr_b200_get_tt(ttcr_b200_grid* g, void* out, size_t slot, int order);
+
+/* Extension: the full traveltime field into a DEVICE buffer of (nx+1)(ny+1)(nz+1) elements. */
+int ttcr_b200_get_tt_device(ttcr_b200_grid* g, void* out_dev, size_t slot, int order);
 
 /* Replaces: Grid3Drnfs::get_niter / get_niterw (Grid3Drnfs.h:56-57), per slot. */
 int ttcr_b200_get_niter(ttcr_b200_grid* g, size_t slot, int* niter, int* niterw);

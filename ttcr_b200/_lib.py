@@ -20,7 +20,7 @@ KERNEL_AUTO, KERNEL_PLANE, KERNEL_TILE = 0, 1, 2
 # every symbol include/ttcr_b200.h declares (tests check that the library exports all of them)
 SYMBOLS = (
     "ttcr_b200_create", "ttcr_b200_destroy", "ttcr_b200_last_error", "ttcr_b200_set_slowness",
-    "ttcr_b200_get_slowness", "ttcr_b200_raytrace", "ttcr_b200_raytrace_multi", "ttcr_b200_get_tt",
+    "ttcr_b200_set_slowness_device", "ttcr_b200_get_tt_device", "ttcr_b200_get_slowness", "ttcr_b200_raytrace", "ttcr_b200_raytrace_multi", "ttcr_b200_get_tt",
     "ttcr_b200_get_niter", "ttcr_b200_set_option", "ttcr_b200_n_slots", "ttcr_b200_solve",
     "ttcr_b200_get_stats", "ttcr_b200_device_bytes", "ttcr_b200_version",
 )
@@ -28,7 +28,7 @@ SYMBOLS = (
 
 class Stats(C.Structure):
     _fields_ = [("niter", C.c_int), ("niterw", C.c_int), ("solve_ms", C.c_double), ("sweep_ms", C.c_double),
-                ("launches", C.c_longlong), ("sweep_launches", C.c_longlong), ("last_change", C.c_double),
+                ("launches", C.c_longlong), ("sweep_launches", C.c_longlong), ("sweeps", C.c_int), ("last_change", C.c_double),
                 ("kernel", C.c_int)]
 
     def asdict(self):
@@ -61,6 +61,8 @@ def load() -> C.CDLL:
     lib.ttcr_b200_destroy.argtypes = [vp]
     lib.ttcr_b200_destroy.restype = None
     lib.ttcr_b200_set_slowness.argtypes = [vp, vp, sz, i32]
+    lib.ttcr_b200_set_slowness_device.argtypes = [vp, vp, sz, i32]
+    lib.ttcr_b200_get_tt_device.argtypes = [vp, vp, sz, i32]
     lib.ttcr_b200_get_slowness.argtypes = [vp, vp, i32]
     lib.ttcr_b200_raytrace.argtypes = [vp, vp, vp, sz, vp, sz, vp, sz]
     lib.ttcr_b200_raytrace_multi.argtypes = [vp, sz, vp, vp, vp, vp, vp, vp, vp, vp]

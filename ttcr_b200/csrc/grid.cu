@@ -50,6 +50,8 @@ static inline unsigned nblocks(size_t n, unsigned threads = 256, unsigned cap = 
 struct GridBase {
     virtual ~GridBase() {}
     virtual void set_slowness(const void* s, size_t n, int order) = 0;
+    virtual void set_slowness_device(const void* s, size_t n, int order) = 0;
+    virtual void get_tt_device(void* out, size_t slot, int order) = 0;
     virtual void get_slowness(void* out, int order) = 0;
     virtual void solve(const void* tx, const void* t0, size_t ntx, size_t slot) = 0;
     virtual void raytrace(const void* tx, const void* t0, size_t ntx, const void* rx, size_t nrx, void* tt,
@@ -127,6 +129,7 @@ class Grid final : public GridBase {
         for (auto& s : slots_) {
             cudaStreamSynchronize(s.stream);
             for (int l = 0; l < 2; ++l) { cudaFree(s.tt[l]); cudaFree(s.mask[l]); }
+            for (auto e : s.sweep_ev) cudaEventDestroy(e);
             cudaFree(s.d_change); cudaFreeHost(s.h_change);
             cudaFree(s.d_pts); cudaFreeHost(s.h_pts);
             tile_free(s.tile);
@@ -141,7 +144,10 @@ class Grid final : public GridBase {
     size_t device_bytes() const override { return bytes_; }
 
     // ---- model -------------------------------------------------------------------------------
-    void set_slowness(const void* s, size_t n, int order) override {
+    void set_slowness(const void* s, size_t n, int order) override { set_slowness_any(s, n, order, cudaMemcpyHostToDevice); }
+    void set_slowness_device(const void* s, size_t n, int order) override { set_slowness_any(s, n, order, cudaMemcpyDeviceToDevice); }
+
+    void set_slowness_any(const void* s, size_t n, int order, cudaMemcpyKind kind) {
         CK(cudaSetDevice(dev_));
         const size_t want = cell_ ? (size_t)g_.ncx * g_.ncy * g_.ncz : d_.nodes();
         if (n != want) throw Err(TTCR_B200_ERR_LENGTH, "Error: slowness vectors of incompatible size.");
@@ -149,7 +155,7 @@ class Grid final : public GridBase {
         std::lock_guard<std::mutex> lk(lin_mu_);
         ensure_lin();
         cudaStream_t st = slots_[0].stream;
-        CK(cudaMemcpyAsync(lin_[0], s, n * sizeof(T), cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(lin_[0], s, n * sizeof(T), kind, st));
         const T* nodes = lin_[0];
         if (cell_) {
             k_cell_to_node<T><<<nblocks(d_.nodes()), 256, 0, st>>>(lin_[0], lin_[1], order, g_.ncx, g_.ncy, g_.ncz);
@@ -182,6 +188,15 @@ class Grid final : public GridBase {
         k_export<T><<<nblocks(d_.nodes()), 256, 0, s.stream>>>(s.tt[0], 0, lin_[0], order, d_);
         CK(cudaGetLastError());
         CK(cudaMemcpyAsync(out, lin_[0], d_.nodes() * sizeof(T), cudaMemcpyDeviceToHost, s.stream));
+        CK(cudaStreamSynchronize(s.stream));
+    }
+
+    void get_tt_device(void* out, size_t slot, int order) override {
+        CK(cudaSetDevice(dev_));
+        Slot& s = slot_at(slot);
+        if (order != 0 && order != 1) throw Err(TTCR_B200_ERR_INVALID, "bad order");
+        k_export<T><<<nblocks(d_.nodes()), 256, 0, s.stream>>>(s.tt[0], 0, (T*)out, order, d_);
+        CK(cudaGetLastError());
         CK(cudaStreamSynchronize(s.stream));
     }
 
@@ -286,6 +301,8 @@ class Grid final : public GridBase {
         size_t pts_cap = 0;
         TileState tile;
         ttcr_b200_stats st{};
+        std::vector<cudaEvent_t> sweep_ev;   // pairs of events around the directional sweeps
+        size_t sweep_ev_used = 0;
     };
 
     Slot& slot_at(size_t slot) {
@@ -395,6 +412,7 @@ class Grid final : public GridBase {
         std::memcpy(s.h_pts + 3 * ntx, vt0.data(), ntx * sizeof(T));
         const FrozenBox fb = frozen_box(vtx, npts);
 
+        s.sweep_ev_used = 0;
         CK(cudaEventRecord(s.e0, s.stream));
         CK(cudaMemcpyAsync(s.d_pts, s.h_pts, 4 * ntx * sizeof(T), cudaMemcpyHostToDevice, s.stream));
         k_reinit_l1<T><<<nblocks(ne), 256, 0, s.stream>>>(s.tt[0], d_);
@@ -403,7 +421,7 @@ class Grid final : public GridBase {
         k_init_fsm<T><<<1, 32, 0, s.stream>>>(g_, d_, s.d_pts, s.d_pts + 3 * ntx, (int)ntx, npts, s.tt[0], slo_[0], s.mask[0],
                                               s.mask[1]);
         CK(cudaGetLastError());
-        s.st.launches += 4;
+        s.st.launches += 2;   // k_reinit_l1, k_init_fsm
 
         int cur = 0;   // layout the field currently lives in
         float sweep_ms = 0.f;
@@ -423,7 +441,20 @@ class Grid final : public GridBase {
                         s.st.launches += 1;
                         cur = want;
                     }
+                    cudaEvent_t ea = nullptr, eb = nullptr;
+                    if (s.sweep_ev_used + 2 <= kMaxSweepEvents) {
+                        while (s.sweep_ev.size() < s.sweep_ev_used + 2) {
+                            cudaEvent_t e;
+                            CK(cudaEventCreate(&e));
+                            s.sweep_ev.push_back(e);
+                        }
+                        ea = s.sweep_ev[s.sweep_ev_used]; eb = s.sweep_ev[s.sweep_ev_used + 1];
+                        s.sweep_ev_used += 2;
+                        CK(cudaEventRecord(ea, s.stream));
+                    }
                     launch_sweep(s, dir, wstage, fb, kernel);
+                    if (eb) CK(cudaEventRecord(eb, s.stream));
+                    s.st.sweeps += 1;
                 }
                 CK(cudaGetLastError());
                 CK(cudaMemcpyAsync(s.h_change, s.d_change, sizeof(double), cudaMemcpyDeviceToHost, s.stream));
@@ -443,9 +474,17 @@ class Grid final : public GridBase {
         float ms = 0.f;
         CK(cudaEventElapsedTime(&ms, s.e0, s.e1));
         s.st.solve_ms = ms;
+        for (size_t i = 0; i + 1 < s.sweep_ev_used; i += 2) {
+            float t = 0.f;
+            CK(cudaEventElapsedTime(&t, s.sweep_ev[i], s.sweep_ev[i + 1]));
+            sweep_ms += t;
+        }
+        if (s.sweep_ev_used < (size_t)2 * s.st.sweeps && s.sweep_ev_used > 0)   // more sweeps than events: extrapolate
+            sweep_ms *= (float)(2.0 * s.st.sweeps / (double)s.sweep_ev_used);
         s.st.sweep_ms = sweep_ms;
     }
 
+    static constexpr size_t kMaxSweepEvents = 2 * 8 * 64;
     Dims d_{};
     Geom<T> g_{};
     T origin_[3];
@@ -538,6 +577,14 @@ void ttcr_b200_destroy(ttcr_b200_grid* g) {
 int ttcr_b200_set_slowness(ttcr_b200_grid* g, const void* s, size_t n, int order) {
     NEED(g);
     return guard([&] { g->impl->set_slowness(s, n, order); });
+}
+int ttcr_b200_set_slowness_device(ttcr_b200_grid* g, const void* s, size_t n, int order) {
+    NEED(g);
+    return guard([&] { g->impl->set_slowness_device(s, n, order); });
+}
+int ttcr_b200_get_tt_device(ttcr_b200_grid* g, void* out, size_t slot, int order) {
+    NEED(g);
+    return guard([&] { g->impl->get_tt_device(out, slot, order); });
 }
 int ttcr_b200_get_slowness(ttcr_b200_grid* g, void* out, int order) {
     NEED(g);

@@ -200,6 +200,18 @@ class _Grid3d:
         s = np.ascontiguousarray(slowness, dtype=self.dtype).reshape(-1)   # C order == z fastest
         self._chk(self._lib.ttcr_b200_set_slowness(self._h, s.ctypes.data, s.size, _lib.ORDER_Z_FASTEST))
 
+    def set_slowness_device(self, device_ptr, n_elements):
+        """Assign slowness from a DEVICE buffer (numpy C order, grid dtype) on this grid's GPU, e.g. the
+        landing tensor of a ``torch.distributed.broadcast``: ``g.set_slowness_device(t.data_ptr(), t.numel())``."""
+        self._chk(self._lib.ttcr_b200_set_slowness_device(self._h, int(device_ptr), int(n_elements),
+                                                          _lib.ORDER_Z_FASTEST))
+
+    def get_grid_traveltimes_device(self, device_ptr, thread_no=0):
+        """Write the traveltime field (numpy C order, grid dtype) into a DEVICE buffer of nx*ny*nz elements."""
+        if thread_no >= self._n_threads:
+            raise ValueError("Thread number is larger than number of threads")
+        self._chk(self._lib.ttcr_b200_get_tt_device(self._h, int(device_ptr), int(thread_no), _lib.ORDER_Z_FASTEST))
+
     def set_velocity(self, velocity):
         """Assign velocity (rgrid.pyx:571-608)."""
         nx, ny, nz = self.shape
