@@ -31,8 +31,8 @@ def check():
         x, y, z = (np.arange(m) * 0.25 for m in shape)
         s = rng.uniform(0.3, 1.0, shape)
         res = []
-        for kernel, opts in ((1, {}), (2, {}), (2, {"tile_warps": 4, "tile_urows": 2, "tile_rows": 2}), (2, {"tile_urows": 1, "tile_rows": 8, "ctas_per_sm": 1}),
-                             (2, {"tile_urows": 2, "tile_depth": 8, "tile_rows": 1})):
+        for kernel, opts in ((1, {}), (2, {}), (2, {"tile_warps": 4, "tile_urows": 2, "tile_rows": 2, "tile_depth": 4}),
+                             (3, {}), (3, {"tile_warps": 4, "tile_rows": 2}), (3, {"tile_rows": 16, "ctas_per_sm": 1})):
             g = Grid3d(x, y, z, cell_slowness=0, tt_from_rp=False, weno=0, dtype=dtype)
             g.set_option("kernel", kernel)
             for k, v in opts.items():
@@ -59,10 +59,9 @@ def timing(sizes):
         g = Grid3d(x, x, x, cell_slowness=0, tt_from_rp=False, weno=0, dtype=np.float32)
         g.set_slowness(s)
         print(f"--- {n}^3 device bytes {g.device_bytes() / 2**30:.2f} GiB", flush=True)
-        combos = [dict(kernel=2, tile_warps=8, tile_urows=r, tile_rows=c, tile_depth=dd, ctas_per_sm=0)
-                  for r, c, dd in itertools.product((2, 1), (2, 4, 8), (4, 8))]
-        combos += [dict(kernel=2, tile_warps=4, tile_urows=r, tile_rows=4, tile_depth=4, ctas_per_sm=0) for r in (1, 2)]
-        combos += [dict(kernel=2, tile_warps=8, tile_urows=2, tile_rows=4, tile_depth=4, ctas_per_sm=o) for o in (1,)]
+        combos = [dict(kernel=3, tile_warps=w, tile_rows=c, ctas_per_sm=o) for w, c, o in itertools.product((8, 4), (2, 4, 8), (0,))]
+        combos += [dict(kernel=3, tile_warps=8, tile_rows=4, ctas_per_sm=o) for o in (1, 2, 3)]
+        combos += [dict(kernel=2, tile_warps=8, tile_urows=1, tile_rows=8, tile_depth=8, ctas_per_sm=0)]
         if n <= 256:
             combos.append(dict(kernel=1))
         for src in ([0.0, 0.0, 0.0],):
@@ -85,7 +84,7 @@ def one(n, opts):
     x, s = gradient(n)
     g = Grid3d(x, x, x, cell_slowness=0, tt_from_rp=False, weno=0, dtype=np.float32)
     g.set_slowness(s)
-    g.set_option("kernel", 2)
+    g.set_option("kernel", 3)
     for kv in opts:
         k, v = kv.split("=")
         g.set_option(k, float(v))

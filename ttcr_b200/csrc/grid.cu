@@ -21,6 +21,7 @@
 #include "../../include/ttcr_b200.h"
 #include "kernels.cuh"
 #include "sweep_tile.cuh"
+#include "sweep_tile3.cuh"
 
 namespace ttcrb200 {
 
@@ -274,7 +275,8 @@ class Grid final : public GridBase {
     void set_option(const std::string& key, double v) override {
         if (key == "tt_from_rp") ttrp_ = v != 0;
         else if (key == "kernel") {
-            if (v != TTCR_B200_KERNEL_AUTO && v != TTCR_B200_KERNEL_PLANE && v != TTCR_B200_KERNEL_TILE)
+            if (v != TTCR_B200_KERNEL_AUTO && v != TTCR_B200_KERNEL_PLANE && v != TTCR_B200_KERNEL_TILE &&
+                v != TTCR_B200_KERNEL_TILE3)
                 throw Err(TTCR_B200_ERR_INVALID, "unknown kernel id");
             kernel_ = (int)v;
         } else if (key == "tile_rows") tile_opt_.chunk = std::max(1, (int)v);
@@ -371,6 +373,12 @@ class Grid final : public GridBase {
     void launch_sweep(Slot& s, int dir, bool weno_stage, const FrozenBox& fb, int kernel) {
         const SweepView w = make_view(d_, dir);
         T* tt = s.tt[w.layout];
+        if (kernel == TTCR_B200_KERNEL_TILE3) {
+            const int nl = tile3_sweep<T>(s.tile, tile_opt_, sm_count_, w, d_, tt, slo_[w.layout], s.mask[w.layout], fb, g_.dx,
+                                         s.d_change, s.stream);
+            s.st.launches += nl; s.st.sweep_launches += nl;
+            return;
+        }
         if (kernel == TTCR_B200_KERNEL_TILE) {
             const int nl = tile_sweep<T>(s.tile, tile_opt_, sm_count_, w, d_, tt, slo_[w.layout], s.mask[w.layout], fb,
                                         g_.dx, weno_stage, s.d_change, s.stream);
@@ -394,6 +402,8 @@ class Grid final : public GridBase {
 
     int pick_kernel(bool weno_stage) const {
         if (kernel_ != TTCR_B200_KERNEL_AUTO) {
+            if (kernel_ == TTCR_B200_KERNEL_TILE3 && !tile3_supported<T>(weno_stage))
+                return tile_supported<T>(weno_stage) ? TTCR_B200_KERNEL_TILE : TTCR_B200_KERNEL_PLANE;
             if (kernel_ == TTCR_B200_KERNEL_TILE && !tile_supported<T>(weno_stage)) return TTCR_B200_KERNEL_PLANE;
             return kernel_;
         }

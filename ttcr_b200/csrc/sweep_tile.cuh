@@ -610,7 +610,8 @@ inline int tile_sweep(TileState& s, const TileOptions& o, int sm_count, const Sw
     TTCR_TILE_CASE(8, 1, 8)
     TTCR_TILE_CASE(4, 1, 4)
 #undef TTCR_TILE_CASE
-    throw std::runtime_error("tile kernel: unsupported (tile_warps, tile_urows, tile_depth) combination");
+    // not an instantiated combination: use the default shape
+    return tile_launch<T, 8, 1, 8>(s, o, sm_count, w, d, tt, slo, frozen, fb, dx, d_change, st);
 }
 
 }  // namespace ttcrb200
