@@ -44,7 +44,7 @@ def make_grid(g, kernel=None, n_threads=1):
     return grid
 
 
-@pytest.mark.parametrize("kernel", [1, 2])
+@pytest.mark.parametrize("kernel", [1, 2, 3])
 @pytest.mark.parametrize("name", golden_names())
 def test_golden(name, kernel):
     g = load_golden(name)
@@ -77,7 +77,7 @@ def _model(n, seed):
     return x, s
 
 
-@pytest.mark.parametrize("kernel", [1, 2])
+@pytest.mark.parametrize("kernel", [1, 2, 3])
 @pytest.mark.parametrize("dtype,weno,n", [(np.float32, 0, 64), (np.float32, 1, 64), (np.float64, 0, 48),
                                           (np.float64, 1, 40), (np.float32, 0, 97)])
 def test_against_oracle_seeded(oracle, kernel, dtype, weno, n):
@@ -103,7 +103,7 @@ def test_against_oracle_seeded(oracle, kernel, dtype, weno, n):
 
 
 def test_plane_and_tile_kernels_agree_bitwise():
-    """both sweep kernels execute the same Gauss-Seidel DAG with the same arithmetic"""
+    """all three sweep kernels execute the same Gauss-Seidel DAG with the same arithmetic"""
     from ttcr_b200 import Grid3d
     n = (70, 45, 83)
     rng = np.random.default_rng(3)
@@ -111,13 +111,17 @@ def test_plane_and_tile_kernels_agree_bitwise():
     x, y, z = (np.arange(m) * 0.25 for m in n)
     src = np.array([[0.1, 3.0, 2.0, 11.1]])
     out = []
-    for kernel in (1, 2):
+    for kernel, opts in ((1, {}), (2, {}), (3, {}), (2, {"tile_urows": 2, "tile_depth": 4, "tile_rows": 2}),
+                         (3, {"tile_warps": 16, "tile_rows": 4}), (3, {"tile_warps": 4, "ctas_per_sm": 1})):
         grid = Grid3d(x, y, z, cell_slowness=0, tt_from_rp=False, weno=1, dtype=np.float32)
         grid.set_option("kernel", kernel)
+        for k, v in opts.items():
+            grid.set_option(k, v)
         grid.raytrace(src, src[:, 1:], s)
         out.append((grid.get_grid_traveltimes(), grid.get_niter()))
-    assert np.array_equal(out[0][0], out[1][0])
-    assert out[0][1] == out[1][1]
+    for o in out[1:]:
+        assert np.array_equal(out[0][0], o[0])
+        assert out[0][1] == o[1]
 
 
 def test_homogeneous_analytic_config2_scaled():

@@ -59,8 +59,8 @@ def timing(sizes):
         g = Grid3d(x, x, x, cell_slowness=0, tt_from_rp=False, weno=0, dtype=np.float32)
         g.set_slowness(s)
         print(f"--- {n}^3 device bytes {g.device_bytes() / 2**30:.2f} GiB", flush=True)
-        combos = [dict(kernel=3, tile_warps=w, tile_rows=c, ctas_per_sm=o) for w, c, o in itertools.product((8, 4), (2, 4, 8), (0,))]
-        combos += [dict(kernel=3, tile_warps=8, tile_rows=4, ctas_per_sm=o) for o in (1, 2, 3)]
+        combos = [dict(kernel=3, tile_warps=w, tile_rows=c, tile_depth=8, ctas_per_sm=0) for w, c in itertools.product((8, 16), (1, 2, 4, 8))]
+        combos += [dict(kernel=3, tile_warps=8, tile_rows=c, tile_depth=4, ctas_per_sm=0) for c in (2, 4)]
         combos += [dict(kernel=2, tile_warps=8, tile_urows=1, tile_rows=8, tile_depth=8, ctas_per_sm=0)]
         if n <= 256:
             combos.append(dict(kernel=1))
@@ -88,8 +88,10 @@ def one(n, opts):
     for kv in opts:
         k, v = kv.split("=")
         g.set_option(k, float(v))
-    st = g.solve(np.array([[0.0, 0.0, 0.0]]))
-    print(st)
+    import os
+    for _ in range(int(os.environ.get("REPS", "1"))):
+        st = g.solve(np.array([[0.0, 0.0, 0.0]]))
+        print(st)
 
 
 if __name__ == "__main__":

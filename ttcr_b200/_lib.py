@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_HERE, "libttcr_b200.so")
 OK, ERR_RUNTIME, ERR_LENGTH, ERR_LOGIC, ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED = range(7)
 F64, F32 = 0, 1
 ORDER_X_FASTEST, ORDER_Z_FASTEST = 0, 1
-KERNEL_AUTO, KERNEL_PLANE, KERNEL_TILE = 0, 1, 2
+KERNEL_AUTO, KERNEL_PLANE, KERNEL_TILE, KERNEL_TILE3 = 0, 1, 2, 3
 
 # every symbol include/ttcr_b200.h declares (tests check that the library exports all of them)
 SYMBOLS = (

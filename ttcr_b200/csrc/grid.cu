@@ -407,8 +407,9 @@ class Grid final : public GridBase {
             if (kernel_ == TTCR_B200_KERNEL_TILE && !tile_supported<T>(weno_stage)) return TTCR_B200_KERNEL_PLANE;
             return kernel_;
         }
-        if (!tile_supported<T>(weno_stage)) return TTCR_B200_KERNEL_PLANE;
-        return TTCR_B200_KERNEL_TILE;
+        if (tile3_supported<T>(weno_stage)) return TTCR_B200_KERNEL_TILE3;   // fp32, first order: TMA-fed tiles
+        if (!tile_supported<T>(weno_stage)) return TTCR_B200_KERNEL_PLANE;      // WENO stage
+        return TTCR_B200_KERNEL_TILE;                                           // fp64, first order
     }
 
     // Grid3Drnfs::raytrace body (Grid3Drnfs.h:92-154) on the device

@@ -505,10 +505,10 @@ inline void tile_alloc(TileState& s, const Dims& d, size_t& bytes) {
     s.cap_tiles = ((d.ni + 3) / 4) * (d.kpad / 32);   // smallest tile height is 4 rows of u
     TCK(cudaMalloc(&s.d_order, s.cap_tiles * sizeof(int)));
     TCK(cudaMalloc(&s.d_flags, s.cap_tiles * sizeof(int)));
-    TCK(cudaMalloc(&s.d_ctrl, 2 * sizeof(int)));
+    TCK(cudaMalloc(&s.d_ctrl, 8 * sizeof(int)));
     TCK(cudaMalloc(&s.d_partial, s.cap_tiles * sizeof(double)));
     TCK(cudaMallocHost(&s.h_abort, sizeof(int)));
-    TCK(cudaMemset(s.d_ctrl, 0, 2 * sizeof(int)));
+    TCK(cudaMemset(s.d_ctrl, 0, 8 * sizeof(int)));
     *s.h_abort = 0;
     bytes += (size_t)s.cap_tiles * (2 * sizeof(int) + sizeof(double));
 }
@@ -522,9 +522,14 @@ inline void tile_free(TileState& s) {
 // called after a stream synchronize: did any tile kernel give up waiting?
 inline void tile_check(TileState& s) {
     if (s.h_abort && *s.h_abort) {
+        int info[8] = {0};
+        cudaMemcpy(info, s.d_ctrl, sizeof(info), cudaMemcpyDeviceToHost);
         *s.h_abort = 0;
-        cudaMemset(s.d_ctrl, 0, 2 * sizeof(int));
-        throw std::runtime_error("tile sweep kernel aborted: a dependency wait exceeded spin_limit");
+        cudaMemset(s.d_ctrl, 0, 8 * sizeof(int));
+        throw std::runtime_error("tile sweep kernel aborted: a dependency wait exceeded spin_limit (reason " +
+                                 std::to_string(info[1]) + ", tile " + std::to_string(info[2]) + ", chunk/step " +
+                                 std::to_string(info[3]) + ", a " + std::to_string(info[4]) + ", b " + std::to_string(info[5]) +
+                                 ", c " + std::to_string(info[6]) + ")");
     }
 }
 

@@ -1,28 +1,36 @@
-// Sweep kernel "TILE3": the tile-marching sweep of sweep_tile.cuh with warp-specialised data movement.
+// Sweep kernel "TILE3": the tile-marching sweep of sweep_tile.cuh with TMA-fed, warp-specialised data
+// movement.
 //
 // Same decomposition, dependency protocol and arithmetic as k_sweep_tile (read its header first); what
 // changes is who moves the data.  In k_sweep_tile every compute thread streams its own rows through
 // register queues, and a step of a compute warp is ~170 mostly serial instructions (address arithmetic,
 // queue rotation, five global loads) of which ~40 are the Godunov update.  Here:
 //
-//   * a LOADER warp (which is also the poller of the upstream flags) issues, per row group, one bulk
-//     asynchronous copy per stream (cp.async.bulk global -> shared, SASS UBLKCP: the 1-D form of TMA),
-//     completing on an mbarrier per chunk of 4 rows.  Streams of a tile with NU rows of u: NU+1
-//     traveltime rings (the tile's rows and row u0+NU; 40 floats per row = 32 lanes + the v0-1 / v0+32
-//     halo lanes), NU slowness rings (32 floats per row), and one ring for row u0-1.
-//   * the COMPUTE warps (one row of u each) read everything from shared memory with immediate offsets:
-//     own next row (jp), the v+1 lane of it (kp), the u+1 ring (up), slowness, the u-1 result of the
-//     neighbouring warp (exchange buffer) and the v-1 halo; one shuffle; godunov(); one predicated
-//     global store; one exchange store; one named barrier.  No global loads, no queues.
+//   * a LOADER thread issues, per chunk of 8 rows, TWO tensor-map TMA copies (cp.async.bulk.tensor.3d,
+//     SASS UTMALDG) into a shared-memory ring: a box of {40 lanes, 8 rows, NU+2 planes} of traveltimes
+//     (the tile's NU rows of u, rows u0-1 and u0+NU, and the v0-1 / v0+32 halo lanes, so every halo the
+//     tile needs arrives in the same box) and a box of {32 lanes, 8 rows, NU planes} of slowness; both
+//     complete on one mbarrier.  The loader is also the poller of the two upstream flags: it issues a
+//     chunk only when the tiles U-1 and V-1 have published the rows its halos hold.
+//     (One 1-D bulk copy per row and stream was tried first: 18 streams x 128..160 B per step made the
+//     TMA unit the bottleneck at ~70 cycles per request.)
+//   * the boxes are rectangular, so all rows of u are loaded for the SAME row range.  The Gauss-Seidel
+//     skew is kept by delaying the warps instead of the data: compute warp j (row u0+j) starts j steps
+//     after warp 0, so at every moment consecutive u still lag one step.  A warp at its local step a
+//     works on row m_first+a and reads from the ring: its own next row (jp) and the v+1 lane of it (kp),
+//     the same row of plane u+1 (up), slowness, the v-1 halo of the previous row, and the (u-1) result
+//     of the neighbouring warp from a small exchange buffer; one shuffle; godunov(); one predicated
+//     global store; one named barrier per step.  No global loads, no register queues.
 //   * the PUBLISHER warp is unchanged (bar.arrive hand-off, release fence, flag store).
 //
-// Ring rows are indexed by the LOCAL row index l of a u row (the step at which that row of u works on
-// it): row i of the tile at step s is on local index s; it reads local s+1 of its own ring (jp, kp) and of
-// ring i+1 (up), slowness local s, and the v-1 halo of local s-1.  The loader numbers its row groups
-// G = l + 1 (group 0 is local -1, needed by the v-1 halo of step 0); slot = G mod 16.
+// Ring geometry: NCH chunk slots of C = 8 rows.  Row group G (= local row + 1; group 0 is local row -1,
+// needed by the v-1 halo of step 0) lives in chunk slot (G / 8) % NCH at box row G % 8 (7 - G % 8 when the
+// sweep runs the row axis downwards, since a box arrives in memory order; likewise for planes and lanes).
 //
-// fp32 only (fp64 rings would need opt-in shared memory); other types use k_sweep_tile.
+// fp32 only; other types use k_sweep_tile.
 #pragma once
+#include <cuda.h>
+
 #include "sweep_tile.cuh"
 
 namespace ttcrb200 {
@@ -45,38 +53,57 @@ __device__ __forceinline__ int mbar_test(unsigned a, unsigned parity) {
                  : "memory");
     return ok;
 }
-// global -> shared bulk copy (bytes multiple of 16, both addresses 16-byte aligned), completing on an mbarrier
-__device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned mbar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-                 "l"(src), "r"(bytes), "r"(mbar)
-                 : "memory");
+// 3-D tensor-map TMA load: box at element coordinates (x, y, z) -> shared, completing on an mbarrier
+__device__ __forceinline__ void tma_load_3d(unsigned dst, const CUtensorMap* map, int x, int y, int z, unsigned mbar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst),
+        "l"(map), "r"(x), "r"(y), "r"(z), "r"(mbar)
+        : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ float lds_f(unsigned a) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_f(unsigned a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
 
-template <int NW>
-struct Tile3Smem {
-    static constexpr int RING = 16;   // row slots per ring
-    static constexpr int TW = 40;     // floats per traveltime ring row: 4 + 32 + 4
-    float T[NW + 1][RING][TW];        // ring i: plane u0+i (old values)
-    float Tlo[RING][TW];              // plane u0-1 (new values of tile U-1)
-    float S[NW][RING][32];
-    float xnew[2][NW][32];
-    unsigned long long full[4];       // one mbarrier per chunk slot
+struct Tile3Geom {
+    static constexpr int C = 8;      // rows per chunk (one TMA box)
+    static constexpr int TW = 40;    // floats per traveltime row: 4 + 32 + 4
 };
 
-template <int NW>
-__global__ void __launch_bounds__((NW + 2) * 32) k_sweep_tile3(TileParams p, float* __restrict__ tt, const float* __restrict__ slo,
-                                                              const uint32_t* __restrict__ frozen, float dx) {
-    using SM = Tile3Smem<NW>;
-    constexpr int RING = SM::RING, TW = SM::TW;
-    constexpr int C = 4, NCH = RING / C;          // rows per mbarrier chunk, chunk slots
+template <int NW, int NCH>
+struct Tile3Layout {
+    static constexpr int C = Tile3Geom::C, TW = Tile3Geom::TW;
+    static constexpr int TROW = TW * 4, SROW = 32 * 4;               // bytes per ring row
+    static constexpr int TPL = C * TROW, SPL = C * SROW;             // bytes per plane of a box
+    static constexpr int CHB_T = (NW + 1) * TPL, CHB_S = NW * SPL;   // bytes per chunk slot (one box)
+    static constexpr int HC = 2, HN = 8;                             // halo plane u0-1: HN chunk slots of HC rows
+    static constexpr int CHB_H = HC * SROW;                          // bytes per halo chunk (32 lanes x HC rows)
+    static constexpr int OFF_T = 0;
+    static constexpr int OFF_S = OFF_T + NCH * CHB_T;
+    static constexpr int OFF_H = OFF_S + NCH * CHB_S;
+    static constexpr int OFF_X = OFF_H + HN * CHB_H;                 // exchange buffer: 2 x NW x 32 floats
+    static constexpr int OFF_BAR = OFF_X + 2 * NW * 32 * 4;          // NCH + HN mbarriers
+    static constexpr int BYTES = OFF_BAR + (NCH + HN) * 8;
+    static_assert(CHB_H % 128 == 0, "TMA destinations must stay 128-byte aligned");
+    static_assert(CHB_T % 128 == 0 && CHB_S % 128 == 0, "TMA destinations must stay 128-byte aligned");
+};
+
+template <int NW, int NCH>
+__global__ void __launch_bounds__((NW + 2) * 32) k_sweep_tile3(const __grid_constant__ CUtensorMap tmT,
+                                                              const __grid_constant__ CUtensorMap tmS,
+                                                              const __grid_constant__ CUtensorMap tmH, TileParams p,
+                                                              float* __restrict__ tt, const uint32_t* __restrict__ frozen,
+                                                              float dx) {
+    using L = Tile3Layout<NW, NCH>;
+    constexpr int C = L::C;
     constexpr int NU = NW, NC = NW * 32, NP = (NW + 1) * 32;
-    constexpr int TROW = TW * 4, SROW = 32 * 4;   // bytes per ring row
-    static_assert(NCH == 4, "parity arithmetic assumes 4 chunk slots of 4 rows");
-    static_assert(NW + RING + 8 <= GUARD, "guard rows too few");
-    static_assert(2 * NW + 2 <= 32, "one loader lane per stream");
-    __shared__ __align__(128) SM sm;
+    static_assert(NW + C + 8 <= GUARD, "guard rows too few");
+    static_assert(C * NCH - 6 - NW - 2 >= 1, "ring too shallow: the loader could never run ahead of the compute warps");
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ double sred[NW];
     __shared__ int sm_tile;
     __shared__ volatile int sm_pubseq, sm_abort, sm_step_done;
@@ -84,7 +111,10 @@ __global__ void __launch_bounds__((NW + 2) * 32) k_sweep_tile3(TileParams p, flo
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const SweepView& w = p.w;
     const float MAXV = FLT_MAX;
-    const unsigned a_full = (unsigned)__cvta_generic_to_shared(&sm.full[0]);
+    const unsigned sbase = (unsigned)__cvta_generic_to_shared(smem_raw);
+    const unsigned a_full = sbase + L::OFF_BAR;
+    const unsigned a_fullh = a_full + 8 * NCH;
+    constexpr int HC = L::HC, HN = L::HN;
     bool first_tile = true;
 
     for (;;) {
@@ -93,8 +123,8 @@ __global__ void __launch_bounds__((NW + 2) * 32) k_sweep_tile3(TileParams p, flo
             const int ab = *((volatile int*)&p.ctrl[1]);
             sm_tile = (ab || t >= p.ntiles) ? -1 : t;
             sm_pubseq = 0; sm_abort = 0; sm_step_done = -1;
-            // fresh barriers for every tile: chunk c of a tile uses slot c % 4 with parity (c / 4) & 1
-            for (int c = 0; c < NCH; ++c) {
+            // fresh barriers for every tile: chunk c uses slot c % NCH with parity (c / NCH) & 1
+            for (int c = 0; c < NCH + HN; ++c) {
                 if (!first_tile) mbar_inval(a_full + 8 * c);
                 mbar_init(a_full + 8 * c, 1);
             }
@@ -109,11 +139,9 @@ __global__ void __launch_bounds__((NW + 2) * 32) k_sweep_tile3(TileParams p, flo
         const int u0 = U * NU, v0 = V * 32;
         const int va = max(v0, w.vlo), vb = min(v0 + 32, w.vhi);
         const int m_first = va - w.joff;
-        const int nrows = (vb - va) + w.nj - 1;
-        const int nsteps = nrows + NU - 1;
-        const int ngroups16 = (nsteps + RING - 1) / RING;     // compute steps are padded to a multiple of RING
-        const int nload = ngroups16 * RING + 4;               // row groups the loader delivers (a multiple of C)
-        const int nchunks = nload / C;
+        const int nrows = (vb - va) + w.nj - 1;                // local rows 0 .. nrows-1
+        const int nglobal = nrows + NU - 1;                    // steps of the tile (warp j runs steps j .. j+nrows-1)
+        const int nchunks = (nrows + 2 + C - 1) / C;           // groups 0 .. nrows+1
         const bool has_u = U > 0, has_v = V > 0;
         const bool has_right = v0 + 32 < w.vhi;
         const int va_p = max(v0 - 32, w.vlo);
@@ -122,7 +150,6 @@ __global__ void __launch_bounds__((NW + 2) * 32) k_sweep_tile3(TileParams p, flo
         const int chunk = p.chunk;
         const int nch = (nrows - 1) / chunk;
         const int ulast = w.nu - 1;
-        const int nexist = min(NU, ulast - u0 + 1);           // rows of the tile that exist
         if (p.trace && threadIdx.x == 0) {
             p.trace[tile * 8 + 0] = gtime();
             unsigned smid;
@@ -131,80 +158,93 @@ __global__ void __launch_bounds__((NW + 2) * 32) k_sweep_tile3(TileParams p, flo
         }
 
         if (warp == NW) {
-            // ================= loader (and poller) =================
-            // lane j owns stream j:  [0, NU]  traveltime ring j (plane u0+j);  NU+1  plane u0-1;
-            //                        [NU+2, 2NU+2)  slowness ring j-NU-2
-            const int j = lane;
-            const bool isT = j <= NU, isLo = j == NU + 1, isS = j >= NU + 2 && j < 2 * NU + 2;
-            const int ring_i = isT ? j : (isS ? j - NU - 2 : 0);
-            const int plane = isLo ? u0 - 1 : u0 + ring_i;
-            bool active = (isT || isS) ? plane <= ulast : (isLo && has_u);
-            // first lane of the copied segment in memory order: traveltime rows carry 4 halo lanes on each side
-            const int halo = (isT || isLo) ? 4 : 0;
-            const long long seg = w.rk ? -(long long)(v0 + 31 + halo) : (long long)(v0 - halo);
-            const int row0 = (isLo ? m_first : m_first - ring_i) - 1;  // absolute row of group 0 (local index -1)
-            const float* src = ((isS) ? slo : (const float*)tt) + w.base + (long long)plane * w.su + seg +
-                               (long long)row0 * w.sm;
-            const unsigned bytes = (isT || isLo) ? TROW : SROW;
-            unsigned dst0;
-            if (isT) dst0 = (unsigned)__cvta_generic_to_shared(&sm.T[ring_i][0][0]);
-            else if (isLo) dst0 = (unsigned)__cvta_generic_to_shared(&sm.Tlo[0][0]);
-            else dst0 = (unsigned)__cvta_generic_to_shared(&sm.S[ring_i][0][0]);
-            if (!active) src = tt;   // never dereferenced
-            // bytes landing per local row, all streams
-            const unsigned group_bytes = (unsigned)(min(NU + 1, ulast - u0 + 1) * TROW + (has_u ? TROW : 0) + nexist * SROW);
-            const int* fu = &p.flags[has_u ? tile - p.nV : tile];
-            const int* fv = &p.flags[has_v ? tile - 1 : tile];
-            int ku = has_u ? 0 : (1 << 30), kv = has_v ? 0 : (1 << 30);
-            int dead = 0;
-            for (int c = 0; c < nchunks && !dead; ++c) {
-                const int g0 = c * C;
-                if (lane == 0) {
-                    long long spins = 0;
-                    // (a) the slots of this chunk hold groups G-RING, last read at step G-RING (its v-1 halo)
-                    // (b) upstream tiles must have finished what the halo lanes / row u0-1 of these rows hold:
-                    //     group G is absolute row m_first-1+G of row u0-1, and at most row count G+dmf of tile V-1
-                    const int need_done = g0 + C - 1 - RING;
-                    const int need_u = min(g0 + C - 1, nrows);
-                    const int need_v = min(g0 + C - 1 + dmf, nrows_p);
-                    for (;;) {
-                        bool ok = sm_step_done >= need_done;
-                        if (ok && ku < need_u) {
-                            const int k2 = ld_relaxed_gpu(fu);
-                            if (k2 > ku) { ku = k2; fence_acq_rel_gpu(); fence_proxy_async(); }
-                            ok = ku >= need_u;
-                        }
+            // ================= loader (and poller): one thread =================
+            if (lane == 0) {
+                // box origins in MEMORY coordinates (x: lane k, y: row within the padded plane, z: plane i)
+                const int xT = w.rk ? p.d.kpad - 36 - v0 : v0 - 4;
+                const int xS = w.rk ? p.d.kpad - 32 - v0 : v0;
+                const int zT = w.ri ? p.d.ni - 1 - (u0 + NU) : u0;          // planes u0 .. u0+NU
+                const int zS = w.ri ? p.d.ni - 1 - (u0 + NU - 1) : u0;
+                const int zH = w.ri ? p.d.ni - 1 - (u0 - 1) : u0 - 1;       // plane u0-1
+                const int* fu = &p.flags[has_u ? tile - p.nV : tile];
+                const int* fv = &p.flags[has_v ? tile - 1 : tile];
+                int ku = has_u ? 0 : (1 << 30), kv = has_v ? 0 : (1 << 30);
+                const int nhch = has_u ? (nrows + HC - 1) / HC : 0;         // halo chunks: local rows 0 .. nrows-1
+                int c = 0, hc = 0;
+                bool dead = false;
+                long long t0 = clock64();
+                while ((c < nchunks || hc < nhch) && !dead) {
+                    bool progress = false;
+                    const int done = sm_step_done;
+                    // ---- main chunk c: groups 8c .. 8c+7 = local rows 8c-1 .. 8c+6 of planes u0 .. u0+NU (old values,
+                    //      except the v0-1 halo lanes, which hold new values of tile V-1: row a needs its count a+dmf+1)
+                    if (c < nchunks) {
+                        const int g0 = c * C;
+                        // slot reuse: chunk c-NCH held local rows up to g0-C*NCH+6, last read (v-1 halo by the last warp)
+                        // one step after that warp worked on the row: global step row + 1 + (NU-1)
+                        bool ok = done >= g0 - C * NCH + 6 + NU;
+                        const int need_v = min(g0 + C - 1 + dmf, nrows_p);
                         if (ok && kv < need_v) {
                             const int k2 = ld_relaxed_gpu(fv);
                             if (k2 > kv) { kv = k2; fence_acq_rel_gpu(); fence_proxy_async(); }
                             ok = kv >= need_v;
                         }
-                        if (ok) break;
-                        if (sm_abort) { dead = 1; break; }
-                        if (++spins > p.spin_limit) {
-                            atomicExch(&p.ctrl[1], 1);
+                        if (ok) {
+                            const int mlo = m_first - 1 + g0;   // oriented rows mlo .. mlo+7 -> memory rows (ascending)
+                            const int y = GUARD + (w.rj ? (w.nm - 1) - (mlo + C - 1) : mlo);
+                            const unsigned mb = a_full + 8 * (c % NCH);
+                            const unsigned slot = (unsigned)(c % NCH);
+                            mbar_expect_tx(mb, L::CHB_T + L::CHB_S);
+                            tma_load_3d(sbase + L::OFF_T + slot * L::CHB_T, &tmT, xT, y, zT, mb);
+                            tma_load_3d(sbase + L::OFF_S + slot * L::CHB_S, &tmS, xS, y, zS, mb);
+                            ++c;
+                            progress = true;
+                        }
+                    }
+                    // ---- halo chunk hc: local rows 2hc, 2hc+1 of plane u0-1 (new values of tile U-1: needs its count 2hc+2)
+                    if (hc < nhch) {
+                        const int a0 = hc * HC;
+                        bool ok = done >= a0 + HC - 1 - HC * HN;            // row a is read at global step a (warp 0) only
+                        const int need_u = min(a0 + HC, nrows);
+                        if (ok && ku < need_u) {
+                            const int k2 = ld_relaxed_gpu(fu);
+                            if (k2 > ku) { ku = k2; fence_acq_rel_gpu(); fence_proxy_async(); }
+                            ok = ku >= need_u;
+                        }
+                        if (ok) {
+                            const int mlo = m_first + a0;
+                            const int y = GUARD + (w.rj ? (w.nm - 1) - (mlo + HC - 1) : mlo);
+                            const unsigned mb = a_fullh + 8 * (hc % HN);
+                            mbar_expect_tx(mb, L::CHB_H);
+                            tma_load_3d(sbase + L::OFF_H + (unsigned)(hc % HN) * L::CHB_H, &tmH, xS, y, zH, mb);
+                            ++hc;
+                            progress = true;
+                        }
+                    }
+                    if (progress) {
+                        t0 = clock64();
+                    } else {
+                        if (sm_abort) { dead = true; break; }
+                        if (clock64() - t0 > (p.spin_limit << 9)) {
+                            if (atomicCAS(&p.ctrl[1], 0, 10) == 0) {
+                                p.ctrl[2] = tile; p.ctrl[3] = c; p.ctrl[4] = sm_step_done; p.ctrl[5] = ku; p.ctrl[6] = kv;
+                            }
                             sm_abort = 1;
-                            dead = 1;
+                            dead = true;
                             break;
                         }
                     }
-                    if (!dead) mbar_expect_tx(a_full + 8 * (c & 3), group_bytes * C);
                 }
-                dead = __shfl_sync(0xffffffffu, dead, 0);
-                if (!dead && active) {
-                    const unsigned mb = a_full + 8 * (c & 3);
-#pragma unroll
-                    for (int r = 0; r < C; ++r) {
-                        const int g = g0 + r;
-                        bulk_g2s(dst0 + (unsigned)((g & (RING - 1)) * bytes), src + (long long)g * w.sm, bytes, mb);
+                // every copy must have landed before the barriers are re-initialised for the next tile
+                if (!dead) {
+                    for (int cc = max(0, nchunks - NCH); cc < nchunks; ++cc) {
+                        const long long t1 = clock64();
+                        while (!mbar_test(a_full + 8 * (cc % NCH), (cc / NCH) & 1) && clock64() - t1 < (p.spin_limit << 9)) {}
                     }
-                }
-            }
-            // every copy must have landed before the barriers are re-initialised for the next tile
-            if (lane == 0 && !dead) {
-                for (int c = max(0, nchunks - NCH); c < nchunks; ++c) {
-                    long long spins = 0;
-                    while (!mbar_test(a_full + 8 * (c & 3), (c >> 2) & 1) && ++spins < (p.spin_limit >> 6)) {}
+                    for (int cc = max(0, nhch - HN); cc < nhch; ++cc) {
+                        const long long t1 = clock64();
+                        while (!mbar_test(a_fullh + 8 * (cc % HN), (cc / HN) & 1) && clock64() - t1 < (p.spin_limit << 9)) {}
+                    }
                 }
             }
             __syncwarp();
@@ -220,7 +260,7 @@ __global__ void __launch_bounds__((NW + 2) * 32) k_sweep_tile3(TileParams p, flo
                 __syncwarp();
             }
         } else {
-            // ================= compute warps: warp wq owns row u0 + wq =================
+            // ================= compute warps: warp wq owns row u0 + wq and runs wq steps behind warp 0 =====
             const int wq = warp;
             const int u = u0 + wq;
             const int v = v0 + lane;
@@ -233,23 +273,29 @@ __global__ void __launch_bounds__((NW + 2) * 32) k_sweep_tile3(TileParams p, flo
             const int sm32 = pin((int)w.sm);
             const int nj = pin(w.nj);
             const int chunk_mask = pin(chunk - 1);
-            // column of this lane in a ring row (rows are in memory order: reversed sweeps run right to left)
-            const int col = w.rk ? 35 - lane : 4 + lane;
-            const int dcol = w.rk ? -1 : 1;                  // column of lane v+1 relative to col
-            const unsigned aT = pin((int)__cvta_generic_to_shared(&sm.T[wq][0][col]));
-            const unsigned aTvp = pin((int)__cvta_generic_to_shared(&sm.T[wq][0][col + dcol]));
-            const unsigned aTvm = pin((int)__cvta_generic_to_shared(&sm.T[wq][0][col - dcol]));
-            const unsigned aTup = pin((int)__cvta_generic_to_shared(&sm.T[wq + 1][0][col]));
-            const unsigned aTlo = pin((int)__cvta_generic_to_shared(&sm.Tlo[0][col]));
-            const unsigned aS = pin((int)__cvta_generic_to_shared(&sm.S[wq][0][w.rk ? 31 - lane : lane]));
-            const unsigned aX = pin((int)__cvta_generic_to_shared(&sm.xnew[0][wq][lane]));
+            // position of this thread inside a box (boxes arrive in memory order)
+            const int col = w.rk ? 35 - lane : 4 + lane;     // lane column in a 40-float row
+            const int dcol = w.rk ? -1 : 1;                  // column step towards lane v+1
+            const int pT = w.ri ? NU - wq : wq;              // plane slot of row u0+wq in the traveltime box (planes u0 .. u0+NU)
+            const int dpl = w.ri ? -1 : 1;                   // plane step towards u+1
+            const int pS = w.ri ? NU - 1 - wq : wq;
+            const unsigned bT = sbase + L::OFF_T + pT * L::TPL + col * 4;
+            const unsigned bTvp = bT + dcol * 4, bTvm = bT - dcol * 4;
+            const unsigned bTup = bT + dpl * L::TPL;         // plane u+1
+            const unsigned bH = sbase + L::OFF_H + (w.rk ? 31 - lane : lane) * 4;   // plane u0-1 ring (32-lane rows)
+            const int hflip = w.rj ? HC - 1 : 0;
+            const unsigned bS = sbase + L::OFF_S + pS * L::SPL + (w.rk ? 31 - lane : lane) * 4;
+            const unsigned aX = sbase + L::OFF_X + (wq * 32 + lane) * 4;
             constexpr int XS = NW * 32 * 4, XW = 32 * 4;
-            // global store pointer: row of step 0 plus a running element offset
-            const int row0 = m_first - wq;
-            const long long e0 = w.base + (long long)min(u, ulast) * w.su + (long long)v * w.sv + (long long)row0 * w.sm;
+            const int rflip = w.rj ? C - 1 : 0;
+            // ring offsets of row group G
+            auto offT = [&](int G) -> unsigned { return (unsigned)(((G >> 3) % NCH) * L::CHB_T + ((G & 7) ^ rflip) * L::TROW); };
+            auto offS = [&](int G) -> unsigned { return (unsigned)(((G >> 3) % NCH) * L::CHB_S + ((G & 7) ^ rflip) * L::SROW); };
+            // global store pointer of local row 0 plus a running element offset
+            const long long e0 = w.base + (long long)min(u, ulast) * w.su + (long long)v * w.sv + (long long)m_first * w.sm;
             float* const stb = pin_ptr(tt + e0);
             int off = pin(0);
-            const int jo0 = (u_ok && v_ok) ? row0 - v + w.joff : -(1 << 30);
+            const int jo0 = (u_ok && v_ok) ? m_first - v + w.joff : -(1 << 30);
             bool any_fz;
             {
                 const int it = w.ri ? ulast - min(u, ulast) : min(u, ulast);
@@ -257,103 +303,96 @@ __global__ void __launch_bounds__((NW + 2) * 32) k_sweep_tile3(TileParams p, flo
                 const int ka = w.rk ? p.d.nk - 1 - kb0 : ka0, kb = w.rk ? p.d.nk - 1 - ka0 : kb0;
                 any_fz = it >= p.fb.ilo && it <= p.fb.ihi && !(kb < p.fb.klo || ka > p.fb.khi);
             }
-            auto wait_chunk = [&](int c) {
-                const unsigned a = a_full + 8 * (c & 3), par = (c >> 2) & 1;
-                long long spins = 0;
+            int gstep = 0;                                   // global step counter of this thread
+            auto wait_bar = [&](unsigned a, unsigned par, int why) {
+                if (mbar_test(a, par)) return;
+                const long long t0 = clock64();
                 while (!mbar_test(a, par)) {   // each attempt suspends the thread for a bounded time
                     if (sm_abort) break;
-                    if (++spins > (p.spin_limit >> 6)) {
-                        atomicExch(&p.ctrl[1], 1);
+                    if (clock64() - t0 > (p.spin_limit << 9)) {   // ~1 s at the default spin_limit
+                        if (atomicCAS(&p.ctrl[1], 0, why) == 0) { p.ctrl[2] = tile; p.ctrl[3] = (int)a; p.ctrl[4] = gstep; p.ctrl[5] = wq; p.ctrl[6] = sm_step_done; }
                         sm_abort = 1;
                         break;
                     }
                 }
             };
-
-            // ---- prologue: groups 0..3 (local -1..2) have landed; old value of local row 0
-            wait_chunk(0);
-            float told = lds_at<TROW>(aT, 0.f);
-            float t_prev = MAXV;
-            float acc = 0.f;
-            bar_compute<NC>();
-            if (p.trace && threadIdx.x == 0) p.trace[tile * 8 + 1] = gtime();
+            auto wait_chunk = [&](int c) { wait_bar(a_full + 8 * (c % NCH), (c / NCH) & 1, 20); };
             int dead = 0;
             int narrive = 0;
+            // one barrier per global step, then the hand-off bookkeeping of that step
+            auto end_step = [&]() {
+                dead |= bar_compute_or<NC>(sm_abort);
+                if (threadIdx.x == 0) sm_step_done = gstep;
+                const int rd = gstep - NU + 2;
+                if (rd > 0 && rd < nrows && (rd & chunk_mask) == 0) {
+                    if (narrive >= 2) {
+                        long long spins = 0;
+                        while (sm_pubseq < narrive - 1 && !sm_abort && ++spins < p.spin_limit) {}
+                    }
+                    bar_pub_arrive<NP>(2 + (narrive & 1));
+                    ++narrive;
+                }
+                ++gstep;
+            };
 
-            for (int g = 0; g < ngroups16 && !dead; ++g) {
+            // ---- warps start one step apart
+            for (int k = 0; k < wq && !dead; ++k) end_step();
+            wait_chunk(0);                                   // groups 0..7 = local rows -1..6
+            float told = lds_f(bT + offT(1));                // old value of local row 0
+            float t_prev = MAXV;
+            float acc = 0.f;
+            if (p.trace && threadIdx.x == 0) p.trace[tile * 8 + 1] = gtime();
+
+            for (int a = 0; a < nrows && !dead; ++a) {
                 if (p.trace && threadIdx.x == 0) {
-                    if (g == ngroups16 / 4) p.trace[tile * 8 + 2] = gtime();
-                    if (g == ngroups16 / 2) p.trace[tile * 8 + 3] = gtime();
-                    if (g == (3 * ngroups16) / 4) p.trace[tile * 8 + 4] = gtime();
+                    if (a == nrows / 4) p.trace[tile * 8 + 2] = gtime();
+                    if (a == nrows / 2) p.trace[tile * 8 + 3] = gtime();
+                    if (a == (3 * nrows) / 4) p.trace[tile * 8 + 4] = gtime();
                 }
-#pragma unroll
-                for (int q = 0; q < RING; ++q) {
-                    const int s = g * RING + q;
-                    // group s+2 (local s+1) is needed from here on: entering a new chunk?
-                    if (((q + 2) & (C - 1)) == 0) wait_chunk((s + 2) >> 2);
-                    const int s1 = (q + 2) & (RING - 1), s0 = (q + 1) & (RING - 1), sm1 = q;   // slots of local s+1, s, s-1
-                    float jp, kp, up, sl, um, kmh;
-                    // (switch on q is resolved at compile time: q is an unrolled loop index)
-#define TTCR_LD(dstv, base, slot, rowb)                                                                       \
-    switch (slot) {                                                                                            \
-        case 0: dstv = lds_at<0 * rowb>(base, 0.f); break;   case 1: dstv = lds_at<1 * rowb>(base, 0.f); break;   \
-        case 2: dstv = lds_at<2 * rowb>(base, 0.f); break;   case 3: dstv = lds_at<3 * rowb>(base, 0.f); break;   \
-        case 4: dstv = lds_at<4 * rowb>(base, 0.f); break;   case 5: dstv = lds_at<5 * rowb>(base, 0.f); break;   \
-        case 6: dstv = lds_at<6 * rowb>(base, 0.f); break;   case 7: dstv = lds_at<7 * rowb>(base, 0.f); break;   \
-        case 8: dstv = lds_at<8 * rowb>(base, 0.f); break;   case 9: dstv = lds_at<9 * rowb>(base, 0.f); break;   \
-        case 10: dstv = lds_at<10 * rowb>(base, 0.f); break; case 11: dstv = lds_at<11 * rowb>(base, 0.f); break; \
-        case 12: dstv = lds_at<12 * rowb>(base, 0.f); break; case 13: dstv = lds_at<13 * rowb>(base, 0.f); break; \
-        case 14: dstv = lds_at<14 * rowb>(base, 0.f); break; default: dstv = lds_at<15 * rowb>(base, 0.f); break; \
-    }
-                    TTCR_LD(jp, aT, s1, TROW)
-                    TTCR_LD(kp, aTvp, s1, TROW)
-                    TTCR_LD(up, aTup, s1, TROW)
-                    TTCR_LD(sl, aS, s0, SROW)
-                    TTCR_LD(kmh, aTvm, sm1, TROW)
-                    if (first_w) { TTCR_LD(um, aTlo, s0, TROW) }
-                    else um = (q & 1) ? lds_at<-XW>(aX, 0.f) : lds_at<XS - XW>(aX, 0.f);
-#undef TTCR_LD
-                    if (!has_um) um = MAXV;
-                    if (!has_up) up = MAXV;
-                    if (lane_hi && !has_right) kp = MAXV;
-                    float km = __shfl_up_sync(0xffffffffu, t_prev, 1);
-                    if (lane_lo) km = has_v ? kmh : MAXV;
-                    const float t = godunov(tmin(km, kp), tmin(t_prev, jp), tmin(um, up), sl * dx);
-                    bool valid = (unsigned)(jo0 + s) < (unsigned)nj;
-                    if (any_fz) {
-                        if (valid) {
-                            const long long e = (long long)(stb + off - tt);
-                            if ((frozen[e >> 5] >> (e & 31)) & 1u) valid = false;
-                        }
-                    }
-                    float tnew = told;
-                    if (valid && t < told) {
-                        tnew = t;
-                        st_stream(stb + off, t);
-                        acc += told - t;
-                    }
-                    t_prev = tnew;
-                    told = jp;
-                    off = pin(off + sm32);
-                    if (q & 1) sts_at<XS>(aX, tnew); else sts_at<0>(aX, tnew);
-                    if (q == RING - 1)
-                        dead = bar_compute_or<NC>(sm_abort);
-                    else
-                        bar_compute<NC>();
-                    if (threadIdx.x == 0) sm_step_done = s;
-                    {
-                        const int rd = s - NU + 2;
-                        if (rd > 0 && rd < nrows && (rd & chunk_mask) == 0) {
-                            if (narrive >= 2) {
-                                long long spins = 0;
-                                while (sm_pubseq < narrive - 1 && !sm_abort && ++spins < p.spin_limit) {}
-                            }
-                            bar_pub_arrive<NP>(2 + (narrive & 1));
-                            ++narrive;
-                        }
+                // group a+2 (local row a+1) is read from here on: entering a new chunk?
+                if (((a + 2) & (C - 1)) == 0) wait_chunk((a + 2) >> 3);
+                const unsigned o1 = offT(a + 2), o0 = offT(a + 1), om = offT(a), os = offS(a + 1);
+                const float jp = lds_f(bT + o1);             // old (u, a+1, v)
+                float kp = lds_f(bTvp + o1);                 // old (u, a+1, v+1)
+                float up = lds_f(bTup + o0);                 // old (u+1, a, v)
+                const float sl = lds_f(bS + os);
+                float um;
+                if (first_w) {                               // new (u0-1, a, v): halo of tile U-1
+                    um = MAXV;
+                    if (has_u) {
+                        const int hcx = a / HC;
+                        if ((a % HC) == 0) wait_bar(a_fullh + 8 * (hcx % HN), (hcx / HN) & 1, 21);
+                        um = lds_f(bH + (unsigned)((hcx % HN) * L::CHB_H + (((a % HC) ^ hflip)) * L::SROW));
                     }
                 }
+                else um = lds_f(aX - XW + ((gstep & 1) ? 0 : XS));   // result of warp wq-1 at the previous step
+                if (!has_um) um = MAXV;
+                if (!has_up) up = MAXV;
+                if (lane_hi && !has_right) kp = MAXV;
+                float km = __shfl_up_sync(0xffffffffu, t_prev, 1);
+                if (lane_lo) km = has_v ? lds_f(bTvm + om) : MAXV;   // new (u, a-1, v0-1): halo of tile V-1
+                const float t = godunov(tmin(km, kp), tmin(t_prev, jp), tmin(um, up), sl * dx);
+                bool valid = (unsigned)(jo0 + a) < (unsigned)nj;
+                if (any_fz) {
+                    if (valid) {
+                        const long long e = (long long)(stb + off - tt);
+                        if ((frozen[e >> 5] >> (e & 31)) & 1u) valid = false;
+                    }
+                }
+                float tnew = told;
+                if (valid && t < told) {
+                    tnew = t;
+                    st_stream(stb + off, t);
+                    acc += told - t;
+                }
+                t_prev = tnew;
+                told = jp;
+                off = pin(off + sm32);
+                sts_f(aX + ((gstep & 1) ? XS : 0), tnew);
+                end_step();
             }
+            // ---- trailing steps of the warps that started earlier, then any arrivals skipped by an abort
+            while (gstep < nglobal && !dead) end_step();
             for (; narrive <= nch; ++narrive) {
                 if (narrive >= 2) {
                     long long spins = 0;
@@ -378,10 +417,42 @@ __global__ void __launch_bounds__((NW + 2) * 32) k_sweep_tile3(TileParams p, flo
     }
 }
 
-template <int NW>
+// ---- host side -----------------------------------------------------------------------------------
+typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                        const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                        CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline PFN_tmapEncodeTiled tmap_encoder() {
+    static PFN_tmapEncodeTiled fn = nullptr;
+    if (!fn) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        TCK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qr));
+        if (!ptr || qr != cudaDriverEntryPointSuccess) throw std::runtime_error("cuTensorMapEncodeTiled is not available");
+        fn = (PFN_tmapEncodeTiled)ptr;
+    }
+    return fn;
+}
+
+// 3-D map over a sheared layout array: dims (kpad lanes, qs rows, ni planes), box (bw lanes, br rows, bp planes)
+inline CUtensorMap make_tile3_map(const void* base, const Dims& d, int bw, int br, int bp) {
+    CUtensorMap m;
+    const cuuint64_t gdim[3] = {(cuuint64_t)d.kpad, (cuuint64_t)d.qs, (cuuint64_t)d.ni};
+    const cuuint64_t gstr[2] = {(cuuint64_t)d.kpad * 4, (cuuint64_t)d.kpad * d.qs * 4};
+    const cuuint32_t box[3] = {(cuuint32_t)bw, (cuuint32_t)br, (cuuint32_t)bp};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult r = tmap_encoder()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base), gdim, gstr, box, estr,
+                                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) throw std::runtime_error("cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
+    return m;
+}
+
+template <int NW, int NCH>
 inline int tile3_launch(TileState& s, const TileOptions& o, int sm_count, const SweepView& w, const Dims& d, float* tt,
                         const float* slo, const uint32_t* frozen, const FrozenBox& fb, float dx, double* d_change,
                         cudaStream_t st) {
+    using L = Tile3Layout<NW, NCH>;
     constexpr int NU = NW;
     TileParams p;
     p.w = w; p.d = d; p.fb = fb;
@@ -399,7 +470,7 @@ inline int tile3_launch(TileState& s, const TileOptions& o, int sm_count, const 
     const int key = 3000000 + NU * 1000 + p.chunk;
     if (s.order_key != key || s.ntiles != p.ntiles) {
         std::vector<std::pair<long long, int>> k(p.ntiles);
-        const long long lag_u = NU + 12 + p.chunk + 4;
+        const long long lag_u = NU + Tile3Geom::C + p.chunk + 4;
         for (int U = 0; U < p.nU; ++U)
             for (int V = 0; V < p.nV; ++V) {
                 const int va = std::max(V * 32, w.vlo);
@@ -413,17 +484,31 @@ inline int tile3_launch(TileState& s, const TileOptions& o, int sm_count, const 
         s.order_key = key;
         s.ntiles = p.ntiles;
     }
+    // tensor maps are cached per (array, box shape)
+    struct MapKey { const void* a; int bw, br, bp, kpad, qs, ni; CUtensorMap m; };
+    static thread_local std::vector<MapKey> cache;
+    auto get_map = [&](const void* a, int bw, int br, int bp) -> CUtensorMap {
+        for (auto& e : cache)
+            if (e.a == a && e.bw == bw && e.br == br && e.bp == bp && e.kpad == d.kpad && e.qs == d.qs && e.ni == d.ni) return e.m;
+        if (cache.size() > 96) cache.clear();
+        cache.push_back({a, bw, br, bp, d.kpad, d.qs, d.ni, make_tile3_map(a, d, bw, br, bp)});
+        return cache.back().m;
+    };
+    const CUtensorMap tmT = get_map(tt, Tile3Geom::TW, Tile3Geom::C, NU + 1);
+    const CUtensorMap tmS = get_map(slo, 32, Tile3Geom::C, NU);
+    const CUtensorMap tmH = get_map(tt, 32, L::HC, 1);
     TCK(cudaMemsetAsync(s.d_flags, 0, p.ntiles * sizeof(int), st));
     TCK(cudaMemsetAsync(s.d_ctrl, 0, sizeof(int), st));
     static int occ_cache = 0;
     if (!occ_cache) {
-        TCK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_cache, k_sweep_tile3<NW>, (NW + 2) * 32, 0));
+        TCK(cudaFuncSetAttribute(k_sweep_tile3<NW, NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::BYTES));
+        TCK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_cache, k_sweep_tile3<NW, NCH>, (NW + 2) * 32, L::BYTES));
         if (occ_cache < 1) throw std::runtime_error("tile3 kernel does not fit on an SM");
     }
     int occ = occ_cache;
     if (o.ctas_per_sm > 0) occ = std::min(occ, o.ctas_per_sm);
     const int grid = std::min(p.ntiles, occ * sm_count);
-    k_sweep_tile3<NW><<<grid, (NW + 2) * 32, 0, st>>>(p, tt, slo, frozen, dx);
+    k_sweep_tile3<NW, NCH><<<grid, (NW + 2) * 32, L::BYTES, st>>>(tmT, tmS, tmH, p, tt, frozen, dx);
     k_sum_partials<<<1, 256, 0, st>>>(s.d_partial, p.ntiles, d_change);
     TCK(cudaMemcpyAsync(s.h_abort, s.d_ctrl + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
     TCK(cudaGetLastError());
@@ -443,7 +528,7 @@ inline int tile3_launch(TileState& s, const TileOptions& o, int sm_count, const 
 }
 
 // fp32, first-order only
-template <typename T> inline bool tile3_supported(bool weno_stage) { return false; }
+template <typename T> inline bool tile3_supported(bool) { return false; }
 template <> inline bool tile3_supported<float>(bool weno_stage) { return !weno_stage; }
 
 template <typename T>
@@ -455,8 +540,11 @@ template <>
 inline int tile3_sweep<float>(TileState& s, const TileOptions& o, int sm_count, const SweepView& w, const Dims& d, float* tt,
                               const float* slo, const uint32_t* frozen, const FrozenBox& fb, float dx, double* d_change,
                               cudaStream_t st) {
-    if (o.warps == 4) return tile3_launch<4>(s, o, sm_count, w, d, tt, slo, frozen, fb, dx, d_change, st);
-    return tile3_launch<8>(s, o, sm_count, w, d, tt, slo, frozen, fb, dx, d_change, st);
+    if (o.warps == 4) return tile3_launch<4, 4>(s, o, sm_count, w, d, tt, slo, frozen, fb, dx, d_change, st);
+    // ring depth: the loader must be able to run ahead, 8*NCH - 6 - NU - 2 >= 1 (see need_done in the kernel)
+    if (o.warps >= 16) return tile3_launch<16, 4>(s, o, sm_count, w, d, tt, slo, frozen, fb, dx, d_change, st);
+    if (o.depth <= 4) return tile3_launch<8, 3>(s, o, sm_count, w, d, tt, slo, frozen, fb, dx, d_change, st);
+    return tile3_launch<8, 4>(s, o, sm_count, w, d, tt, slo, frozen, fb, dx, d_change, st);
 }
 
 }  // namespace ttcrb200
