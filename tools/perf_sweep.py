@@ -32,7 +32,8 @@ def check():
         s = rng.uniform(0.3, 1.0, shape)
         res = []
         for kernel, opts in ((1, {}), (2, {}), (2, {"tile_warps": 4, "tile_urows": 2, "tile_rows": 2, "tile_depth": 4}),
-                             (3, {}), (3, {"tile_warps": 4, "tile_rows": 2}), (3, {"tile_rows": 16, "ctas_per_sm": 1})):
+                             (3, {}), (3, {"tile_warps": 4, "tile_rows": 2}), (3, {"tile_rows": 16, "ctas_per_sm": 1}),
+                             (4, {}), (4, {"tile_warps": 16}), (4, {"tile_depth": 4, "ctas_per_sm": 1})):
             g = Grid3d(x, y, z, cell_slowness=0, tt_from_rp=False, weno=0, dtype=dtype)
             g.set_option("kernel", kernel)
             for k, v in opts.items():
@@ -59,8 +60,8 @@ def timing(sizes):
         g = Grid3d(x, x, x, cell_slowness=0, tt_from_rp=False, weno=0, dtype=np.float32)
         g.set_slowness(s)
         print(f"--- {n}^3 device bytes {g.device_bytes() / 2**30:.2f} GiB", flush=True)
-        combos = [dict(kernel=3, tile_warps=w, tile_rows=c, tile_depth=8, ctas_per_sm=0) for w, c in itertools.product((8, 16), (1, 2, 4, 8))]
-        combos += [dict(kernel=3, tile_warps=8, tile_rows=c, tile_depth=4, ctas_per_sm=0) for c in (2, 4)]
+        combos = [dict(kernel=4, tile_warps=w, tile_depth=dp, ctas_per_sm=c) for w, dp, c in ((8, 8, 0), (8, 4, 0), (16, 8, 0), (8, 8, 2), (8, 8, 1))]
+        combos += [dict(kernel=3, tile_warps=8, tile_rows=4, tile_depth=8, ctas_per_sm=0)]
         combos += [dict(kernel=2, tile_warps=8, tile_urows=1, tile_rows=8, tile_depth=8, ctas_per_sm=0)]
         if n <= 256:
             combos.append(dict(kernel=1))
@@ -84,7 +85,7 @@ def one(n, opts):
     x, s = gradient(n)
     g = Grid3d(x, x, x, cell_slowness=0, tt_from_rp=False, weno=0, dtype=np.float32)
     g.set_slowness(s)
-    g.set_option("kernel", 3)
+    g.set_option("kernel", 4)
     for kv in opts:
         k, v = kv.split("=")
         g.set_option(k, float(v))

@@ -28,3 +28,14 @@ while pos < len(raw):
     for U in (0, nU // 2):
         st = (T[U, :, 1] - t0) / 1e3
         print(f"  U={U}: start over V {st.round(1)}")
+    # progress-based lags: time at which each tile reached 1/4, 1/2, 3/4 of its rows
+    for name, i in (("q1", 2), ("q2", 3), ("q3", 4), ("end", 5)):
+        x = (T[:, :, i] - t0) / 1e3
+        du = np.diff(x, axis=0)
+        dv = np.diff(x, axis=1)
+        print(f"  {name}: U-hop lag mean {du.mean():.2f} (V=0: {du[:, 0].mean():.2f}, p10 {np.percentile(du, 10):.2f}, p90 {np.percentile(du, 90):.2f});"
+              f" V-hop lag mean {dv.mean():.2f} (U=0: {dv[0].mean():.2f})")
+    run = (T[:, :, 5] - T[:, :, 1]) / 1e3
+    print(f"  run time per tile: U=0 row {run[0].round(0)}; V=0 col [::8] {run[::8, 0].round(0)}")
+    print(f"  tile (0,0): start {(T[0,0,1]-t0)/1e3:.1f} q1 {(T[0,0,2]-t0)/1e3:.1f} q2 {(T[0,0,3]-t0)/1e3:.1f} q3 {(T[0,0,4]-t0)/1e3:.1f} end {(T[0,0,5]-t0)/1e3:.1f}")
+    print(f"  last tile: ticket {(T[-1,-1,0]-t0)/1e3:.1f} start {(T[-1,-1,1]-t0)/1e3:.1f} end {(T[-1,-1,5]-t0)/1e3:.1f}")

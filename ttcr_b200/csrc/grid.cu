@@ -22,6 +22,7 @@
 #include "kernels.cuh"
 #include "sweep_tile.cuh"
 #include "sweep_tile3.cuh"
+#include "sweep_tile4.cuh"
 
 namespace ttcrb200 {
 
@@ -276,7 +277,7 @@ class Grid final : public GridBase {
         if (key == "tt_from_rp") ttrp_ = v != 0;
         else if (key == "kernel") {
             if (v != TTCR_B200_KERNEL_AUTO && v != TTCR_B200_KERNEL_PLANE && v != TTCR_B200_KERNEL_TILE &&
-                v != TTCR_B200_KERNEL_TILE3)
+                v != TTCR_B200_KERNEL_TILE3 && v != TTCR_B200_KERNEL_TILE4)
                 throw Err(TTCR_B200_ERR_INVALID, "unknown kernel id");
             kernel_ = (int)v;
         } else if (key == "tile_rows") tile_opt_.chunk = std::max(1, (int)v);
@@ -373,6 +374,12 @@ class Grid final : public GridBase {
     void launch_sweep(Slot& s, int dir, bool weno_stage, const FrozenBox& fb, int kernel) {
         const SweepView w = make_view(d_, dir);
         T* tt = s.tt[w.layout];
+        if (kernel == TTCR_B200_KERNEL_TILE4) {
+            const int nl = tile4_sweep<T>(s.tile, tile_opt_, sm_count_, w, d_, tt, slo_[w.layout], s.mask[w.layout], fb, g_.dx,
+                                         s.d_change, s.stream);
+            s.st.launches += nl; s.st.sweep_launches += nl;
+            return;
+        }
         if (kernel == TTCR_B200_KERNEL_TILE3) {
             const int nl = tile3_sweep<T>(s.tile, tile_opt_, sm_count_, w, d_, tt, slo_[w.layout], s.mask[w.layout], fb, g_.dx,
                                          s.d_change, s.stream);
@@ -402,7 +409,7 @@ class Grid final : public GridBase {
 
     int pick_kernel(bool weno_stage) const {
         if (kernel_ != TTCR_B200_KERNEL_AUTO) {
-            if (kernel_ == TTCR_B200_KERNEL_TILE3 && !tile3_supported<T>(weno_stage))
+            if ((kernel_ == TTCR_B200_KERNEL_TILE3 || kernel_ == TTCR_B200_KERNEL_TILE4) && !tile3_supported<T>(weno_stage))
                 return tile_supported<T>(weno_stage) ? TTCR_B200_KERNEL_TILE : TTCR_B200_KERNEL_PLANE;
             if (kernel_ == TTCR_B200_KERNEL_TILE && !tile_supported<T>(weno_stage)) return TTCR_B200_KERNEL_PLANE;
             return kernel_;

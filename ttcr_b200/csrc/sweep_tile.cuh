@@ -64,6 +64,11 @@ struct TileState {
     int cap_tiles = 0;
     int order_key = -1;
     int ntiles = 0;
+    // mailboxes of k_sweep_tile4 (allocated on first use)
+    unsigned long long* d_mbu = nullptr;
+    unsigned long long* d_mbv = nullptr;
+    int mb_rows = 0, mb_tiles = 0;
+    unsigned serial = 0;
 };
 
 struct TileParams {
@@ -515,6 +520,7 @@ inline void tile_alloc(TileState& s, const Dims& d, size_t& bytes) {
 
 inline void tile_free(TileState& s) {
     cudaFree(s.d_order); cudaFree(s.d_flags); cudaFree(s.d_ctrl); cudaFree(s.d_partial);
+    cudaFree(s.d_mbu); cudaFree(s.d_mbv);
     cudaFreeHost(s.h_abort);
     s = TileState{};
 }
