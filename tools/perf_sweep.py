@@ -27,13 +27,15 @@ def check():
     rng = np.random.default_rng(0)
     ok = True
     for shape, dtype, src in (((40, 33, 70), np.float32, [3.3, 2.2, 9.1]), ((65, 64, 31), np.float32, [0, 0, 0]),
-                              ((33, 100, 45), np.float64, [8.0, 20.0, 11.0]), ((129, 128, 130), np.float32, [16.0, 16.0, 16.0])):
+                              ((33, 100, 45), np.float64, [8.0, 20.0, 11.0]), ((129, 128, 130), np.float32, [16.0, 16.0, 16.0]),
+                              ((21, 30, 200), np.float32, [2.6, 3.1, 30.2]), ((50, 17, 260), np.float32, [12.25, 4.0, 64.75])):
         x, y, z = (np.arange(m) * 0.25 for m in shape)
         s = rng.uniform(0.3, 1.0, shape)
         res = []
         for kernel, opts in ((1, {}), (2, {}), (2, {"tile_warps": 4, "tile_urows": 2, "tile_rows": 2, "tile_depth": 4}),
                              (3, {}), (3, {"tile_warps": 4, "tile_rows": 2}), (3, {"tile_rows": 16, "ctas_per_sm": 1}),
-                             (4, {}), (4, {"tile_warps": 16}), (4, {"tile_depth": 4, "ctas_per_sm": 1})):
+                             (4, {}), (4, {"tile_warps": 16}), (4, {"tile_depth": 4, "ctas_per_sm": 1}),
+                             (5, {"tile_warps": 4}), (5, {"tile_warps": 8}), (5, {"tile_warps": 4, "tile_depth": 4, "ctas_per_sm": 1})):
             g = Grid3d(x, y, z, cell_slowness=0, tt_from_rp=False, weno=0, dtype=dtype)
             g.set_option("kernel", kernel)
             for k, v in opts.items():
@@ -60,11 +62,8 @@ def timing(sizes):
         g = Grid3d(x, x, x, cell_slowness=0, tt_from_rp=False, weno=0, dtype=np.float32)
         g.set_slowness(s)
         print(f"--- {n}^3 device bytes {g.device_bytes() / 2**30:.2f} GiB", flush=True)
-        combos = [dict(kernel=4, tile_warps=w, tile_depth=dp, ctas_per_sm=c) for w, dp, c in ((8, 8, 0), (8, 4, 0), (16, 8, 0), (8, 8, 2), (8, 8, 1))]
-        combos += [dict(kernel=3, tile_warps=8, tile_rows=4, tile_depth=8, ctas_per_sm=0)]
-        combos += [dict(kernel=2, tile_warps=8, tile_urows=1, tile_rows=8, tile_depth=8, ctas_per_sm=0)]
-        if n <= 256:
-            combos.append(dict(kernel=1))
+        combos = [dict(kernel=5, tile_warps=w, tile_depth=dp, ctas_per_sm=c) for w, dp, c in ((4, 8, 0), (4, 8, 1), (4, 4, 0), (8, 8, 0))]
+        combos += [dict(kernel=4, tile_warps=8, tile_depth=4, ctas_per_sm=0)]
         for src in ([0.0, 0.0, 0.0],):
             for c in combos:
                 for k, v in c.items():

@@ -22,7 +22,7 @@
 #include "kernels.cuh"
 #include "sweep_tile.cuh"
 #include "sweep_tile3.cuh"
-#include "sweep_tile4.cuh"
+#include "sweep_tile5.cuh"
 
 namespace ttcrb200 {
 
@@ -100,9 +100,9 @@ class Grid final : public GridBase {
 
         const size_t ne = d_.elems();
         for (int l = 0; l < 2; ++l) {
-            CK(cudaMalloc(&slo_[l], ne * sizeof(T)));
-            bytes_ += ne * sizeof(T);
-            CK(cudaMemset(slo_[l], 0, ne * sizeof(T)));
+            slo_[l] = alloc_field(ne);
+            // slots that are no node hold NaN: their update is NaN and never passes `t < old` (sweep_tile5.cuh)
+            CK(cudaMemset(slo_[l], 0xFF, ne * sizeof(T)));
         }
         slots_.resize(nslots);
         for (auto& s : slots_) {
@@ -110,9 +110,9 @@ class Grid final : public GridBase {
             CK(cudaEventCreate(&s.e0));
             CK(cudaEventCreate(&s.e1));
             for (int l = 0; l < 2; ++l) {
-                CK(cudaMalloc(&s.tt[l], ne * sizeof(T)));
+                s.tt[l] = alloc_field(ne);
                 CK(cudaMalloc(&s.mask[l], ne / 32 * sizeof(uint32_t)));
-                bytes_ += ne * sizeof(T) + ne / 8;
+                bytes_ += ne / 8;
                 k_fill<T><<<nblocks(ne), 256, 0, s.stream>>>(s.tt[l], ne, Lim<T>::max());
                 CK(cudaMemsetAsync(s.mask[l], 0, ne / 8, s.stream));
             }
@@ -130,15 +130,16 @@ class Grid final : public GridBase {
         cudaSetDevice(dev_);
         for (auto& s : slots_) {
             cudaStreamSynchronize(s.stream);
-            for (int l = 0; l < 2; ++l) { cudaFree(s.tt[l]); cudaFree(s.mask[l]); }
+            for (int l = 0; l < 2; ++l) { free_field(s.tt[l]); cudaFree(s.mask[l]); }
             for (auto e : s.sweep_ev) cudaEventDestroy(e);
             cudaFree(s.d_change); cudaFreeHost(s.h_change);
             cudaFree(s.d_pts); cudaFreeHost(s.h_pts);
             tile_free(s.tile);
+            tile5_free(s.tile5);
             cudaEventDestroy(s.e0); cudaEventDestroy(s.e1);
             cudaStreamDestroy(s.stream);
         }
-        for (int l = 0; l < 2; ++l) cudaFree(slo_[l]);
+        for (int l = 0; l < 2; ++l) free_field(slo_[l]);
         cudaFree(lin_[0]); cudaFree(lin_[1]);
     }
 
@@ -277,7 +278,7 @@ class Grid final : public GridBase {
         if (key == "tt_from_rp") ttrp_ = v != 0;
         else if (key == "kernel") {
             if (v != TTCR_B200_KERNEL_AUTO && v != TTCR_B200_KERNEL_PLANE && v != TTCR_B200_KERNEL_TILE &&
-                v != TTCR_B200_KERNEL_TILE3 && v != TTCR_B200_KERNEL_TILE4)
+                v != TTCR_B200_KERNEL_TILE3 && v != TTCR_B200_KERNEL_TILE4 && v != TTCR_B200_KERNEL_TILE5)
                 throw Err(TTCR_B200_ERR_INVALID, "unknown kernel id");
             kernel_ = (int)v;
         } else if (key == "tile_rows") tile_opt_.chunk = std::max(1, (int)v);
@@ -303,10 +304,25 @@ class Grid final : public GridBase {
         T* h_pts = nullptr;
         size_t pts_cap = 0;
         TileState tile;
+        Tile5State tile5;
         ttcr_b200_stats st{};
         std::vector<cudaEvent_t> sweep_ev;   // pairs of events around the directional sweeps
         size_t sweep_ev_used = 0;
     };
+
+    // Field arrays (traveltime, slowness) carry ni rows of front padding: the skewed tensor map of k_sweep_patch
+    // (make_tile5_map, "plus" variant) is based that far below the array and the TMA unit wants a mapped base.
+    size_t front_pad() const { return (size_t)d_.ni * d_.kpad; }
+    T* alloc_field(size_t ne) {
+        T* raw = nullptr;
+        CK(cudaMalloc(&raw, (ne + front_pad()) * sizeof(T)));
+        CK(cudaMemset(raw, 0, front_pad() * sizeof(T)));
+        bytes_ += (ne + front_pad()) * sizeof(T);
+        return raw + front_pad();
+    }
+    void free_field(T* p) {
+        if (p) cudaFree(p - front_pad());
+    }
 
     Slot& slot_at(size_t slot) {
         if (slot >= slots_.size()) throw Err(TTCR_B200_ERR_INVALID, "Thread number is larger than number of threads");
@@ -374,6 +390,12 @@ class Grid final : public GridBase {
     void launch_sweep(Slot& s, int dir, bool weno_stage, const FrozenBox& fb, int kernel) {
         const SweepView w = make_view(d_, dir);
         T* tt = s.tt[w.layout];
+        if (kernel == TTCR_B200_KERNEL_TILE5) {
+            const int nl = tile5_sweep<T>(s.tile, s.tile5, tile_opt_, sm_count_, w, d_, tt, slo_[w.layout], s.mask[w.layout], fb,
+                                         g_.dx, s.d_change, s.stream);
+            s.st.launches += nl; s.st.sweep_launches += nl;
+            return;
+        }
         if (kernel == TTCR_B200_KERNEL_TILE4) {
             const int nl = tile4_sweep<T>(s.tile, tile_opt_, sm_count_, w, d_, tt, slo_[w.layout], s.mask[w.layout], fb, g_.dx,
                                          s.d_change, s.stream);
@@ -409,12 +431,13 @@ class Grid final : public GridBase {
 
     int pick_kernel(bool weno_stage) const {
         if (kernel_ != TTCR_B200_KERNEL_AUTO) {
-            if ((kernel_ == TTCR_B200_KERNEL_TILE3 || kernel_ == TTCR_B200_KERNEL_TILE4) && !tile3_supported<T>(weno_stage))
+            if ((kernel_ == TTCR_B200_KERNEL_TILE3 || kernel_ == TTCR_B200_KERNEL_TILE4 || kernel_ == TTCR_B200_KERNEL_TILE5) &&
+                !tile3_supported<T>(weno_stage))
                 return tile_supported<T>(weno_stage) ? TTCR_B200_KERNEL_TILE : TTCR_B200_KERNEL_PLANE;
             if (kernel_ == TTCR_B200_KERNEL_TILE && !tile_supported<T>(weno_stage)) return TTCR_B200_KERNEL_PLANE;
             return kernel_;
         }
-        if (tile3_supported<T>(weno_stage)) return TTCR_B200_KERNEL_TILE3;   // fp32, first order: TMA-fed tiles
+        if (tile4_supported<T>(weno_stage)) return TTCR_B200_KERNEL_TILE4;   // fp32, first order: TMA-fed tiles, mailbox hand-off
         if (!tile_supported<T>(weno_stage)) return TTCR_B200_KERNEL_PLANE;      // WENO stage
         return TTCR_B200_KERNEL_TILE;                                           // fp64, first order
     }
@@ -451,7 +474,9 @@ class Grid final : public GridBase {
             T change = Lim<T>::max();
             while (change >= epsilon_ && it < maxit_) {
                 CK(cudaMemsetAsync(s.d_change, 0, sizeof(double), s.stream));
+                static const int dbg_dirs = getenv("TTCR_B200_DEBUG_DIRS") ? atoi(getenv("TTCR_B200_DEBUG_DIRS")) : 255;
                 for (int dir = 0; dir < 8; ++dir) {
+                    if (!((dbg_dirs >> dir) & 1)) continue;   // debugging aid: run a subset of the sweep directions
                     const int want = make_view(d_, dir).layout;
                     if (want != cur) {
                         const dim3 grid((d_.nk + 31) / 32, (d_.nj + 31) / 32, d_.ni);
@@ -486,7 +511,11 @@ class Grid final : public GridBase {
             }
             if (wstage) s.st.niterw = it; else s.st.niter = it;
         }
-        if (cur != 0) throw Err(TTCR_B200_ERR_LOGIC, "internal: field not in layout L1 after the last sweep");
+        if (cur != 0) {   // only reachable with TTCR_B200_DEBUG_DIRS
+            const dim3 grid((d_.nk + 31) / 32, (d_.nj + 31) / 32, d_.ni);
+            k_relayout<T><<<grid, dim3(32, 8), 0, s.stream>>>(s.tt[cur], cur, s.tt[0], d_);
+            cur = 0;
+        }
         CK(cudaEventRecord(s.e1, s.stream));
         CK(cudaEventSynchronize(s.e1));
         float ms = 0.f;

@@ -1,0 +1,757 @@
+// Sweep kernel "TILE5" (k_sweep_patch): register-patch tile march.
+//
+// What bounds a directional sweep on a B200 is not HBM but the 3N-step dependency chain and the number of
+// instructions issued per node: k_sweep_tile4 issues ~200 warp instructions per 32
+// nodes and synchronises 8 warps with a CTA barrier at every step.  This kernel keeps the decomposition
+// (sheared layouts, tiles marching along the row axis m, tickets in dependency order, tagged mailboxes) and
+// changes the work assignment so that almost every instruction is arithmetic of the Godunov update:
+//
+//   * a THREAD owns a patch of 4 consecutive lanes (v) x R consecutive planes (u) and marches along m.
+//     Plane r of the patch runs r rows behind plane 0, so at macro-step a the thread updates the 4R nodes
+//     (u0+r, a-r, 4l..4l+3): all mutually independent (ILP 4R), and
+//         (u-1, m, v)    = the thread's own result of plane r-1 at the previous step      (register)
+//         (u, m-1, v)    = own previous result                                            (register)
+//         (u, m-1, v-1)  = own previous result of the lane to the left / one shuffle for element 0
+//         (u+1, m, v)    = the "next old row" of plane r+1, which the thread loads anyway (register)
+//         (u, m+1, v), (u, m+1, v+1) = one LDS.128 (+ one LDS.32 for the lane beyond the patch)
+//     i.e. per 4 nodes: 2 LDS.128 (traveltime row, slowness row), 1 LDS.32, 1 SHFL, <= 1 STG.128.
+//   * a WARP (128 lanes x R planes) is self-sufficient: lane 0 issues its own TMA boxes (one 3-D box of
+//     traveltimes {132 lanes, C rows, R+1 planes}, one of slowness {128, C, R} per chunk of C steps) into a
+//     private ring and the warp waits on its own mbarriers.  The plane skew is put into the TENSOR MAP
+//     (plane stride = (rows per plane -+ 1) rows), so a box arrives already skewed and every smem address of
+//     a step is ring base + immediate.
+//   * there is NO CTA barrier in the march.  A CTA stacks NU warps along u (tile = NU*R planes x 128
+//     lanes).  Warp w hands the results of its last plane to warp w+1 through a shared-memory ring of
+//     tagged 8-byte words {row tag, value} (an aligned 8-byte shared access is single-copy atomic: the
+//     reader that sees the tag has the value; no fence, no barrier).  Between tiles the same words travel
+//     through global mailboxes (as in k_sweep_tile4): the last warp writes them, and an IMPORTER warp of the
+//     consuming CTA polls them with a rolling two-row prefetch and re-tags them into the shared rings, so
+//     compute warps only ever read shared memory.  The importer also feeds the v0-1 lane results of tile
+//     V-1 (one word per plane and row) and synthesises +MAX where no neighbour exists.
+//   * slots that are no node hold +MAX (traveltime) and NaN (slowness): the update of such a slot is NaN
+//     and `t < old` fails, so the march needs no validity test at all.  Frozen nodes (source box) and the
+//     grid's last planes are handled by a slow variant of the step that only the few affected warps run.
+//
+// fp32, first-order stage only.  Results are bit-identical to the other sweep kernels (same DAG, same
+// arithmetic: update.cuh).
+#pragma once
+#include "sweep_tile4.cuh"
+
+namespace ttcrb200 {
+
+struct Tile5Mail {
+    unsigned long long* u = nullptr;   // [tile][row][2 halves][32 lanes][2 words]: last plane of the tile (1 KiB per row)
+    unsigned long long* v = nullptr;   // [tile][MARGIN + row][PU words]: lane v0+127 of every plane
+    int rows = 0;                      // row stride per tile
+    unsigned serial = 0;               // sweep launch counter = tag of the current sweep
+    static constexpr int MARGIN = 8;
+};
+
+struct Tile5Params {
+    SweepView w;
+    Dims d;
+    FrozenBox fb;
+    int nU, nV, ntiles;
+    long long spin_limit;
+    const int* order;
+    int* ctrl;
+    double* partial;   // [tile][NU]
+    long long* trace;
+};
+
+constexpr int t5_round128(int x) { return (x + 127) / 128 * 128; }
+
+template <int NU, int R, int C, int NCH, int DU_>
+struct Tile5Layout {
+    static constexpr int PU = NU * R;
+    static constexpr int TW = 132;                                   // floats per traveltime row: 128 + 4
+    static constexpr int TROW = TW * 4, SROW = 128 * 4;
+    static constexpr int TPL = C * TROW, SPL = C * SROW;             // bytes per plane of a box
+    static constexpr int CHB_T = t5_round128((R + 1) * TPL), CHB_S = R * SPL;
+    static constexpr int WARP_BYTES = NCH * (CHB_T + CHB_S);
+    static constexpr int DU = DU_;                                   // rows per U ring
+    static constexpr int URING = DU * 1024;
+    static constexpr int DV = 64;                                    // macro-steps per V ring
+    static constexpr int VRING = DV * R * 8;
+    static constexpr int OFF_RING = 0;                               // NU x [T slots][S slots]
+    static constexpr int OFF_U = OFF_RING + NU * WARP_BYTES;         // NU U rings (ring w = input of warp w)
+    static constexpr int OFF_V = OFF_U + NU * URING;                 // NU V rings
+    static constexpr int OFF_BAR = OFF_V + NU * VRING;               // NU x NCH mbarriers
+    static constexpr int OFF_PROG = OFF_BAR + NU * NCH * 8;          // NU progress counters
+    static constexpr int OFF_FLG = OFF_PROG + NU * 4;                // dead, tile
+    static constexpr int OFF_RED = (OFF_FLG + 8 + 7) / 8 * 8;
+    static constexpr int BYTES = OFF_RED + NU * 8;
+    static_assert(CHB_S % 128 == 0 && WARP_BYTES % 128 == 0 && URING % 128 == 0, "TMA destinations must stay 128-byte aligned");
+    static_assert(DV >= NU * R + DU + 8, "V ring too shallow for the skew between the warps");
+    static_assert(R + C + 4 <= GUARD, "guard rows too few");
+};
+
+// ---- shared / global access helpers ---------------------------------------------------------------
+__device__ __forceinline__ float4 lds_f4(unsigned a) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint4 lds_u4(unsigned a) {
+    uint4 v;
+    asm volatile("ld.volatile.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint2 lds_u2(unsigned a) {
+    uint2 v;
+    asm volatile("ld.volatile.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_u4(unsigned a, unsigned x, unsigned y, unsigned z, unsigned w) {
+    asm volatile("st.volatile.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+__device__ __forceinline__ void sts_u2(unsigned a, unsigned x, unsigned y) {
+    asm volatile("st.volatile.shared.v2.u32 [%0], {%1, %2};" ::"r"(a), "r"(x), "r"(y) : "memory");
+}
+// two tagged words {value, tag} x 2 with one 16-byte store / load (each 8-byte half is single-copy atomic)
+__device__ __forceinline__ void st_mail2(unsigned long long* p, unsigned tag, float a, float b) {
+    asm volatile(
+        "{\n\t.reg .b64 x, y;\n\tmov.b64 x, {%1, %2};\n\tmov.b64 y, {%3, %2};\n\tst.relaxed.gpu.global.v2.b64 [%0], {x, y};\n\t}" ::"l"(p),
+        "r"(__float_as_uint(a)), "r"(tag), "r"(__float_as_uint(b))
+        : "memory");
+}
+__device__ __forceinline__ uint4 ld_mail2(const unsigned long long* p) {
+    uint4 v;
+    asm volatile(
+        "{\n\t.reg .b64 x, y;\n\tld.relaxed.gpu.global.v2.b64 {x, y}, [%4];\n\tmov.b64 {%0, %1}, x;\n\tmov.b64 {%2, %3}, y;\n\t}"
+        : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+        : "l"(p)
+        : "memory");
+    return v;
+}
+__device__ __forceinline__ float4 ldg_f4_stream(const float* p) {
+    float4 v;
+    asm volatile("ld.global.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ bool vt_ghost(int vt, int kpad) { return vt >= kpad; }
+__device__ __forceinline__ void stg_f4_stream(float* p, float x, float y, float z, float w) {
+    asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
+}
+template <bool REV> __device__ __forceinline__ float4 ord4(float4 v) { return REV ? make_float4(v.w, v.z, v.y, v.x) : v; }
+
+// RJ: the sweep runs the row axis downwards, RK: the lane axis (boxes arrive in memory order).
+template <int NU, int R, int C, int NCH, int DU_, bool RJ, bool RK>
+__global__ void __launch_bounds__((NU + 1) * 32, (NU <= 4 ? 2 : 1)) k_sweep_patch(const __grid_constant__ CUtensorMap tmT,
+                                                                  const __grid_constant__ CUtensorMap tmS, Tile5Params p,
+                                                                  Tile5Mail mail, float* __restrict__ tt,
+                                                                  const uint32_t* __restrict__ frozen, float dx) {
+    using L = Tile5Layout<NU, R, C, NCH, DU_>;
+    constexpr int PU = L::PU, DU = L::DU, DV = L::DV;
+    constexpr int MG = Tile5Mail::MARGIN;
+    constexpr int G = 2;   // rows of mailbox loads the importer keeps in flight
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const SweepView& w = p.w;
+    const float MAXV = FLT_MAX;
+    const unsigned sbase = (unsigned)__cvta_generic_to_shared(smem_raw);
+    const unsigned a_dead = sbase + L::OFF_FLG, a_tile = a_dead + 4;
+    const unsigned a_prog = sbase + L::OFF_PROG;
+    const unsigned serial = mail.serial;
+    const long long spin_cycles = p.spin_limit << 9;
+    unsigned gc = 0;   // chunks this warp has consumed since the kernel started: slot gc % NCH, parity (gc / NCH) & 1
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < NU * NCH; ++i) mbar_init(sbase + L::OFF_BAR + 8 * i, 1);
+        fence_mbar_init();
+    }
+
+    for (;;) {
+        __syncthreads();   // everybody is done with the previous tile (rings, flags)
+        if (threadIdx.x == 0) {
+            const int t = atomicAdd(&p.ctrl[0], 1);
+            const int ab = *((volatile int*)&p.ctrl[1]);
+            sts_i(a_tile, (ab || t >= p.ntiles) ? -1 : t);
+            sts_i(a_dead, 0);
+        }
+        // clear the tags of all rings and the progress counters
+        for (unsigned o = threadIdx.x * 16; o < (unsigned)(L::OFF_BAR - L::OFF_U); o += (NU + 1) * 32 * 16)
+            sts_u4(sbase + L::OFF_U + o, 0u, 0u, 0u, 0u);
+        if (threadIdx.x < NU) sts_i(a_prog + 4 * threadIdx.x, 0);
+        __syncthreads();
+        const int ticket = lds_i(a_tile);
+        if (ticket < 0) break;
+        const int tile = p.order[ticket];
+        const int U = tile / p.nV, V = tile - U * p.nV;
+        const int u0 = U * PU, v0 = V * 128;
+        const int va = max(v0, w.vlo), vb = min(v0 + 128, w.vhi);
+        const int m_first = va - w.joff;
+        const int nrows = (vb - va) + w.nj - 1;                // local rows 0 .. nrows-1 hold all nodes of the tile
+        const int nsteps = nrows + R - 1;                      // macro-steps (plane r runs r rows behind plane 0)
+        const int nchunks = (nsteps + C - 1) / C;
+        const int nA = nchunks * C;                            // macro-steps executed (the surplus ones touch no node)
+        const bool has_u = U > 0, has_v = V > 0;
+        const bool has_right = v0 + 128 < w.vhi;
+        const bool has_down = U + 1 < p.nU;
+        const int va_p = max(v0 - 128, w.vlo);
+        const int nrows_p = (v0 - va_p) + w.nj - 1;            // rows of tile V-1
+        const int dmf = m_first - (va_p - w.joff);             // its local row index of my local row 0
+        if (p.trace && threadIdx.x == 0) {
+            p.trace[tile * 8 + 0] = gtime();
+            unsigned smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            p.trace[tile * 8 + 7] = smid;
+        }
+
+        if (warp == NU) {
+            // ================= importer =====================================================================
+            // macro-step a: U ring 0 <- row a of the last plane of tile U-1; V ring w, slot a <- for every plane
+            // (w, r) the lane v0-1 result of row a-r of tile V-1.  +MAX where there is no such node.
+            const unsigned long long* const mu_in = mail.u + ((size_t)(has_u ? tile - p.nV : tile) * mail.rows) * 128 + lane * 2;
+            const int pw = lane / R, pr = lane - pw * R;                      // lane < PU: plane (pw, pr)
+            const bool vlane = lane < PU;
+            const unsigned long long* const mv_in =
+                mail.v + ((size_t)(has_v ? tile - 1 : tile) * mail.rows + MG) * PU + lane;
+            const unsigned a_vring = sbase + L::OFF_V + pw * L::VRING + pr * 8;
+            const unsigned a_uring = sbase + L::OFF_U + lane * 16;
+            const unsigned a_prog0 = a_prog, a_progl = a_prog + 4 * (NU - 1);
+            bool dead = false;
+            auto give_up = [&](int why, int x) {
+                if (atomicCAS(&p.ctrl[1], 0, why) == 0) { p.ctrl[2] = tile; p.ctrl[3] = x; p.ctrl[4] = lane; p.ctrl[5] = NU; }
+                sts_i(a_dead, 1);
+            };
+            // rolling prefetch of depth G
+            uint4 qa[G], qb[G];
+            unsigned long long qv[G];
+            auto v_row = [&](int a) { return a - pr - 1 + dmf; };            // row of tile V-1 this lane needs at step a
+            auto v_inr = [&](int a) {
+                const int rr = a - pr, rp = rr - 1 + dmf;
+                return has_v && vlane && rr >= 0 && rr < nrows && rp >= 0 && rp < nrows_p;
+            };
+            auto issue = [&](int a, int s) {
+                if (has_u && a < nrows) {
+                    qa[s] = ld_mail2(mu_in + (size_t)a * 128);
+                    qb[s] = ld_mail2(mu_in + (size_t)a * 128 + 64);
+                }
+                if (v_inr(a)) qv[s] = ld_mail(mv_in + (long long)v_row(a) * PU);
+            };
+#pragma unroll
+            for (int s = 0; s < G; ++s) {
+                qa[s] = qb[s] = make_uint4(0, 0, 0, 0);
+                qv[s] = 0;
+                if (s < nA) issue(s, s);
+            }
+            for (int a0 = 0; a0 < nA && !dead; a0 += G) {
+#pragma unroll
+                for (int s = 0; s < G; ++s) {
+                    const int a = a0 + s;
+                    if (a >= nA || dead) break;
+                    const unsigned tag = (unsigned)(a + 1);
+                    // ---- back-pressure: the slots about to be overwritten have been read
+                    {
+                        const long long t0 = clock64();
+                        while (lds_i(a_prog0) < a - DU + 1 || lds_i(a_progl) < a - DV + 1) {
+                            if (lds_i(a_dead)) { dead = true; break; }
+                            if (clock64() - t0 > spin_cycles) { give_up(30, a); dead = true; break; }
+                        }
+                        if (dead) break;
+                    }
+                    // ---- V words
+                    if (vlane) {
+                        float val = MAXV;
+                        if (v_inr(a)) {
+                            unsigned long long x = qv[s];
+                            if ((unsigned)(x >> 32) != serial) {
+                                const unsigned long long* const q = mv_in + (long long)v_row(a) * PU;
+                                const long long t0 = clock64();
+                                for (;;) {
+                                    x = ld_mail(q);
+                                    if ((unsigned)(x >> 32) == serial) break;
+                                    if (lds_i(a_dead)) { dead = true; break; }
+                                    if (clock64() - t0 > spin_cycles) { give_up(31, a); dead = true; break; }
+                                }
+                            }
+                            val = __uint_as_float((unsigned)x);
+                        }
+                        sts_u2(a_vring + (unsigned)(a & (DV - 1)) * (R * 8), __float_as_uint(val), tag);
+                    }
+                    // ---- U row
+                    if (a < nrows) {
+                        uint4 xa, xb;
+                        if (has_u) {
+                            xa = qa[s]; xb = qb[s];
+                            if (xa.y != serial || xa.w != serial || xb.y != serial || xb.w != serial) {
+                                const unsigned long long* const q = mu_in + (size_t)a * 128;
+                                const long long t0 = clock64();
+                                for (;;) {
+                                    xa = ld_mail2(q);
+                                    xb = ld_mail2(q + 64);
+                                    if (xa.y == serial && xa.w == serial && xb.y == serial && xb.w == serial) break;
+                                    if (lds_i(a_dead)) { dead = true; break; }
+                                    if (clock64() - t0 > spin_cycles) { give_up(32, a); dead = true; break; }
+                                }
+                            }
+                        } else {
+                            xa.x = xa.z = xb.x = xb.z = __float_as_uint(MAXV);
+                        }
+                        const unsigned ar = a_uring + (unsigned)(a & (DU - 1)) * 1024;
+                        sts_u4(ar, xa.x, tag, xa.z, tag);
+                        sts_u4(ar + 512, xb.x, tag, xb.z, tag);
+                    }
+                    dead = __any_sync(0xffffffffu, dead);
+                    if (!dead && a + G < nA) issue(a + G, s);
+                }
+            }
+        } else {
+            // ================= compute warps ==============================================================
+            const int wu = warp;
+            const int u0w = u0 + wu * R;                       // first plane of this warp
+            const int ulast = w.nu - 1;
+            const bool edge = u0w + R > ulast;                 // some (u+1) plane of the patch does not exist
+            const int nch = u0w > ulast ? 0 : nchunks;         // warps wholly past the grid's last plane do nothing
+            const bool ghost = vt_ghost(v0 + 4 * lane, p.d.kpad);   // lanes past the end of the row: TMA zero-fills them
+            const bool last_w = wu == NU - 1;
+            const int vt = v0 + 4 * lane;                      // oriented lane of element 0
+            const bool kill = vt + 4 >= w.vhi;                 // element 3 has no v+1 neighbour
+            const int mail_v_out = (lane == 31 && has_right) ? 1 : 0;
+            const unsigned tag_g = serial;
+            // ---- ring addresses
+            const unsigned a_ring = sbase + L::OFF_RING + wu * L::WARP_BYTES;
+            const unsigned a_bar = sbase + L::OFF_BAR + wu * NCH * 8;
+            const int colT = RK ? 128 - 4 * lane : 4 * lane;   // column of the float4 in a 132-float row (memory order)
+            const int colH = RK ? colT - 1 : colT + 4;         // column of lane v+4
+            const int colS = RK ? 124 - 4 * lane : 4 * lane;
+            unsigned aT[R + 1], aS[R];
+#pragma unroll
+            for (int r = 0; r <= R; ++r) aT[r] = a_ring + (w.ri ? R - r : r) * L::TPL + colT * 4;
+#pragma unroll
+            for (int r = 0; r < R; ++r) aS[r] = a_ring + NCH * L::CHB_T + (w.ri ? R - 1 - r : r) * L::SPL + colS * 4;
+            const int dH = (colH - colT) * 4;
+            const unsigned a_uin = sbase + L::OFF_U + wu * L::URING + lane * 16;
+            const unsigned a_uout = sbase + L::OFF_U + (wu + 1) * L::URING + lane * 16;   // not used by the last warp
+            const unsigned a_vin = sbase + L::OFF_V + wu * L::VRING;
+            const unsigned a_myprog = a_prog + 4 * wu, a_nxprog = a_prog + 4 * (last_w ? wu : wu + 1);
+            // ---- global addresses
+            // element offset of (u0w + r, local row 0, element 0 .. 3 in memory order)
+            long long e0[R];
+#pragma unroll
+            for (int r = 0; r < R; ++r)
+                e0[r] = w.base + (long long)min(u0w + r, ulast) * w.su + (long long)m_first * w.sm + (long long)vt * w.sv - (RK ? 3 : 0);
+            unsigned long long* const mu_out = mail.u + ((size_t)tile * mail.rows) * 128 + lane * 2;
+            unsigned long long* const mv_out = mail.v + ((size_t)tile * mail.rows + MG) * PU + wu * R;
+            // ---- TMA box origins (memory coordinates), see the header: plane p of a box sits at row Y0 -+ p
+            const bool minus_map = (w.ri != 0) == (w.rj != 0);
+            const int xT = RK ? p.d.kpad - 132 - v0 : v0;
+            const int xS = RK ? p.d.kpad - 128 - v0 : v0;
+            const int zT = w.ri ? p.d.ni - 1 - (u0w + R) : u0w;
+            const int zS = w.ri ? p.d.ni - 1 - (u0w + R - 1) : u0w;
+            // first memory row of box plane 0 for chunk 0 (T: rows cC - r + 1 .., S: rows cC - r ..)
+            const int rT0 = w.ri ? R : 0, rS0 = w.ri ? R - 1 : 0;
+            const int yT0 = RJ ? GUARD + (w.nm - 1) - (m_first - rT0 + C) : GUARD + m_first - rT0 + 1;
+            const int yS0 = RJ ? GUARD + (w.nm - 1) - (m_first - rS0 + C - 1) : GUARD + m_first - rS0;
+            const int yT = minus_map ? yT0 + zT : yT0 - zT + p.d.ni;   // the "plus" map is based ni rows below the array
+            const int yS = minus_map ? yS0 + zS : yS0 - zS + p.d.ni;
+            const int dyc = RJ ? -C : C;                       // rows per chunk in memory direction
+            int issued = 0;
+            auto issue_chunk = [&](int c, unsigned g) {        // chunk c of this tile -> ring slot g % NCH
+                const unsigned slot = g % NCH;
+                ++issued;
+                const unsigned mb = a_bar + 8 * slot;
+                mbar_expect_tx(mb, (R + 1) * L::TPL + R * L::SPL);
+                tma_load_3d(a_ring + slot * L::CHB_T, &tmT, xT, yT + c * dyc, zT, mb);
+                tma_load_3d(a_ring + NCH * L::CHB_T + slot * L::CHB_S, &tmS, xS, yS + c * dyc, zS, mb);
+            };
+            // ---- frozen nodes: macro-steps in which this warp may touch one, and which patch elements
+            unsigned fzmask = 0;   // bit r*4+e: element may be frozen (plane and lane inside the source box)
+            int wz_lo = 1 << 30, wz_hi = -(1 << 30);
+            if (p.fb.jhi >= p.fb.jlo) {
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const int uu = u0w + r;
+                    const int it = w.ri ? ulast - uu : uu;
+                    if (uu > ulast || it < p.fb.ilo || it > p.fb.ihi) continue;
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int v = vt + e;
+                        if (v < w.vlo || v >= w.vhi) continue;
+                        const int ko = v - w.vlo, kt = w.rk ? p.d.nk - 1 - ko : ko;
+                        if (kt < p.fb.klo || kt > p.fb.khi) continue;
+                        fzmask |= 1u << (r * 4 + e);
+                        const int jol = RJ ? w.nj - 1 - p.fb.jhi : p.fb.jlo, joh = RJ ? w.nj - 1 - p.fb.jlo : p.fb.jhi;
+                        // oriented j = m_first + row - v + joff  ->  row = j - joff + v - m_first, macro-step = row + r
+                        wz_lo = min(wz_lo, jol - w.joff + v - m_first + r);
+                        wz_hi = max(wz_hi, joh - w.joff + v - m_first + r);
+                    }
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                wz_lo = min(wz_lo, __shfl_xor_sync(0xffffffffu, wz_lo, o));
+                wz_hi = max(wz_hi, __shfl_xor_sync(0xffffffffu, wz_hi, o));
+            }
+            const int wz_cnt = wz_hi >= wz_lo ? wz_hi - wz_lo + 1 : 0;
+
+            bool dead = false;
+            auto give_up = [&](int why, int x, int a) {
+                if (atomicCAS(&p.ctrl[1], 0, why) == 0) { p.ctrl[2] = tile; p.ctrl[3] = x; p.ctrl[4] = a; p.ctrl[5] = wu; p.ctrl[6] = lane; }
+                sts_i(a_dead, 1);
+            };
+            auto wait_chunk = [&](unsigned g) {
+                const unsigned mb = a_bar + 8 * (g % NCH), par = (g / NCH) & 1;
+                if (mbar_test(mb, par)) return;
+                const long long t0 = clock64();
+                while (!mbar_test(mb, par)) {
+                    if (lds_i(a_dead)) { dead = true; break; }
+                    if (clock64() - t0 > spin_cycles) { give_up(40, (int)g, 0); dead = true; break; }
+                }
+            };
+
+            // ---- prologue: fill the ring, load the old values of local row 0
+            const unsigned g0 = gc;
+            if (lane == 0)
+                for (int c = 0; c < NCH - 1 && c < nch; ++c) issue_chunk(c, g0 + c);
+            float4 told[R], tprev[R];
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                // rows before local row 0 hold no node of the tile; a ghost lane must never see `t < old`
+                const float ini = ghost ? 0.f : MAXV;
+                told[r] = make_float4(ini, ini, ini, ini);
+                tprev[r] = told[r];
+            }
+            if (nch > 0 && !ghost) told[0] = ord4<RK>(ldg_f4_stream(tt + e0[0]));
+            if (nch == 0 && lane == 0) sts_i(a_myprog, 1 << 29);
+            float acc = 0.f;
+            if (p.trace && threadIdx.x == 0) p.trace[tile * 8 + 1] = gtime();
+
+            unsigned cT = 0, cS = 0;   // byte offsets of the current chunk slot
+            int a = 0;
+
+            auto step = [&](auto IC, auto SLOWC) {
+                constexpr int I = decltype(IC)::value;
+                constexpr bool SLOW = decltype(SLOWC)::value != 0;
+                constexpr int RT = (RJ ? C - 1 - I : I) * L::TROW, RS = (RJ ? C - 1 - I : I) * L::SROW;
+                // ---- loads of old values (all independent of other warps)
+                float4 jp[R], sl[R], up;
+                float h[R];
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    jp[r] = ord4<RK>(lds_f4(aT[r] + cT + RT));
+                    h[r] = lds_f(aT[r] + cT + RT + dH);
+                    sl[r] = ord4<RK>(lds_f4(aS[r] + cS + RS));
+                    if (kill) h[r] = MAXV;
+                }
+                up = ord4<RK>(lds_f4(aT[R] + cT + RT));
+                // ---- new values from the neighbours: (u0w-1, a, .) and lane v0-1 of every plane
+                const unsigned tag = (unsigned)(a + 1);
+                float4 um = make_float4(MAXV, MAXV, MAXV, MAXV);
+                if (a < nrows) {
+                    const unsigned ar = a_uin + (unsigned)(a & (DU - 1)) * 1024;
+                    uint4 xa = lds_u4(ar), xb = lds_u4(ar + 512);
+                    if (((xa.y ^ tag) | (xa.w ^ tag) | (xb.y ^ tag) | (xb.w ^ tag)) != 0) {
+                        const long long t0 = clock64();
+                        for (;;) {
+                            xa = lds_u4(ar); xb = lds_u4(ar + 512);
+                            if (((xa.y ^ tag) | (xa.w ^ tag) | (xb.y ^ tag) | (xb.w ^ tag)) == 0) break;
+                            if (lds_i(a_dead)) { dead = true; break; }
+                            if (clock64() - t0 > spin_cycles) { give_up(41, 0, a); dead = true; break; }
+                        }
+                    }
+                    um = make_float4(__uint_as_float(xa.x), __uint_as_float(xa.z), __uint_as_float(xb.x), __uint_as_float(xb.z));
+                }
+                float vm[R];
+                {
+                    const unsigned av = a_vin + (unsigned)(a & (DV - 1)) * (R * 8);
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        uint2 x = lds_u2(av + r * 8);
+                        if (x.y != tag) {
+                            const long long t0 = clock64();
+                            for (;;) {
+                                x = lds_u2(av + r * 8);
+                                if (x.y == tag) break;
+                                if (lds_i(a_dead)) { dead = true; break; }
+                                if (clock64() - t0 > spin_cycles) { give_up(42, r, a); dead = true; break; }
+                            }
+                        }
+                        vm[r] = __uint_as_float(x.x);
+                    }
+                }
+                float km0[R];
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    km0[r] = __shfl_up_sync(0xffffffffu, tprev[r].w, 1);
+                    if (lane == 0) km0[r] = vm[r];
+                }
+                // ---- the ring slot of warp wu+1 that this step overwrites has been read
+                if (!last_w && lds_i(a_nxprog) < a - (R - 1) - DU + 1) {
+                    const long long t0 = clock64();
+                    while (lds_i(a_nxprog) < a - (R - 1) - DU + 1) {
+                        if (lds_i(a_dead)) { dead = true; break; }
+                        if (clock64() - t0 > spin_cycles) { give_up(43, 0, a); dead = true; break; }
+                    }
+                }
+                // ---- update, last plane first (plane r reads the previous-step result of plane r-1)
+#pragma unroll
+                for (int r = R - 1; r >= 0; --r) {
+                    float4 upv = (r == R - 1) ? up : jp[r + 1 < R ? r + 1 : r];
+                    const float4 umv = (r == 0) ? um : tprev[r > 0 ? r - 1 : 0];
+                    if (SLOW) {
+                        if (u0w + r >= ulast) upv = make_float4(MAXV, MAXV, MAXV, MAXV);
+                    }
+                    const float4 tp = tprev[r], j = jp[r], s = sl[r], o = told[r];
+                    const float t0 = godunov(tmin(km0[r], j.y), tmin(tp.x, j.x), tmin(umv.x, upv.x), s.x * dx);
+                    const float t1 = godunov(tmin(tp.x, j.z), tmin(tp.y, j.y), tmin(umv.y, upv.y), s.y * dx);
+                    const float t2 = godunov(tmin(tp.y, j.w), tmin(tp.z, j.z), tmin(umv.z, upv.z), s.z * dx);
+                    const float t3 = godunov(tmin(tp.z, h[r]), tmin(tp.w, j.w), tmin(umv.w, upv.w), s.w * dx);
+                    bool c0 = t0 < o.x, c1 = t1 < o.y, c2 = t2 < o.z, c3 = t3 < o.w;
+                    float* const dst = tt + (e0[r] + (long long)(a - r) * w.sm);
+                    if (SLOW) {
+                        if (u0w + r > ulast) c0 = c1 = c2 = c3 = false;
+                        const unsigned fm = ((unsigned)(a - wz_lo) < (unsigned)wz_cnt) ? (fzmask >> (r * 4)) & 15u : 0u;
+                        if (fm) {
+                            const long long eb = dst - tt;
+                            if ((fm & 1u) && frozen_bit(frozen, eb + (RK ? 3 : 0))) c0 = false;
+                            if ((fm & 2u) && frozen_bit(frozen, eb + (RK ? 2 : 1))) c1 = false;
+                            if ((fm & 4u) && frozen_bit(frozen, eb + (RK ? 1 : 2))) c2 = false;
+                            if ((fm & 8u) && frozen_bit(frozen, eb + (RK ? 0 : 3))) c3 = false;
+                        }
+                    }
+                    float4 n;
+                    n.x = c0 ? t0 : o.x; n.y = c1 ? t1 : o.y; n.z = c2 ? t2 : o.z; n.w = c3 ? t3 : o.w;
+                    if (c0 || c1 || c2 || c3) {
+                        if (RK) stg_f4_stream(dst, n.w, n.z, n.y, n.x); else stg_f4_stream(dst, n.x, n.y, n.z, n.w);
+                        acc += ((o.x - n.x) + (o.y - n.y)) + ((o.z - n.z) + (o.w - n.w));
+                    }
+                    // lane v0+127 of this plane -> tile V+1
+                    st_mail_if(mv_out + (long long)(a - r) * PU + r, tag_g, n.w, mail_v_out);
+                    if (r == R - 1) {
+                        // last plane of the patch -> warp wu+1 / tile U+1
+                        const int row = a - (R - 1);
+                        if (row >= 0 && row < nrows) {
+                            if (!last_w) {
+                                const unsigned ar = a_uout + (unsigned)(row & (DU - 1)) * 1024;
+                                const unsigned tg = (unsigned)(row + 1);
+                                sts_u4(ar, __float_as_uint(n.x), tg, __float_as_uint(n.y), tg);
+                                sts_u4(ar + 512, __float_as_uint(n.z), tg, __float_as_uint(n.w), tg);
+                            } else if (has_down) {
+                                st_mail2(mu_out + (size_t)row * 128, tag_g, n.x, n.y);
+                                st_mail2(mu_out + (size_t)row * 128 + 64, tag_g, n.z, n.w);
+                            }
+                        }
+                    }
+                    tprev[r] = n;
+                    told[r] = j;
+                }
+                ++a;
+                if (lane == 0) sts_i(a_myprog, a);
+            };
+
+            for (int c = 0; c < nch && !dead; ++c) {
+                const unsigned g = g0 + c;
+                wait_chunk(g);
+                dead = __any_sync(0xffffffffu, dead);
+                if (dead) break;
+                // the slot of chunk c-1 is free: refill it with chunk c + NCH - 1
+                if (lane == 0 && c + NCH - 1 < nch) issue_chunk(c + NCH - 1, g + NCH - 1);
+                cT = (g % NCH) * L::CHB_T;
+                cS = (g % NCH) * L::CHB_S;
+                const bool slow = edge || (wz_cnt > 0 && a + C > wz_lo && a <= wz_hi);
+                if (slow) {
+                    if constexpr (C >= 1) step(IntC<0>{}, IntC<1>{});
+                    if constexpr (C >= 2) step(IntC<1>{}, IntC<1>{});
+                    if constexpr (C >= 3) step(IntC<2>{}, IntC<1>{});
+                    if constexpr (C >= 4) step(IntC<3>{}, IntC<1>{});
+                } else {
+                    if constexpr (C >= 1) step(IntC<0>{}, IntC<0>{});
+                    if constexpr (C >= 2) step(IntC<1>{}, IntC<0>{});
+                    if constexpr (C >= 3) step(IntC<2>{}, IntC<0>{});
+                    if constexpr (C >= 4) step(IntC<3>{}, IntC<0>{});
+                }
+                dead = __any_sync(0xffffffffu, dead);
+            }
+            // a warp that gave up still has copies in flight: they must land before the ring is reused
+            if (dead && lane == 0) {
+                const long long t0 = clock64();
+                for (int c = max(0, issued - NCH); c < issued; ++c) {
+                    const unsigned g = g0 + c;
+                    while (!mbar_test(a_bar + 8 * (g % NCH), (g / NCH) & 1) && clock64() - t0 < spin_cycles) {}
+                }
+            }
+            gc = g0 + nch;
+            if (lane == 0) sts_i(a_myprog, 1 << 29);   // release anybody still waiting for this warp
+            double dacc = (double)acc;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) dacc += __shfl_xor_sync(0xffffffffu, dacc, o);
+            if (lane == 0) p.partial[(size_t)tile * NU + wu] = dacc;
+            if (p.trace && threadIdx.x == 0) p.trace[tile * 8 + 5] = gtime();
+        }
+    }
+}
+
+// ---- host side -----------------------------------------------------------------------------------
+// 3-D map with the plane skew built in: plane z starts (qs -+ 1) rows after plane z-1
+inline CUtensorMap make_tile5_map(const void* base, const Dims& d, bool minus, int bw, int br, int bp) {
+    CUtensorMap m;
+    // "plus" map: row = y + z * (qs + 1) would need negative y for the rows of high planes; the base is moved ni rows
+    // down instead and every y carries +ni (addresses of in-bounds coordinates the kernel uses stay inside the array)
+    if (!minus) base = static_cast<const char*>(base) - (size_t)d.ni * d.kpad * 4;
+    const cuuint64_t gdim[3] = {(cuuint64_t)d.kpad, (cuuint64_t)(d.qs + 2 * d.ni + 64), (cuuint64_t)d.ni};
+    const cuuint64_t gstr[2] = {(cuuint64_t)d.kpad * 4, (cuuint64_t)d.kpad * (cuuint64_t)(minus ? d.qs - 1 : d.qs + 1) * 4};
+    const cuuint32_t box[3] = {(cuuint32_t)bw, (cuuint32_t)br, (cuuint32_t)bp};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult r = tmap_encoder()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base), gdim, gstr, box, estr,
+                                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) throw std::runtime_error("cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
+    return m;
+}
+
+struct Tile5State {
+    unsigned long long* d_mbu = nullptr;
+    unsigned long long* d_mbv = nullptr;
+    double* d_partial = nullptr;
+    int* d_order = nullptr;
+    int mb_rows = 0, mb_tiles = 0, mb_pu = 0;
+    int order_key = -1, ntiles = 0;
+    unsigned serial = 0;
+};
+inline void tile5_free(Tile5State& s) {
+    cudaFree(s.d_mbu); cudaFree(s.d_mbv); cudaFree(s.d_partial); cudaFree(s.d_order);
+    s = Tile5State{};
+}
+
+template <int NU, int R, int C, int NCH, int DU_>
+inline int tile5_launch(TileState& s, Tile5State& s5, const TileOptions& o, int sm_count, const SweepView& w, const Dims& d,
+                        float* tt, const float* slo, const uint32_t* frozen, const FrozenBox& fb, float dx, double* d_change,
+                        cudaStream_t st) {
+    using L = Tile5Layout<NU, R, C, NCH, DU_>;
+    constexpr int PU = L::PU;
+    Tile5Params p;
+    p.w = w; p.d = d; p.fb = fb;
+    p.nV = (d.kpad + 127) / 128;
+    p.nU = (w.nu + PU - 1) / PU;
+    p.ntiles = p.nU * p.nV;
+    p.spin_limit = o.spin_limit;
+    p.ctrl = s.d_ctrl;
+    static long long* d_trace = nullptr;   // debug only, not thread safe
+    static int trace_cap = 0;
+    const char* trace_path = getenv("TTCR_B200_TRACE");
+    if (trace_path && trace_cap < p.ntiles) {
+        cudaFree(d_trace);
+        TCK(cudaMalloc(&d_trace, (size_t)p.ntiles * 8 * sizeof(long long)));
+        trace_cap = p.ntiles;
+    }
+    p.trace = trace_path ? d_trace : nullptr;
+    const int rows = d.nj + 128 + 2 * Tile5Mail::MARGIN;
+    if (!s5.d_mbu || s5.mb_tiles < p.ntiles || s5.mb_rows != rows || s5.mb_pu != PU) {
+        TCK(cudaStreamSynchronize(st));
+        tile5_free(s5);
+        s5.mb_rows = rows; s5.mb_tiles = p.ntiles; s5.mb_pu = PU;
+        const size_t nu = (size_t)s5.mb_tiles * s5.mb_rows * 128, nv = (size_t)s5.mb_tiles * s5.mb_rows * PU;
+        TCK(cudaMalloc(&s5.d_mbu, nu * 8));
+        TCK(cudaMalloc(&s5.d_mbv, nv * 8));
+        TCK(cudaMalloc(&s5.d_partial, (size_t)p.ntiles * NU * sizeof(double)));
+        TCK(cudaMalloc(&s5.d_order, (size_t)p.ntiles * sizeof(int)));
+        TCK(cudaMemsetAsync(s5.d_mbu, 0, nu * 8, st));
+        TCK(cudaMemsetAsync(s5.d_mbv, 0, nv * 8, st));
+        s5.serial = 0;
+        s5.order_key = -1;
+    }
+    Tile5Mail mail;
+    mail.u = s5.d_mbu; mail.v = s5.d_mbv; mail.rows = s5.mb_rows;
+    mail.serial = ++s5.serial;
+    if (mail.serial == 0) {   // wrapped: clear the tags once every 2^32 sweeps
+        TCK(cudaMemsetAsync(s5.d_mbu, 0, (size_t)s5.mb_tiles * s5.mb_rows * 128 * 8, st));
+        TCK(cudaMemsetAsync(s5.d_mbv, 0, (size_t)s5.mb_tiles * s5.mb_rows * PU * 8, st));
+        mail.serial = s5.serial = 1;
+    }
+    p.order = s5.d_order; p.partial = s5.d_partial;
+    const int key = 5000000 + PU * 100000 + w.vlo;   // the order depends on the tile height and on where the lanes start
+    if (s5.order_key != key || s5.ntiles != p.ntiles) {
+        // ticket order: a linear extension of (U-1,V) < (U,V), (U,V-1) < (U,V), sorted by estimated start time
+        std::vector<std::pair<long long, int>> k(p.ntiles);
+        const long long lag_u = PU + 4;
+        for (int U = 0; U < p.nU; ++U)
+            for (int V = 0; V < p.nV; ++V) {
+                const int va = std::max(V * 128, w.vlo);
+                k[U * p.nV + V] = {U * lag_u + (long long)(va - w.joff), U * p.nV + V};
+            }
+        std::stable_sort(k.begin(), k.end());
+        std::vector<int> order(p.ntiles);
+        for (int i = 0; i < p.ntiles; ++i) order[i] = k[i].second;
+        TCK(cudaMemcpyAsync(s5.d_order, order.data(), p.ntiles * sizeof(int), cudaMemcpyHostToDevice, st));
+        TCK(cudaStreamSynchronize(st));
+        s5.order_key = key;
+        s5.ntiles = p.ntiles;
+    }
+    struct MapKey { const void* a; int minus, bw, br, bp, kpad, qs, ni; CUtensorMap m; };
+    static thread_local std::vector<MapKey> cache;
+    auto get_map = [&](const void* a, bool minus, int bw, int br, int bp) -> CUtensorMap {
+        for (auto& e : cache)
+            if (e.a == a && e.minus == (int)minus && e.bw == bw && e.br == br && e.bp == bp && e.kpad == d.kpad && e.qs == d.qs && e.ni == d.ni)
+                return e.m;
+        if (cache.size() > 96) cache.clear();
+        cache.push_back({a, (int)minus, bw, br, bp, d.kpad, d.qs, d.ni, make_tile5_map(a, d, minus, bw, br, bp)});
+        return cache.back().m;
+    };
+    const bool minus = (w.ri != 0) == (w.rj != 0);
+    const CUtensorMap tmT = get_map(tt, minus, L::TW, C, R + 1);
+    const CUtensorMap tmS = get_map(slo, minus, 128, C, R);
+    TCK(cudaMemsetAsync(s.d_ctrl, 0, sizeof(int), st));
+    // (the four variants share one function-pointer type, so they are set up together, once)
+    static int occ_cache = 0;
+    if (!occ_cache) {
+        auto prep = [&](auto kern) {
+            int occ = 0;
+            TCK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::BYTES));
+            TCK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, (NU + 1) * 32, L::BYTES));
+            return occ;
+        };
+        int occ = prep(k_sweep_patch<NU, R, C, NCH, DU_, false, false>);
+        occ = std::min(occ, prep(k_sweep_patch<NU, R, C, NCH, DU_, false, true>));
+        occ = std::min(occ, prep(k_sweep_patch<NU, R, C, NCH, DU_, true, false>));
+        occ = std::min(occ, prep(k_sweep_patch<NU, R, C, NCH, DU_, true, true>));
+        if (occ < 1) throw std::runtime_error("tile5 kernel does not fit on an SM");
+        occ_cache = occ;
+    }
+    int occ = occ_cache;
+    if (o.ctas_per_sm > 0) occ = std::min(occ, o.ctas_per_sm);
+    const int grid = std::min(p.ntiles, occ * sm_count);
+    auto launch = [&](auto kern) { kern<<<grid, (NU + 1) * 32, L::BYTES, st>>>(tmT, tmS, p, mail, tt, frozen, dx); };
+    if (w.rj) {
+        if (w.rk) launch(k_sweep_patch<NU, R, C, NCH, DU_, true, true>); else launch(k_sweep_patch<NU, R, C, NCH, DU_, true, false>);
+    } else {
+        if (w.rk) launch(k_sweep_patch<NU, R, C, NCH, DU_, false, true>); else launch(k_sweep_patch<NU, R, C, NCH, DU_, false, false>);
+    }
+    k_sum_partials<<<1, 256, 0, st>>>(s5.d_partial, p.ntiles * NU, d_change);
+    TCK(cudaMemcpyAsync(s.h_abort, s.d_ctrl + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+    TCK(cudaGetLastError());
+    if (trace_path) {
+        std::vector<long long> h((size_t)p.ntiles * 8);
+        TCK(cudaStreamSynchronize(st));
+        TCK(cudaMemcpy(h.data(), d_trace, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+        FILE* f = fopen(trace_path, "ab");
+        if (f) {
+            const int hdr[4] = {p.ntiles, p.nU, p.nV, PU};
+            fwrite(hdr, sizeof(int), 4, f);
+            fwrite(h.data(), sizeof(long long), h.size(), f);
+            fclose(f);
+        }
+    }
+    return 2;
+}
+
+template <typename T> inline bool tile5_supported(bool) { return false; }
+template <> inline bool tile5_supported<float>(bool weno_stage) { return !weno_stage; }
+
+template <typename T>
+inline int tile5_sweep(TileState&, Tile5State&, const TileOptions&, int, const SweepView&, const Dims&, T*, const T*,
+                       const uint32_t*, const FrozenBox&, T, double*, cudaStream_t) {
+    throw std::runtime_error("tile5 kernel: fp32 only");
+}
+template <>
+inline int tile5_sweep<float>(TileState& s, Tile5State& s5, const TileOptions& o, int sm_count, const SweepView& w,
+                              const Dims& d, float* tt, const float* slo, const uint32_t* frozen, const FrozenBox& fb, float dx,
+                              double* d_change, cudaStream_t st) {
+    if (o.warps >= 8) return tile5_launch<8, 2, 2, 3, 8>(s, s5, o, sm_count, w, d, tt, slo, frozen, fb, dx, d_change, st);
+    if (o.depth <= 4) return tile5_launch<4, 2, 2, 4, 4>(s, s5, o, sm_count, w, d, tt, slo, frozen, fb, dx, d_change, st);
+    return tile5_launch<4, 2, 2, 3, 8>(s, s5, o, sm_count, w, d, tt, slo, frozen, fb, dx, d_change, st);
+}
+
+}  // namespace ttcrb200
