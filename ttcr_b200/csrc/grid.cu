@@ -502,6 +502,7 @@ class Grid final : public GridBase {
                 CK(cudaGetLastError());
                 CK(cudaMemcpyAsync(s.h_change, s.d_change, sizeof(double), cudaMemcpyDeviceToHost, s.stream));
                 CK(cudaStreamSynchronize(s.stream));
+                if (s.tile.h_abort && *s.tile.h_abort) tile5_dump(s.tile5);
                 tile_check(s.tile);
                 const double c = *s.h_change;
                 s.st.last_change = c;

@@ -37,6 +37,10 @@
 #pragma once
 #include "sweep_tile4.cuh"
 
+#ifndef TTCR_T5_TRACE_TILE
+#define TTCR_T5_TRACE_TILE 0
+#endif
+
 namespace ttcrb200 {
 
 struct Tile5Mail {
@@ -57,6 +61,8 @@ struct Tile5Params {
     int* ctrl;
     double* partial;   // [tile][NU]
     long long* trace;
+    int trace_a0, trace_tile;   // per-step clocks: first step and tile of the window (debug)
+    int* dbg;                   // [tile][NU + 2][16]: what every warp was waiting for when a march was given up
 };
 
 constexpr int t5_round128(int x) { return (x + 127) / 128 * 128; }
@@ -133,11 +139,16 @@ __device__ __forceinline__ bool vt_ghost(int vt, int kpad) { return vt >= kpad; 
 __device__ __forceinline__ void stg_f4_stream(float* p, float x, float y, float z, float w) {
     asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
 }
+__device__ __forceinline__ void stg_f4_stream_if(float* p, float x, float y, float z, float w, int on) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %5, 0;\n\t@q st.global.L1::no_allocate.v4.f32 [%0], {%1, %2, %3, %4};\n\t}" ::"l"(p),
+                 "f"(x), "f"(y), "f"(z), "f"(w), "r"(on)
+                 : "memory");
+}
 template <bool REV> __device__ __forceinline__ float4 ord4(float4 v) { return REV ? make_float4(v.w, v.z, v.y, v.x) : v; }
 
 // RJ: the sweep runs the row axis downwards, RK: the lane axis (boxes arrive in memory order).
 template <int NU, int R, int C, int NCH, int DU_, bool RJ, bool RK>
-__global__ void __launch_bounds__((NU + 1) * 32, (NU <= 4 ? 2 : 1)) k_sweep_patch(const __grid_constant__ CUtensorMap tmT,
+__global__ void __launch_bounds__((NU + 2) * 32, (NU <= 4 ? 2 : 1)) k_sweep_patch(const __grid_constant__ CUtensorMap tmT,
                                                                   const __grid_constant__ CUtensorMap tmS, Tile5Params p,
                                                                   Tile5Mail mail, float* __restrict__ tt,
                                                                   const uint32_t* __restrict__ frozen, float dx) {
@@ -171,7 +182,7 @@ __global__ void __launch_bounds__((NU + 1) * 32, (NU <= 4 ? 2 : 1)) k_sweep_patc
             sts_i(a_dead, 0);
         }
         // clear the tags of all rings and the progress counters
-        for (unsigned o = threadIdx.x * 16; o < (unsigned)(L::OFF_BAR - L::OFF_U); o += (NU + 1) * 32 * 16)
+        for (unsigned o = threadIdx.x * 16; o < (unsigned)(L::OFF_BAR - L::OFF_U); o += (NU + 2) * 32 * 16)
             sts_u4(sbase + L::OFF_U + o, 0u, 0u, 0u, 0u);
         if (threadIdx.x < NU) sts_i(a_prog + 4 * threadIdx.x, 0);
         __syncthreads();
@@ -206,6 +217,7 @@ __global__ void __launch_bounds__((NU + 1) * 32, (NU <= 4 ? 2 : 1)) k_sweep_patc
             const unsigned long long* const mu_in = mail.u + ((size_t)(has_u ? tile - p.nV : tile) * mail.rows) * 128 + lane * 2;
             const int pw = lane / R, pr = lane - pw * R;                      // lane < PU: plane (pw, pr)
             const bool vlane = lane < PU;
+            const bool vlive = vlane && u0 + pw * R <= w.nu - 1;             // the warp that owns the plane marches (sends words)
             const unsigned long long* const mv_in =
                 mail.v + ((size_t)(has_v ? tile - 1 : tile) * mail.rows + MG) * PU + lane;
             const unsigned a_vring = sbase + L::OFF_V + pw * L::VRING + pr * 8;
@@ -222,7 +234,7 @@ __global__ void __launch_bounds__((NU + 1) * 32, (NU <= 4 ? 2 : 1)) k_sweep_patc
             auto v_row = [&](int a) { return a - pr - 1 + dmf; };            // row of tile V-1 this lane needs at step a
             auto v_inr = [&](int a) {
                 const int rr = a - pr, rp = rr - 1 + dmf;
-                return has_v && vlane && rr >= 0 && rr < nrows && rp >= 0 && rp < nrows_p;
+                return has_v && vlive && rr >= 0 && rr < nrows && rp >= 0 && rp < nrows_p;
             };
             auto issue = [&](int a, int s) {
                 if (has_u && a < nrows) {
@@ -295,9 +307,78 @@ __global__ void __launch_bounds__((NU + 1) * 32, (NU <= 4 ? 2 : 1)) k_sweep_patc
                         sts_u4(ar + 512, xb.x, tag, xb.z, tag);
                     }
                     dead = __any_sync(0xffffffffu, dead);
+                    if (dead && lane == 0) {
+                        int* const q = p.dbg + ((size_t)tile * (NU + 2) + NU) * 16;
+                        q[0] = 30; q[1] = a; q[2] = lds_i(a_prog0); q[3] = lds_i(a_progl); q[4] = has_u; q[5] = has_v; q[6] = nA; q[7] = nrows;
+                    }
                     if (!dead && a + G < nA) issue(a + G, s);
                 }
             }
+        } else if (warp == NU + 1) {
+            // ================= loader: lane wu feeds the ring of compute warp wu ============================
+            // Box origins in memory coordinates (x: lane, y: row, z: plane); plane p of a box sits at row Y0 -+ p (the
+            // skew is in the tensor map, see make_tile5_map).  T box: local rows cC - r + 1 .. of plane r = 0 .. R
+            // (the "next old row" of every plane at every step of the chunk), S box: local rows cC - r .. of plane
+            // r = 0 .. R-1.  Chunk c may be issued once the warp has finished chunk c - NCH (same ring slot).
+            const int wu = lane;
+            const int u0w = u0 + wu * R;
+            const int nch = (wu < NU && u0w <= w.nu - 1) ? nchunks : 0;
+            const unsigned a_ring = sbase + L::OFF_RING + wu * L::WARP_BYTES;
+            const unsigned a_bar = sbase + L::OFF_BAR + wu * NCH * 8;
+            const bool minus_map = (w.ri != 0) == (w.rj != 0);
+            const int xT = RK ? p.d.kpad - 132 - v0 : v0;
+            const int xS = RK ? p.d.kpad - 128 - v0 : v0;
+            const int zT = w.ri ? p.d.ni - 1 - (u0w + R) : u0w;
+            const int zS = w.ri ? p.d.ni - 1 - (u0w + R - 1) : u0w;
+            const int rT0 = w.ri ? R : 0, rS0 = w.ri ? R - 1 : 0;
+            const int yT0 = RJ ? GUARD + (w.nm - 1) - (m_first - rT0 + C) : GUARD + m_first - rT0 + 1;
+            const int yS0 = RJ ? GUARD + (w.nm - 1) - (m_first - rS0 + C - 1) : GUARD + m_first - rS0;
+            const int yT = minus_map ? yT0 + zT : yT0 - zT + p.d.ni;   // the "plus" map is based ni rows below the array
+            const int yS = minus_map ? yS0 + zS : yS0 - zS + p.d.ni;
+            const int dyc = RJ ? -C : C;                       // rows per chunk in memory direction
+            const unsigned a_wprog = a_prog + 4 * (wu < NU ? wu : 0);
+            long long t0 = clock64();
+            bool dead = false;
+            int c = 0;
+            while (c < nch) {
+                if (c < NCH || lds_i(a_wprog) >= (c - NCH + 1) * C) {
+                    const unsigned g = gc + (unsigned)c;
+                    const unsigned slot = g % NCH;
+                    const unsigned mb = a_bar + 8 * slot;
+                    mbar_expect_tx(mb, (R + 1) * L::TPL + R * L::SPL);
+                    tma_load_3d(a_ring + slot * L::CHB_T, &tmT, xT, yT + c * dyc, zT, mb);
+                    tma_load_3d(a_ring + NCH * L::CHB_T + slot * L::CHB_S, &tmS, xS, yS + c * dyc, zS, mb);
+                    ++c;
+                    t0 = clock64();
+                } else {
+                    if (lds_i(a_dead)) { dead = true; }
+                    else if (clock64() - t0 > spin_cycles) dead = true;
+                    if (dead) {
+                        int* const q = p.dbg + ((size_t)tile * (NU + 2) + NU + 1) * 16 + (wu & 1) * 8;
+                        const int pg = lds_i(a_wprog);
+                        const unsigned ur = sbase + L::OFF_U + wu * L::URING + (unsigned)(pg & (DU - 1)) * 1024;
+                        q[0] = 50; q[1] = c; q[2] = pg; q[3] = wu; q[4] = lds_i(ur + 4);          // tag of lane 0, word 0
+                        q[5] = lds_i(ur + 16 * 13 + 4); q[6] = lds_i(ur + 512 + 16 * 31 + 12);    // lane 13 word 0, lane 31 word 3
+                        q[7] = lds_i(sbase + L::OFF_V + wu * L::VRING + (unsigned)(pg & (DV - 1)) * (R * 8) + 4);
+                    }
+                    if (dead) {
+                        if (atomicCAS(&p.ctrl[1], 0, 50) == 0) { p.ctrl[2] = tile; p.ctrl[3] = c; p.ctrl[4] = lds_i(a_wprog); p.ctrl[5] = wu; }
+                        sts_i(a_dead, 1);
+                        dead = true;
+                        break;
+                    }
+                }
+            }
+            // a march that was given up may leave copies in flight: they must land before the CTA goes on
+            if (dead) {
+                const long long t1 = clock64();
+                for (int cc = max(0, c - NCH); cc < c; ++cc) {
+                    const unsigned g = gc + (unsigned)cc;
+                    while (!mbar_test(a_bar + 8 * (g % NCH), (g / NCH) & 1) && clock64() - t1 < spin_cycles) {}
+                }
+            }
+            gc += (unsigned)nch;
+            __syncwarp();
         } else {
             // ================= compute warps ==============================================================
             const int wu = warp;
@@ -335,28 +416,6 @@ __global__ void __launch_bounds__((NU + 1) * 32, (NU <= 4 ? 2 : 1)) k_sweep_patc
                 e0[r] = w.base + (long long)min(u0w + r, ulast) * w.su + (long long)m_first * w.sm + (long long)vt * w.sv - (RK ? 3 : 0);
             unsigned long long* const mu_out = mail.u + ((size_t)tile * mail.rows) * 128 + lane * 2;
             unsigned long long* const mv_out = mail.v + ((size_t)tile * mail.rows + MG) * PU + wu * R;
-            // ---- TMA box origins (memory coordinates), see the header: plane p of a box sits at row Y0 -+ p
-            const bool minus_map = (w.ri != 0) == (w.rj != 0);
-            const int xT = RK ? p.d.kpad - 132 - v0 : v0;
-            const int xS = RK ? p.d.kpad - 128 - v0 : v0;
-            const int zT = w.ri ? p.d.ni - 1 - (u0w + R) : u0w;
-            const int zS = w.ri ? p.d.ni - 1 - (u0w + R - 1) : u0w;
-            // first memory row of box plane 0 for chunk 0 (T: rows cC - r + 1 .., S: rows cC - r ..)
-            const int rT0 = w.ri ? R : 0, rS0 = w.ri ? R - 1 : 0;
-            const int yT0 = RJ ? GUARD + (w.nm - 1) - (m_first - rT0 + C) : GUARD + m_first - rT0 + 1;
-            const int yS0 = RJ ? GUARD + (w.nm - 1) - (m_first - rS0 + C - 1) : GUARD + m_first - rS0;
-            const int yT = minus_map ? yT0 + zT : yT0 - zT + p.d.ni;   // the "plus" map is based ni rows below the array
-            const int yS = minus_map ? yS0 + zS : yS0 - zS + p.d.ni;
-            const int dyc = RJ ? -C : C;                       // rows per chunk in memory direction
-            int issued = 0;
-            auto issue_chunk = [&](int c, unsigned g) {        // chunk c of this tile -> ring slot g % NCH
-                const unsigned slot = g % NCH;
-                ++issued;
-                const unsigned mb = a_bar + 8 * slot;
-                mbar_expect_tx(mb, (R + 1) * L::TPL + R * L::SPL);
-                tma_load_3d(a_ring + slot * L::CHB_T, &tmT, xT, yT + c * dyc, zT, mb);
-                tma_load_3d(a_ring + NCH * L::CHB_T + slot * L::CHB_S, &tmS, xS, yS + c * dyc, zS, mb);
-            };
             // ---- frozen nodes: macro-steps in which this warp may touch one, and which patch elements
             unsigned fzmask = 0;   // bit r*4+e: element may be frozen (plane and lane inside the source box)
             int wz_lo = 1 << 30, wz_hi = -(1 << 30);
@@ -400,12 +459,14 @@ __global__ void __launch_bounds__((NU + 1) * 32, (NU <= 4 ? 2 : 1)) k_sweep_patc
                     if (lds_i(a_dead)) { dead = true; break; }
                     if (clock64() - t0 > spin_cycles) { give_up(40, (int)g, 0); dead = true; break; }
                 }
+                if (dead && lane == 0) {
+                    int* const q = p.dbg + ((size_t)tile * (NU + 2) + wu) * 16;
+                    q[0] = 40; q[1] = (int)g; q[2] = (int)gc;
+                }
             };
 
             // ---- prologue: fill the ring, load the old values of local row 0
             const unsigned g0 = gc;
-            if (lane == 0)
-                for (int c = 0; c < NCH - 1 && c < nch; ++c) issue_chunk(c, g0 + c);
             float4 told[R], tprev[R];
 #pragma unroll
             for (int r = 0; r < R; ++r) {
@@ -426,7 +487,11 @@ __global__ void __launch_bounds__((NU + 1) * 32, (NU <= 4 ? 2 : 1)) k_sweep_patc
                 constexpr int I = decltype(IC)::value;
                 constexpr bool SLOW = decltype(SLOWC)::value != 0;
                 constexpr int RT = (RJ ? C - 1 - I : I) * L::TROW, RS = (RJ ? C - 1 - I : I) * L::SROW;
-                // ---- loads of old values (all independent of other warps)
+                long long* const tr = (p.trace && tile == p.trace_tile && lane == 0 && a >= p.trace_a0 && a < p.trace_a0 + 128 && wu < 8)
+                                          ? p.trace + (size_t)p.ntiles * 8 + ((wu * 128 + (a - p.trace_a0)) * 4) : nullptr;
+                if (tr) tr[0] = clock64();
+                // ---- (1) every shared-memory load of the step, back to back: old values (TMA ring) and the words of
+                //          the neighbours (rings): (u0w-1, a, .), lane v0-1 of every plane, progress of warp wu+1
                 float4 jp[R], sl[R], up;
                 float h[R];
 #pragma unroll
@@ -434,59 +499,65 @@ __global__ void __launch_bounds__((NU + 1) * 32, (NU <= 4 ? 2 : 1)) k_sweep_patc
                     jp[r] = ord4<RK>(lds_f4(aT[r] + cT + RT));
                     h[r] = lds_f(aT[r] + cT + RT + dH);
                     sl[r] = ord4<RK>(lds_f4(aS[r] + cS + RS));
-                    if (kill) h[r] = MAXV;
                 }
                 up = ord4<RK>(lds_f4(aT[R] + cT + RT));
-                // ---- new values from the neighbours: (u0w-1, a, .) and lane v0-1 of every plane
                 const unsigned tag = (unsigned)(a + 1);
-                float4 um = make_float4(MAXV, MAXV, MAXV, MAXV);
-                if (a < nrows) {
-                    const unsigned ar = a_uin + (unsigned)(a & (DU - 1)) * 1024;
-                    uint4 xa = lds_u4(ar), xb = lds_u4(ar + 512);
-                    if (((xa.y ^ tag) | (xa.w ^ tag) | (xb.y ^ tag) | (xb.w ^ tag)) != 0) {
-                        const long long t0 = clock64();
-                        for (;;) {
-                            xa = lds_u4(ar); xb = lds_u4(ar + 512);
-                            if (((xa.y ^ tag) | (xa.w ^ tag) | (xb.y ^ tag) | (xb.w ^ tag)) == 0) break;
-                            if (lds_i(a_dead)) { dead = true; break; }
-                            if (clock64() - t0 > spin_cycles) { give_up(41, 0, a); dead = true; break; }
-                        }
-                    }
-                    um = make_float4(__uint_as_float(xa.x), __uint_as_float(xa.z), __uint_as_float(xb.x), __uint_as_float(xb.z));
-                }
-                float vm[R];
-                {
-                    const unsigned av = a_vin + (unsigned)(a & (DV - 1)) * (R * 8);
+                const unsigned ar = a_uin + (unsigned)(a & (DU - 1)) * 1024;
+                const unsigned av = a_vin + (unsigned)(a & (DV - 1)) * (R * 8);
+                const bool need_u = a < nrows;
+                const int nx_need = last_w ? -(1 << 30) : a - (R - 1) - DU + 1;   // the slot this step overwrites has been read
+                uint4 xa = lds_u4(ar), xb = lds_u4(ar + 512);
+                uint2 xv[R];
 #pragma unroll
-                    for (int r = 0; r < R; ++r) {
-                        uint2 x = lds_u2(av + r * 8);
-                        if (x.y != tag) {
-                            const long long t0 = clock64();
-                            for (;;) {
-                                x = lds_u2(av + r * 8);
-                                if (x.y == tag) break;
-                                if (lds_i(a_dead)) { dead = true; break; }
-                                if (clock64() - t0 > spin_cycles) { give_up(42, r, a); dead = true; break; }
-                            }
-                        }
-                        vm[r] = __uint_as_float(x.x);
-                    }
-                }
+                for (int r = 0; r < R; ++r) xv[r] = lds_u2(av + r * 8);
+                int nxp = lds_i(a_nxprog);
+                // ---- (2) lane l-1's previous result
                 float km0[R];
 #pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    km0[r] = __shfl_up_sync(0xffffffffu, tprev[r].w, 1);
-                    if (lane == 0) km0[r] = vm[r];
-                }
-                // ---- the ring slot of warp wu+1 that this step overwrites has been read
-                if (!last_w && lds_i(a_nxprog) < a - (R - 1) - DU + 1) {
+                for (int r = 0; r < R; ++r) km0[r] = __shfl_up_sync(0xffffffffu, tprev[r].w, 1);
+                // ---- (3) one test for everything that comes from other warps
+                auto stale = [&]() {
+                    unsigned bad = need_u ? ((xa.y ^ tag) | (xa.w ^ tag) | (xb.y ^ tag) | (xb.w ^ tag)) : 0u;
+#pragma unroll
+                    for (int r = 0; r < R; ++r) bad |= xv[r].y ^ tag;
+                    if (nxp < nx_need) bad |= 1u;
+                    return bad != 0;
+                };
+                if (stale()) {
                     const long long t0 = clock64();
-                    while (lds_i(a_nxprog) < a - (R - 1) - DU + 1) {
+                    for (;;) {
+                        xa = lds_u4(ar); xb = lds_u4(ar + 512);
+#pragma unroll
+                        for (int r = 0; r < R; ++r) xv[r] = lds_u2(av + r * 8);
+                        nxp = lds_i(a_nxprog);
+                        if (!stale()) break;
                         if (lds_i(a_dead)) { dead = true; break; }
-                        if (clock64() - t0 > spin_cycles) { give_up(43, 0, a); dead = true; break; }
+                        if (clock64() - t0 > spin_cycles) { give_up(41, nxp, a); dead = true; break; }
+                    }
+                    if (dead) {
+                        int* const q = p.dbg + ((size_t)tile * (NU + 2) + wu) * 16;
+                        if (lane == 0 || lane == 31) {
+                            int* const ql = q + (lane ? 8 : 0);
+                            ql[0] = 41; ql[1] = a; ql[2] = need_u ? (int)xa.y : -1; ql[3] = need_u ? (int)xb.w : -1; ql[4] = (int)xv[0].y; ql[5] = nxp;
+                        }
+                        atomicOr((unsigned*)&q[6], 1u << lane);          // lanes that were spinning
+                        atomicMax(&q[7], a + 1);                          // ... and their step
+                        atomicMax(&q[14], 1000 - a);
+                        q[8] = 41;
+                        atomicOr((unsigned*)&q[15], (need_u && ((xa.y ^ tag) | (xa.w ^ tag) | (xb.y ^ tag) | (xb.w ^ tag))) ? 1u << lane : 0u);
                     }
                 }
-                // ---- update, last plane first (plane r reads the previous-step result of plane r-1)
+                if (tr) tr[1] = clock64();
+                float4 um = make_float4(__uint_as_float(xa.x), __uint_as_float(xa.z), __uint_as_float(xb.x), __uint_as_float(xb.z));
+                if (!need_u) um = make_float4(MAXV, MAXV, MAXV, MAXV);
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    if (lane == 0) km0[r] = __uint_as_float(xv[r].x);
+                    if (kill) h[r] = MAXV;
+                }
+                if (tr) tr[2] = clock64();
+                // ---- (4) update, last plane first (plane r reads the previous-step result of plane r-1); branch free
+                float4 nlast;
 #pragma unroll
                 for (int r = R - 1; r >= 0; --r) {
                     float4 upv = (r == R - 1) ? up : jp[r + 1 < R ? r + 1 : r];
@@ -514,31 +585,35 @@ __global__ void __launch_bounds__((NU + 1) * 32, (NU <= 4 ? 2 : 1)) k_sweep_patc
                     }
                     float4 n;
                     n.x = c0 ? t0 : o.x; n.y = c1 ? t1 : o.y; n.z = c2 ? t2 : o.z; n.w = c3 ? t3 : o.w;
-                    if (c0 || c1 || c2 || c3) {
-                        if (RK) stg_f4_stream(dst, n.w, n.z, n.y, n.x); else stg_f4_stream(dst, n.x, n.y, n.z, n.w);
-                        acc += ((o.x - n.x) + (o.y - n.y)) + ((o.z - n.z) + (o.w - n.w));
-                    }
+                    const int ch = (c0 || c1 || c2 || c3) ? 1 : 0;
+                    if (RK) stg_f4_stream_if(dst, n.w, n.z, n.y, n.x, ch); else stg_f4_stream_if(dst, n.x, n.y, n.z, n.w, ch);
+                    acc += ((o.x - n.x) + (o.y - n.y)) + ((o.z - n.z) + (o.w - n.w));
                     // lane v0+127 of this plane -> tile V+1
                     st_mail_if(mv_out + (long long)(a - r) * PU + r, tag_g, n.w, mail_v_out);
-                    if (r == R - 1) {
-                        // last plane of the patch -> warp wu+1 / tile U+1
-                        const int row = a - (R - 1);
-                        if (row >= 0 && row < nrows) {
-                            if (!last_w) {
-                                const unsigned ar = a_uout + (unsigned)(row & (DU - 1)) * 1024;
-                                const unsigned tg = (unsigned)(row + 1);
-                                sts_u4(ar, __float_as_uint(n.x), tg, __float_as_uint(n.y), tg);
-                                sts_u4(ar + 512, __float_as_uint(n.z), tg, __float_as_uint(n.w), tg);
-                            } else if (has_down) {
-                                st_mail2(mu_out + (size_t)row * 128, tag_g, n.x, n.y);
-                                st_mail2(mu_out + (size_t)row * 128 + 64, tag_g, n.z, n.w);
-                            }
-                        }
-                    }
+                    if (r == R - 1) nlast = n;
                     tprev[r] = n;
                     told[r] = j;
                 }
+                // ---- (5) last plane of the patch -> warp wu+1 / tile U+1
+                {
+                    const int row = a - (R - 1);
+                    if (row >= 0 && row < nrows) {
+                        if (!last_w) {
+                            const unsigned ao = a_uout + (unsigned)(row & (DU - 1)) * 1024;
+                            const unsigned tg = (unsigned)(row + 1);
+                            sts_u4(ao, __float_as_uint(nlast.x), tg, __float_as_uint(nlast.y), tg);
+                            sts_u4(ao + 512, __float_as_uint(nlast.z), tg, __float_as_uint(nlast.w), tg);
+                        } else if (has_down) {
+                            st_mail2(mu_out + (size_t)row * 128, tag_g, nlast.x, nlast.y);
+                            st_mail2(mu_out + (size_t)row * 128 + 64, tag_g, nlast.z, nlast.w);
+                        }
+                    }
+                }
+                if (tr) tr[3] = clock64();
                 ++a;
+                // every lane is done with the ring slots of this step before the step is reported complete (lanes may have
+                // left the wait above at different times; the producers reuse a slot as soon as they see the report)
+                __syncwarp();
                 if (lane == 0) sts_i(a_myprog, a);
             };
 
@@ -547,8 +622,6 @@ __global__ void __launch_bounds__((NU + 1) * 32, (NU <= 4 ? 2 : 1)) k_sweep_patc
                 wait_chunk(g);
                 dead = __any_sync(0xffffffffu, dead);
                 if (dead) break;
-                // the slot of chunk c-1 is free: refill it with chunk c + NCH - 1
-                if (lane == 0 && c + NCH - 1 < nch) issue_chunk(c + NCH - 1, g + NCH - 1);
                 cT = (g % NCH) * L::CHB_T;
                 cS = (g % NCH) * L::CHB_S;
                 const bool slow = edge || (wz_cnt > 0 && a + C > wz_lo && a <= wz_hi);
@@ -564,13 +637,11 @@ __global__ void __launch_bounds__((NU + 1) * 32, (NU <= 4 ? 2 : 1)) k_sweep_patc
                     if constexpr (C >= 4) step(IntC<3>{}, IntC<0>{});
                 }
                 dead = __any_sync(0xffffffffu, dead);
-            }
-            // a warp that gave up still has copies in flight: they must land before the ring is reused
-            if (dead && lane == 0) {
-                const long long t0 = clock64();
-                for (int c = max(0, issued - NCH); c < issued; ++c) {
-                    const unsigned g = g0 + c;
-                    while (!mbar_test(a_bar + 8 * (g % NCH), (g / NCH) & 1) && clock64() - t0 < spin_cycles) {}
+                if (p.trace && threadIdx.x == 0) {
+                    const int q = nrows / 4;
+                    if (a - C < q && a >= q) p.trace[tile * 8 + 2] = gtime();
+                    if (a - C < 2 * q && a >= 2 * q) p.trace[tile * 8 + 3] = gtime();
+                    if (a - C < 3 * q && a >= 3 * q) p.trace[tile * 8 + 4] = gtime();
                 }
             }
             gc = g0 + nch;
@@ -607,12 +678,14 @@ struct Tile5State {
     unsigned long long* d_mbv = nullptr;
     double* d_partial = nullptr;
     int* d_order = nullptr;
+    int* d_dbg = nullptr;
+    int dbg_n = 0;
     int mb_rows = 0, mb_tiles = 0, mb_pu = 0;
     int order_key = -1, ntiles = 0;
     unsigned serial = 0;
 };
 inline void tile5_free(Tile5State& s) {
-    cudaFree(s.d_mbu); cudaFree(s.d_mbv); cudaFree(s.d_partial); cudaFree(s.d_order);
+    cudaFree(s.d_mbu); cudaFree(s.d_mbv); cudaFree(s.d_partial); cudaFree(s.d_order); cudaFree(s.d_dbg);
     s = Tile5State{};
 }
 
@@ -634,10 +707,12 @@ inline int tile5_launch(TileState& s, Tile5State& s5, const TileOptions& o, int 
     const char* trace_path = getenv("TTCR_B200_TRACE");
     if (trace_path && trace_cap < p.ntiles) {
         cudaFree(d_trace);
-        TCK(cudaMalloc(&d_trace, (size_t)p.ntiles * 8 * sizeof(long long)));
+        TCK(cudaMalloc(&d_trace, ((size_t)p.ntiles * 8 + 8192) * sizeof(long long)));
         trace_cap = p.ntiles;
     }
     p.trace = trace_path ? d_trace : nullptr;
+    p.trace_a0 = getenv("TTCR_B200_TRACE_A0") ? atoi(getenv("TTCR_B200_TRACE_A0")) : 200;
+    p.trace_tile = getenv("TTCR_B200_TRACE_TILE") ? atoi(getenv("TTCR_B200_TRACE_TILE")) : 0;
     const int rows = d.nj + 128 + 2 * Tile5Mail::MARGIN;
     if (!s5.d_mbu || s5.mb_tiles < p.ntiles || s5.mb_rows != rows || s5.mb_pu != PU) {
         TCK(cudaStreamSynchronize(st));
@@ -648,6 +723,9 @@ inline int tile5_launch(TileState& s, Tile5State& s5, const TileOptions& o, int 
         TCK(cudaMalloc(&s5.d_mbv, nv * 8));
         TCK(cudaMalloc(&s5.d_partial, (size_t)p.ntiles * NU * sizeof(double)));
         TCK(cudaMalloc(&s5.d_order, (size_t)p.ntiles * sizeof(int)));
+        s5.dbg_n = p.ntiles * (NU + 2) * 16;
+        TCK(cudaMalloc(&s5.d_dbg, (size_t)s5.dbg_n * sizeof(int)));
+        TCK(cudaMemsetAsync(s5.d_dbg, 0, (size_t)s5.dbg_n * sizeof(int), st));
         TCK(cudaMemsetAsync(s5.d_mbu, 0, nu * 8, st));
         TCK(cudaMemsetAsync(s5.d_mbv, 0, nv * 8, st));
         s5.serial = 0;
@@ -661,7 +739,7 @@ inline int tile5_launch(TileState& s, Tile5State& s5, const TileOptions& o, int 
         TCK(cudaMemsetAsync(s5.d_mbv, 0, (size_t)s5.mb_tiles * s5.mb_rows * PU * 8, st));
         mail.serial = s5.serial = 1;
     }
-    p.order = s5.d_order; p.partial = s5.d_partial;
+    p.order = s5.d_order; p.partial = s5.d_partial; p.dbg = s5.d_dbg;
     const int key = 5000000 + PU * 100000 + w.vlo;   // the order depends on the tile height and on where the lanes start
     if (s5.order_key != key || s5.ntiles != p.ntiles) {
         // ticket order: a linear extension of (U-1,V) < (U,V), (U,V-1) < (U,V), sorted by estimated start time
@@ -700,7 +778,7 @@ inline int tile5_launch(TileState& s, Tile5State& s5, const TileOptions& o, int 
         auto prep = [&](auto kern) {
             int occ = 0;
             TCK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::BYTES));
-            TCK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, (NU + 1) * 32, L::BYTES));
+            TCK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, (NU + 2) * 32, L::BYTES));
             return occ;
         };
         int occ = prep(k_sweep_patch<NU, R, C, NCH, DU_, false, false>);
@@ -713,7 +791,7 @@ inline int tile5_launch(TileState& s, Tile5State& s5, const TileOptions& o, int 
     int occ = occ_cache;
     if (o.ctas_per_sm > 0) occ = std::min(occ, o.ctas_per_sm);
     const int grid = std::min(p.ntiles, occ * sm_count);
-    auto launch = [&](auto kern) { kern<<<grid, (NU + 1) * 32, L::BYTES, st>>>(tmT, tmS, p, mail, tt, frozen, dx); };
+    auto launch = [&](auto kern) { kern<<<grid, (NU + 2) * 32, L::BYTES, st>>>(tmT, tmS, p, mail, tt, frozen, dx); };
     if (w.rj) {
         if (w.rk) launch(k_sweep_patch<NU, R, C, NCH, DU_, true, true>); else launch(k_sweep_patch<NU, R, C, NCH, DU_, true, false>);
     } else {
@@ -723,18 +801,33 @@ inline int tile5_launch(TileState& s, Tile5State& s5, const TileOptions& o, int 
     TCK(cudaMemcpyAsync(s.h_abort, s.d_ctrl + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
     TCK(cudaGetLastError());
     if (trace_path) {
-        std::vector<long long> h((size_t)p.ntiles * 8);
+        std::vector<long long> h((size_t)p.ntiles * 8 + 8192);
         TCK(cudaStreamSynchronize(st));
         TCK(cudaMemcpy(h.data(), d_trace, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
         FILE* f = fopen(trace_path, "ab");
         if (f) {
             const int hdr[4] = {p.ntiles, p.nU, p.nV, PU};
             fwrite(hdr, sizeof(int), 4, f);
-            fwrite(h.data(), sizeof(long long), h.size(), f);
+            fwrite(h.data(), sizeof(long long), (size_t)p.ntiles * 8, f);
             fclose(f);
+        }
+        if (const char* sp = getenv("TTCR_B200_TRACE_STEPS")) {   // per-step clocks of one tile (steps 200..327), 4 stamps per step
+            FILE* g = fopen(sp, "ab");
+            if (g) { fwrite(h.data() + (size_t)p.ntiles * 8, sizeof(long long), 8192, g); fclose(g); }
         }
     }
     return 2;
+}
+
+// debugging aid (TTCR_B200_DEBUG=1): after an abort, print what every warp was waiting for
+inline void tile5_dump(Tile5State& s5) {
+    if (!s5.d_dbg || !getenv("TTCR_B200_DEBUG")) return;
+    std::vector<int> h(s5.dbg_n);
+    cudaMemcpy(h.data(), s5.d_dbg, h.size() * sizeof(int), cudaMemcpyDeviceToHost);
+    for (int i = 0; i + 8 <= s5.dbg_n; i += 8)
+        if (h[i])
+            fprintf(stderr, "t5dbg slot %d (tile,warp = slot/16): why %d | %d %d %d %d %d %d %d\n", i / 8, h[i], h[i + 1], h[i + 2], h[i + 3],
+                    h[i + 4], h[i + 5], h[i + 6], h[i + 7]);
 }
 
 template <typename T> inline bool tile5_supported(bool) { return false; }
@@ -749,9 +842,11 @@ template <>
 inline int tile5_sweep<float>(TileState& s, Tile5State& s5, const TileOptions& o, int sm_count, const SweepView& w,
                               const Dims& d, float* tt, const float* slo, const uint32_t* frozen, const FrozenBox& fb, float dx,
                               double* d_change, cudaStream_t st) {
-    if (o.warps >= 8) return tile5_launch<8, 2, 2, 3, 8>(s, s5, o, sm_count, w, d, tt, slo, frozen, fb, dx, d_change, st);
-    if (o.depth <= 4) return tile5_launch<4, 2, 2, 4, 4>(s, s5, o, sm_count, w, d, tt, slo, frozen, fb, dx, d_change, st);
-    return tile5_launch<4, 2, 2, 3, 8>(s, s5, o, sm_count, w, d, tt, slo, frozen, fb, dx, d_change, st);
+    // <compute warps, planes per thread, steps per TMA chunk, ring slots, rows per U ring>
+    if (o.rows >= 2) return tile5_launch<4, 2, 2, 3, 8>(s, s5, o, sm_count, w, d, tt, slo, frozen, fb, dx, d_change, st);
+    if (o.warps <= 4) return tile5_launch<4, 1, 4, 3, 8>(s, s5, o, sm_count, w, d, tt, slo, frozen, fb, dx, d_change, st);
+    if (o.depth >= 16) return tile5_launch<8, 1, 4, 3, 8>(s, s5, o, sm_count, w, d, tt, slo, frozen, fb, dx, d_change, st);
+    return tile5_launch<8, 1, 4, 3, 4>(s, s5, o, sm_count, w, d, tt, slo, frozen, fb, dx, d_change, st);
 }
 
 }  // namespace ttcrb200
