@@ -37,8 +37,11 @@
 #pragma once
 #include "sweep_tile4.cuh"
 
-#ifndef TTCR_T5_TRACE_TILE
-#define TTCR_T5_TRACE_TILE 0
+#ifndef TTCR_T5_CLOCK
+#define TTCR_T5_CLOCK clock64   // gtime: globaltimer (ns, comparable across SMs, coarse)
+#endif
+#ifndef TTCR_T5_STEP_TRACE
+#define TTCR_T5_STEP_TRACE 0   // 1: per-step clocks of one tile (TTCR_B200_TRACE_STEPS); costs ~20 % of a step
 #endif
 
 namespace ttcrb200 {
@@ -155,7 +158,7 @@ __global__ void __launch_bounds__((NU + 2) * 32, (NU <= 4 ? 2 : 1)) k_sweep_patc
     using L = Tile5Layout<NU, R, C, NCH, DU_>;
     constexpr int PU = L::PU, DU = L::DU, DV = L::DV;
     constexpr int MG = Tile5Mail::MARGIN;
-    constexpr int G = 2;   // rows of mailbox loads the importer keeps in flight
+    constexpr int G = 2;   // rows of mailbox loads the importer keeps in flight (deeper = more stale polls = larger lag)
     extern __shared__ __align__(128) unsigned char smem_raw[];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -259,6 +262,7 @@ __global__ void __launch_bounds__((NU + 2) * 32, (NU <= 4 ? 2 : 1)) k_sweep_patc
                     {
                         const long long t0 = clock64();
                         while (lds_i(a_prog0) < a - DU + 1 || lds_i(a_progl) < a - DV + 1) {
+                            __nanosleep(100);
                             if (lds_i(a_dead)) { dead = true; break; }
                             if (clock64() - t0 > spin_cycles) { give_up(30, a); dead = true; break; }
                         }
@@ -351,6 +355,7 @@ __global__ void __launch_bounds__((NU + 2) * 32, (NU <= 4 ? 2 : 1)) k_sweep_patc
                     ++c;
                     t0 = clock64();
                 } else {
+                    __nanosleep(200);   // a chunk is C steps of slack: do not steal issue slots from the compute warps
                     if (lds_i(a_dead)) { dead = true; }
                     else if (clock64() - t0 > spin_cycles) dead = true;
                     if (dead) {
@@ -446,6 +451,8 @@ __global__ void __launch_bounds__((NU + 2) * 32, (NU <= 4 ? 2 : 1)) k_sweep_patc
             }
             const int wz_cnt = wz_hi >= wz_lo ? wz_hi - wz_lo + 1 : 0;
 
+            const bool trace_on = p.trace && tile == p.trace_tile && lane == 0 && wu < 8;
+            (void)trace_on;
             bool dead = false;
             auto give_up = [&](int why, int x, int a) {
                 if (atomicCAS(&p.ctrl[1], 0, why) == 0) { p.ctrl[2] = tile; p.ctrl[3] = x; p.ctrl[4] = a; p.ctrl[5] = wu; p.ctrl[6] = lane; }
@@ -480,27 +487,34 @@ __global__ void __launch_bounds__((NU + 2) * 32, (NU <= 4 ? 2 : 1)) k_sweep_patc
             float acc = 0.f;
             if (p.trace && threadIdx.x == 0) p.trace[tile * 8 + 1] = gtime();
 
-            unsigned cT = 0, cS = 0;   // byte offsets of the current chunk slot
-            int a = 0;
-
-            auto step = [&](auto IC, auto SLOWC) {
-                constexpr int I = decltype(IC)::value;
-                constexpr bool SLOW = decltype(SLOWC)::value != 0;
-                constexpr int RT = (RJ ? C - 1 - I : I) * L::TROW, RS = (RJ ? C - 1 - I : I) * L::SROW;
-                long long* const tr = (p.trace && tile == p.trace_tile && lane == 0 && a >= p.trace_a0 && a < p.trace_a0 + 128 && wu < 8)
-                                          ? p.trace + (size_t)p.ntiles * 8 + ((wu * 128 + (a - p.trace_a0)) * 4) : nullptr;
-                if (tr) tr[0] = clock64();
-                // ---- (1) every shared-memory load of the step, back to back: old values (TMA ring) and the words of
-                //          the neighbours (rings): (u0w-1, a, .), lane v0-1 of every plane, progress of warp wu+1
-                float4 jp[R], sl[R], up;
-                float h[R];
+            // old values of the step about to run, loaded one step ahead (software pipeline): the "next old row" of
+            // every plane (jp) with its lane v+4 (h), slowness (sl), and the next old row of plane u0w+R (up)
+            float4 jp[R], sl[R], up;
+            float h[R];
+            auto load_old = [&](unsigned oT, unsigned oS, float4 (&xj)[R], float (&xh)[R], float4 (&xs)[R], float4& xu) {
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
-                    jp[r] = ord4<RK>(lds_f4(aT[r] + cT + RT));
-                    h[r] = lds_f(aT[r] + cT + RT + dH);
-                    sl[r] = ord4<RK>(lds_f4(aS[r] + cS + RS));
+                    xj[r] = ord4<RK>(lds_f4(aT[r] + oT));
+                    xh[r] = lds_f(aT[r] + oT + dH);
+                    xs[r] = ord4<RK>(lds_f4(aS[r] + oS));
                 }
-                up = ord4<RK>(lds_f4(aT[R] + cT + RT));
+                xu = ord4<RK>(lds_f4(aT[R] + oT));
+            };
+            unsigned cT = 0, cS = 0;   // byte offsets of the current chunk slot
+            int a = 0;
+            int cidx = 0;              // current chunk
+            bool slow = false;
+
+            auto step = [&](auto IC) {
+                constexpr int I = decltype(IC)::value;
+                constexpr int RTN = (RJ ? C - 1 - (I + 1) : I + 1) * L::TROW, RSN = (RJ ? C - 1 - (I + 1) : I + 1) * L::SROW;
+                constexpr int RT0 = (RJ ? C - 1 : 0) * L::TROW, RS0 = (RJ ? C - 1 : 0) * L::SROW;
+#if TTCR_T5_STEP_TRACE
+                long long* const tr = (trace_on && (unsigned)(a - p.trace_a0) < 128u)
+                                          ? p.trace + (size_t)p.ntiles * 8 + ((wu * 128 + (a - p.trace_a0)) * 4) : nullptr;
+                if (tr) tr[0] = TTCR_T5_CLOCK();
+#endif
+                // ---- (1) the words of the neighbours (rings): (u0w-1, a, .), lane v0-1 of every plane, progress of warp wu+1
                 const unsigned tag = (unsigned)(a + 1);
                 const unsigned ar = a_uin + (unsigned)(a & (DU - 1)) * 1024;
                 const unsigned av = a_vin + (unsigned)(a & (DV - 1)) * (R * 8);
@@ -515,6 +529,10 @@ __global__ void __launch_bounds__((NU + 2) * 32, (NU <= 4 ? 2 : 1)) k_sweep_patc
                 float km0[R];
 #pragma unroll
                 for (int r = 0; r < R; ++r) km0[r] = __shfl_up_sync(0xffffffffu, tprev[r].w, 1);
+                // The shuffle is a convergence point: every lane has left step a-1, so its ring slots may be reused.  (Lanes
+                // can leave the wait below at different times; reporting at the end of a step would let a producer overwrite
+                // a slot that a late lane is still polling.)
+                if (lane == 0) sts_i(a_myprog, a);
                 // ---- (3) one test for everything that comes from other warps
                 auto stale = [&]() {
                     unsigned bad = need_u ? ((xa.y ^ tag) | (xa.w ^ tag) | (xb.y ^ tag) | (xb.w ^ tag)) : 0u;
@@ -540,14 +558,27 @@ __global__ void __launch_bounds__((NU + 2) * 32, (NU <= 4 ? 2 : 1)) k_sweep_patc
                             int* const ql = q + (lane ? 8 : 0);
                             ql[0] = 41; ql[1] = a; ql[2] = need_u ? (int)xa.y : -1; ql[3] = need_u ? (int)xb.w : -1; ql[4] = (int)xv[0].y; ql[5] = nxp;
                         }
-                        atomicOr((unsigned*)&q[6], 1u << lane);          // lanes that were spinning
+                        atomicOr((unsigned*)&q[6], 1u << lane);          // lanes that were polling
                         atomicMax(&q[7], a + 1);                          // ... and their step
-                        atomicMax(&q[14], 1000 - a);
-                        q[8] = 41;
-                        atomicOr((unsigned*)&q[15], (need_u && ((xa.y ^ tag) | (xa.w ^ tag) | (xb.y ^ tag) | (xb.w ^ tag))) ? 1u << lane : 0u);
                     }
                 }
-                if (tr) tr[1] = clock64();
+#if TTCR_T5_STEP_TRACE
+                if (tr) tr[1] = TTCR_T5_CLOCK();
+#endif
+                // ---- (4) old values of the NEXT step (they do not depend on anybody: the loads overlap the arithmetic)
+                float4 jn[R], sn[R], un;
+                float hn[R];
+                if constexpr (I + 1 < C) {
+                    load_old(cT + RTN, cS + RSN, jn, hn, sn, un);
+                } else {
+                    if (cidx + 1 < nch) {
+                        const unsigned g = g0 + (unsigned)(cidx + 1);
+                        wait_chunk(g);
+                        cT = (g % NCH) * L::CHB_T;
+                        cS = (g % NCH) * L::CHB_S;
+                    }
+                    load_old(cT + RT0, cS + RS0, jn, hn, sn, un);   // (after the last chunk: a harmless re-read)
+                }
                 float4 um = make_float4(__uint_as_float(xa.x), __uint_as_float(xa.z), __uint_as_float(xb.x), __uint_as_float(xb.z));
                 if (!need_u) um = make_float4(MAXV, MAXV, MAXV, MAXV);
 #pragma unroll
@@ -555,16 +586,16 @@ __global__ void __launch_bounds__((NU + 2) * 32, (NU <= 4 ? 2 : 1)) k_sweep_patc
                     if (lane == 0) km0[r] = __uint_as_float(xv[r].x);
                     if (kill) h[r] = MAXV;
                 }
-                if (tr) tr[2] = clock64();
-                // ---- (4) update, last plane first (plane r reads the previous-step result of plane r-1); branch free
+#if TTCR_T5_STEP_TRACE
+                if (tr) tr[2] = TTCR_T5_CLOCK();
+#endif
+                // ---- (5) update, last plane first (plane r reads the previous-step result of plane r-1); branch free
                 float4 nlast;
 #pragma unroll
                 for (int r = R - 1; r >= 0; --r) {
                     float4 upv = (r == R - 1) ? up : jp[r + 1 < R ? r + 1 : r];
                     const float4 umv = (r == 0) ? um : tprev[r > 0 ? r - 1 : 0];
-                    if (SLOW) {
-                        if (u0w + r >= ulast) upv = make_float4(MAXV, MAXV, MAXV, MAXV);
-                    }
+                    if (slow && u0w + r >= ulast) upv = make_float4(MAXV, MAXV, MAXV, MAXV);
                     const float4 tp = tprev[r], j = jp[r], s = sl[r], o = told[r];
                     const float t0 = godunov(tmin(km0[r], j.y), tmin(tp.x, j.x), tmin(umv.x, upv.x), s.x * dx);
                     const float t1 = godunov(tmin(tp.x, j.z), tmin(tp.y, j.y), tmin(umv.y, upv.y), s.y * dx);
@@ -572,7 +603,7 @@ __global__ void __launch_bounds__((NU + 2) * 32, (NU <= 4 ? 2 : 1)) k_sweep_patc
                     const float t3 = godunov(tmin(tp.z, h[r]), tmin(tp.w, j.w), tmin(umv.w, upv.w), s.w * dx);
                     bool c0 = t0 < o.x, c1 = t1 < o.y, c2 = t2 < o.z, c3 = t3 < o.w;
                     float* const dst = tt + (e0[r] + (long long)(a - r) * w.sm);
-                    if (SLOW) {
+                    if (slow) {   // warp-uniform: last planes of the grid, rows that may hold frozen nodes
                         if (u0w + r > ulast) c0 = c1 = c2 = c3 = false;
                         const unsigned fm = ((unsigned)(a - wz_lo) < (unsigned)wz_cnt) ? (fzmask >> (r * 4)) & 15u : 0u;
                         if (fm) {
@@ -594,7 +625,7 @@ __global__ void __launch_bounds__((NU + 2) * 32, (NU <= 4 ? 2 : 1)) k_sweep_patc
                     tprev[r] = n;
                     told[r] = j;
                 }
-                // ---- (5) last plane of the patch -> warp wu+1 / tile U+1
+                // ---- (6) last plane of the patch -> warp wu+1 / tile U+1
                 {
                     const int row = a - (R - 1);
                     if (row >= 0 && row < nrows) {
@@ -609,33 +640,28 @@ __global__ void __launch_bounds__((NU + 2) * 32, (NU <= 4 ? 2 : 1)) k_sweep_patc
                         }
                     }
                 }
-                if (tr) tr[3] = clock64();
+#if TTCR_T5_STEP_TRACE
+                if (tr) tr[3] = TTCR_T5_CLOCK();
+#endif
+#pragma unroll
+                for (int r = 0; r < R; ++r) { jp[r] = jn[r]; h[r] = hn[r]; sl[r] = sn[r]; }
+                up = un;
                 ++a;
-                // every lane is done with the ring slots of this step before the step is reported complete (lanes may have
-                // left the wait above at different times; the producers reuse a slot as soon as they see the report)
-                __syncwarp();
-                if (lane == 0) sts_i(a_myprog, a);
             };
 
-            for (int c = 0; c < nch && !dead; ++c) {
-                const unsigned g = g0 + c;
-                wait_chunk(g);
-                dead = __any_sync(0xffffffffu, dead);
-                if (dead) break;
-                cT = (g % NCH) * L::CHB_T;
-                cS = (g % NCH) * L::CHB_S;
-                const bool slow = edge || (wz_cnt > 0 && a + C > wz_lo && a <= wz_hi);
-                if (slow) {
-                    if constexpr (C >= 1) step(IntC<0>{}, IntC<1>{});
-                    if constexpr (C >= 2) step(IntC<1>{}, IntC<1>{});
-                    if constexpr (C >= 3) step(IntC<2>{}, IntC<1>{});
-                    if constexpr (C >= 4) step(IntC<3>{}, IntC<1>{});
-                } else {
-                    if constexpr (C >= 1) step(IntC<0>{}, IntC<0>{});
-                    if constexpr (C >= 2) step(IntC<1>{}, IntC<0>{});
-                    if constexpr (C >= 3) step(IntC<2>{}, IntC<0>{});
-                    if constexpr (C >= 4) step(IntC<3>{}, IntC<0>{});
-                }
+            if (nch > 0) {
+                wait_chunk(g0);
+                cT = (g0 % NCH) * L::CHB_T;
+                cS = (g0 % NCH) * L::CHB_S;
+                load_old(cT + (RJ ? C - 1 : 0) * L::TROW, cS + (RJ ? C - 1 : 0) * L::SROW, jp, h, sl, up);
+            }
+            dead = __any_sync(0xffffffffu, dead);
+            for (cidx = 0; cidx < nch && !dead; ++cidx) {
+                slow = edge || (wz_cnt > 0 && a + C > wz_lo && a <= wz_hi);
+                if constexpr (C >= 1) step(IntC<0>{});
+                if constexpr (C >= 2) step(IntC<1>{});
+                if constexpr (C >= 3) step(IntC<2>{});
+                if constexpr (C >= 4) step(IntC<3>{});
                 dead = __any_sync(0xffffffffu, dead);
                 if (p.trace && threadIdx.x == 0) {
                     const int q = nrows / 4;
