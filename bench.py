@@ -38,6 +38,7 @@ METRIC = "Mnodes/s (grid nodes x sweep-iters / s) on 512^3 FSM"
 UNIT = "Mnodes/s"
 BYTES_PER_NODE_SWEEP = 12.0   # tt read + tt write + slowness read, fp32
 CPU_SAMPLE_N = 192            # nodes per side of the bounded CPU sample
+KERNEL_NAMES = {1: "k_sweep_plane", 2: "k_sweep_tile", 3: "k_sweep_tile3", 4: "k_sweep_tile4", 5: "k_sweep_patch"}
 
 
 def gradient_model(n, dtype=np.float32):
@@ -85,6 +86,23 @@ class ClockSampler:
         except OSError:
             pass
 
+    def _lines(self):
+        try:
+            with open(self.f.name) as f:
+                return f.read().splitlines()
+        except OSError:
+            return []
+
+    def wait_first_sample(self, timeout=8.0):
+        """nvidia-smi needs about a second to start; block until it has written a line"""
+        t0 = time.perf_counter()
+        while self.p is not None and not self._lines() and time.perf_counter() - t0 < timeout:
+            time.sleep(0.05)
+
+    def mark(self):
+        """the timed region starts here: earlier samples are dropped"""
+        self.skip = len(self._lines())
+
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
         if self.p is None:
@@ -97,7 +115,10 @@ class ClockSampler:
         self.f.flush()
         self.f.seek(0)
         sm, mx, reasons = [], [], set()
-        for line in self.f.read().splitlines():
+        lines = self.f.read().splitlines()
+        if len(lines) > getattr(self, "skip", 0):
+            lines = lines[getattr(self, "skip", 0):]
+        for line in lines:
             c = [t.strip() for t in line.split(",")]
             if len(c) < 9:
                 continue
@@ -230,10 +251,12 @@ def main():
         torch.cuda.synchronize()
 
     # ---- device-resident arm -----------------------------------------------------------------------
+    clocks = ClockSampler(local_rank)
     for _ in range(warm):
         g.solve(src)
+    clocks.wait_first_sample()
     barrier()
-    clocks = ClockSampler(local_rank)
+    clocks.mark()
     t_wall = time.perf_counter()
     dev_ms = sweep_ms = 0.0
     sweeps = launches = sweep_launches = 0
@@ -297,7 +320,7 @@ def main():
                     "call": "Grid3d.raytrace(src, rcv, slowness): slowness from pinned host memory, 441 receiver times back"},
             "gpu_launches": int(tot[7]),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": "k_sweep_tile (one launch = one directional sweep)",
+                         "traffic": traffic, "kernel": KERNEL_NAMES.get(st["kernel"], str(st["kernel"])) + " (one launch = one directional sweep)",
                          "algorithmic_bytes_per_launch": BYTES_PER_NODE_SWEEP * nodes,
                          "avg_launch_ms": per_launch_ms, "peak_source": peak_src},
             "clocks": clk,

@@ -437,7 +437,7 @@ class Grid final : public GridBase {
             if (kernel_ == TTCR_B200_KERNEL_TILE && !tile_supported<T>(weno_stage)) return TTCR_B200_KERNEL_PLANE;
             return kernel_;
         }
-        if (tile4_supported<T>(weno_stage)) return TTCR_B200_KERNEL_TILE4;   // fp32, first order: TMA-fed tiles, mailbox hand-off
+        if (tile5_supported<T>(weno_stage)) return TTCR_B200_KERNEL_TILE5;   // fp32, first order: register-patch march (sweep_tile5.cuh)
         if (!tile_supported<T>(weno_stage)) return TTCR_B200_KERNEL_PLANE;      // WENO stage
         return TTCR_B200_KERNEL_TILE;                                           // fp64, first order
     }
