@@ -147,7 +147,38 @@ __device__ __forceinline__ void stg_f4_stream_if(float* p, float x, float y, flo
                  "f"(x), "f"(y), "f"(z), "f"(w), "r"(on)
                  : "memory");
 }
+__device__ __forceinline__ void sts_u4_if(unsigned a, unsigned x, unsigned y, unsigned z, unsigned w, bool on) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %5, 0;\n\t@q st.volatile.shared.v4.u32 [%0], {%1, %2, %3, %4};\n\t}" ::"r"(a), "r"(x),
+                 "r"(y), "r"(z), "r"(w), "r"((int)on)
+                 : "memory");
+}
+__device__ __forceinline__ void st_mail2_if(unsigned long long* p, unsigned tag, float a, float b, int on) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t.reg .b64 x, y;\n\tsetp.ne.s32 q, %4, 0;\n\tmov.b64 x, {%1, %2};\n\tmov.b64 y, {%3, %2};\n\t"
+        "@q st.relaxed.gpu.global.v2.b64 [%0], {x, y};\n\t}" ::"l"(p),
+        "r"(__float_as_uint(a)), "r"(tag), "r"(__float_as_uint(b)), "r"(on)
+        : "memory");
+}
 template <bool REV> __device__ __forceinline__ float4 ord4(float4 v) { return REV ? make_float4(v.w, v.z, v.y, v.x) : v; }
+
+// Cold path of a march step, out of line so that the hot loop stays small: poll the ring words of step `tag-1`
+// until they are all there (U words of this lane, V words, progress of the next warp) or the march is given up.
+// Returns 0 when ready, 1 when another warp gave up, 2 on timeout.
+template <int R>
+__device__ __noinline__ int t5_wait_words(unsigned ar, unsigned av, unsigned a_nxprog, unsigned a_dead, unsigned tag, int need_u,
+                                          int nx_need, long long spin_cycles) {
+    const long long t0 = clock64();
+    for (;;) {
+        const uint4 xa = lds_u4(ar), xb = lds_u4(ar + 512);
+        unsigned bad = need_u ? ((xa.y ^ tag) | (xa.w ^ tag) | (xb.y ^ tag) | (xb.w ^ tag)) : 0u;
+#pragma unroll
+        for (int r = 0; r < R; ++r) bad |= lds_u2(av + r * 8).y ^ tag;
+        if (lds_i(a_nxprog) < nx_need) bad |= 1u;
+        if (!bad) return 0;
+        if (lds_i(a_dead)) return 1;
+        if (clock64() - t0 > spin_cycles) return 2;
+    }
+}
 
 // RJ: the sweep runs the row axis downwards, RK: the lane axis (boxes arrive in memory order).
 template <int NU, int R, int C, int NCH, int DU_, bool RJ, bool RK>
@@ -500,15 +531,24 @@ __global__ void __launch_bounds__((NU + 2) * 32, (NU <= 4 ? 2 : 1)) k_sweep_patc
                 }
                 xu = ord4<RK>(lds_f4(aT[R] + oT));
             };
-            unsigned cT = 0, cS = 0;   // byte offsets of the current chunk slot
-            int a = 0;
-            int cidx = 0;              // current chunk
-            bool slow = false;
+            // row i of a chunk slot sits at byte offset (RJ ? C-1-i : i) * row bytes: boxes arrive in memory order
+            constexpr int RT0 = (RJ ? C - 1 : 0) * L::TROW, RS0 = (RJ ? C - 1 : 0) * L::SROW;
+            constexpr int DRT = RJ ? -L::TROW : L::TROW, DRS = RJ ? -L::SROW : L::SROW;
+            unsigned oT = 0, oS = 0;   // byte offsets (slot + row) of the NEXT step's old values
+            int cidx = 0;              // chunk the next step's old values come from
+            const float QNAN = __int_as_float(0x7fc00000);
+            const int ulim = nrows;    // rows 0 .. nrows-1 of the last plane are handed on
 
-            auto step = [&](auto IC) {
-                constexpr int I = decltype(IC)::value;
-                constexpr int RTN = (RJ ? C - 1 - (I + 1) : I + 1) * L::TROW, RSN = (RJ ? C - 1 - (I + 1) : I + 1) * L::SROW;
-                constexpr int RT0 = (RJ ? C - 1 : 0) * L::TROW, RS0 = (RJ ? C - 1 : 0) * L::SROW;
+            if (nch > 0) {
+                wait_chunk(g0);
+                oT = (g0 % NCH) * L::CHB_T + RT0;
+                oS = (g0 % NCH) * L::CHB_S + RS0;
+                load_old(oT, oS, jp, h, sl, up);
+            }
+            dead = __any_sync(0xffffffffu, dead);
+            const int nsteps_w = dead ? 0 : nch * C;
+
+            for (int a = 0; a < nsteps_w; ++a) {
 #if TTCR_T5_STEP_TRACE
                 long long* const tr = (trace_on && (unsigned)(a - p.trace_a0) < 128u)
                                           ? p.trace + (size_t)p.ntiles * 8 + ((wu * 128 + (a - p.trace_a0)) * 4) : nullptr;
@@ -533,33 +573,29 @@ __global__ void __launch_bounds__((NU + 2) * 32, (NU <= 4 ? 2 : 1)) k_sweep_patc
                 // can leave the wait below at different times; reporting at the end of a step would let a producer overwrite
                 // a slot that a late lane is still polling.)
                 if (lane == 0) sts_i(a_myprog, a);
-                // ---- (3) one test for everything that comes from other warps
-                auto stale = [&]() {
+                // ---- (3) one test for everything that comes from other warps; the wait itself is out of line
+                {
                     unsigned bad = need_u ? ((xa.y ^ tag) | (xa.w ^ tag) | (xb.y ^ tag) | (xb.w ^ tag)) : 0u;
 #pragma unroll
                     for (int r = 0; r < R; ++r) bad |= xv[r].y ^ tag;
                     if (nxp < nx_need) bad |= 1u;
-                    return bad != 0;
-                };
-                if (stale()) {
-                    const long long t0 = clock64();
-                    for (;;) {
+                    if (bad) {
+                        const int rc = t5_wait_words<R>(ar, av, a_nxprog, a_dead, tag, need_u ? 1 : 0, nx_need, spin_cycles);
                         xa = lds_u4(ar); xb = lds_u4(ar + 512);
 #pragma unroll
                         for (int r = 0; r < R; ++r) xv[r] = lds_u2(av + r * 8);
-                        nxp = lds_i(a_nxprog);
-                        if (!stale()) break;
-                        if (lds_i(a_dead)) { dead = true; break; }
-                        if (clock64() - t0 > spin_cycles) { give_up(41, nxp, a); dead = true; break; }
-                    }
-                    if (dead) {
-                        int* const q = p.dbg + ((size_t)tile * (NU + 2) + wu) * 16;
-                        if (lane == 0 || lane == 31) {
-                            int* const ql = q + (lane ? 8 : 0);
-                            ql[0] = 41; ql[1] = a; ql[2] = need_u ? (int)xa.y : -1; ql[3] = need_u ? (int)xb.w : -1; ql[4] = (int)xv[0].y; ql[5] = nxp;
+                        if (rc) {
+                            if (rc == 2) give_up(41, lds_i(a_nxprog), a);
+                            dead = true;
+                            int* const q = p.dbg + ((size_t)tile * (NU + 2) + wu) * 16;
+                            if (lane == 0 || lane == 31) {
+                                int* const ql = q + (lane ? 8 : 0);
+                                ql[0] = 41; ql[1] = a; ql[2] = need_u ? (int)xa.y : -1; ql[3] = need_u ? (int)xb.w : -1; ql[4] = (int)xv[0].y;
+                                ql[5] = lds_i(a_nxprog);
+                            }
+                            atomicOr((unsigned*)&q[6], 1u << lane);          // lanes that were polling
+                            atomicMax(&q[7], a + 1);                          // ... and their step
                         }
-                        atomicOr((unsigned*)&q[6], 1u << lane);          // lanes that were polling
-                        atomicMax(&q[7], a + 1);                          // ... and their step
                     }
                 }
 #if TTCR_T5_STEP_TRACE
@@ -568,16 +604,18 @@ __global__ void __launch_bounds__((NU + 2) * 32, (NU <= 4 ? 2 : 1)) k_sweep_patc
                 // ---- (4) old values of the NEXT step (they do not depend on anybody: the loads overlap the arithmetic)
                 float4 jn[R], sn[R], un;
                 float hn[R];
-                if constexpr (I + 1 < C) {
-                    load_old(cT + RTN, cS + RSN, jn, hn, sn, un);
-                } else {
-                    if (cidx + 1 < nch) {
-                        const unsigned g = g0 + (unsigned)(cidx + 1);
+                {
+                    const int an = a + 1;
+                    if ((an & (C - 1)) != 0) {
+                        oT += (unsigned)DRT; oS += (unsigned)DRS;
+                    } else if (an < nsteps_w) {
+                        cidx = an / C;
+                        const unsigned g = g0 + (unsigned)cidx;
                         wait_chunk(g);
-                        cT = (g % NCH) * L::CHB_T;
-                        cS = (g % NCH) * L::CHB_S;
-                    }
-                    load_old(cT + RT0, cS + RS0, jn, hn, sn, un);   // (after the last chunk: a harmless re-read)
+                        oT = (g % NCH) * L::CHB_T + RT0;
+                        oS = (g % NCH) * L::CHB_S + RS0;
+                    }   // (after the last chunk: a harmless re-read)
+                    load_old(oT, oS, jn, hn, sn, un);
                 }
                 float4 um = make_float4(__uint_as_float(xa.x), __uint_as_float(xa.z), __uint_as_float(xb.x), __uint_as_float(xb.z));
                 if (!need_u) um = make_float4(MAXV, MAXV, MAXV, MAXV);
@@ -586,34 +624,46 @@ __global__ void __launch_bounds__((NU + 2) * 32, (NU <= 4 ? 2 : 1)) k_sweep_patc
                     if (lane == 0) km0[r] = __uint_as_float(xv[r].x);
                     if (kill) h[r] = MAXV;
                 }
+                // ---- (5) rare: last planes of the grid, rows that may hold frozen nodes.  A node that must not change gets
+                //          NaN slowness: its update is NaN and fails `t < old` like every non-node slot.
+                if (edge || (unsigned)(a - wz_lo) < (unsigned)wz_cnt) {
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        unsigned fm = ((unsigned)(a - wz_lo) < (unsigned)wz_cnt) ? (fzmask >> (r * 4)) & 15u : 0u;
+                        if (fm) {
+                            const long long eb = e0[r] + (long long)(a - r) * w.sm;
+                            unsigned fz = 0;
+                            if ((fm & 1u) && frozen_bit(frozen, eb + (RK ? 3 : 0))) fz |= 1u;
+                            if ((fm & 2u) && frozen_bit(frozen, eb + (RK ? 2 : 1))) fz |= 2u;
+                            if ((fm & 4u) && frozen_bit(frozen, eb + (RK ? 1 : 2))) fz |= 4u;
+                            if ((fm & 8u) && frozen_bit(frozen, eb + (RK ? 0 : 3))) fz |= 8u;
+                            fm = fz;
+                        }
+                        if (u0w + r > ulast) fm = 15u;
+                        if (fm & 1u) sl[r].x = QNAN;
+                        if (fm & 2u) sl[r].y = QNAN;
+                        if (fm & 4u) sl[r].z = QNAN;
+                        if (fm & 8u) sl[r].w = QNAN;
+                        if (r == R - 1 && u0w + r >= ulast) up = make_float4(MAXV, MAXV, MAXV, MAXV);   // no (u+1) plane
+                    }
+                }
 #if TTCR_T5_STEP_TRACE
                 if (tr) tr[2] = TTCR_T5_CLOCK();
 #endif
-                // ---- (5) update, last plane first (plane r reads the previous-step result of plane r-1); branch free
+                // ---- (6) update, last plane first (plane r reads the previous-step result of plane r-1); branch free
                 float4 nlast;
 #pragma unroll
                 for (int r = R - 1; r >= 0; --r) {
                     float4 upv = (r == R - 1) ? up : jp[r + 1 < R ? r + 1 : r];
+                    if (R > 1 && r < R - 1 && u0w + r >= ulast) upv = make_float4(MAXV, MAXV, MAXV, MAXV);
                     const float4 umv = (r == 0) ? um : tprev[r > 0 ? r - 1 : 0];
-                    if (slow && u0w + r >= ulast) upv = make_float4(MAXV, MAXV, MAXV, MAXV);
                     const float4 tp = tprev[r], j = jp[r], s = sl[r], o = told[r];
                     const float t0 = godunov(tmin(km0[r], j.y), tmin(tp.x, j.x), tmin(umv.x, upv.x), s.x * dx);
                     const float t1 = godunov(tmin(tp.x, j.z), tmin(tp.y, j.y), tmin(umv.y, upv.y), s.y * dx);
                     const float t2 = godunov(tmin(tp.y, j.w), tmin(tp.z, j.z), tmin(umv.z, upv.z), s.z * dx);
                     const float t3 = godunov(tmin(tp.z, h[r]), tmin(tp.w, j.w), tmin(umv.w, upv.w), s.w * dx);
-                    bool c0 = t0 < o.x, c1 = t1 < o.y, c2 = t2 < o.z, c3 = t3 < o.w;
+                    const bool c0 = t0 < o.x, c1 = t1 < o.y, c2 = t2 < o.z, c3 = t3 < o.w;
                     float* const dst = tt + (e0[r] + (long long)(a - r) * w.sm);
-                    if (slow) {   // warp-uniform: last planes of the grid, rows that may hold frozen nodes
-                        if (u0w + r > ulast) c0 = c1 = c2 = c3 = false;
-                        const unsigned fm = ((unsigned)(a - wz_lo) < (unsigned)wz_cnt) ? (fzmask >> (r * 4)) & 15u : 0u;
-                        if (fm) {
-                            const long long eb = dst - tt;
-                            if ((fm & 1u) && frozen_bit(frozen, eb + (RK ? 3 : 0))) c0 = false;
-                            if ((fm & 2u) && frozen_bit(frozen, eb + (RK ? 2 : 1))) c1 = false;
-                            if ((fm & 4u) && frozen_bit(frozen, eb + (RK ? 1 : 2))) c2 = false;
-                            if ((fm & 8u) && frozen_bit(frozen, eb + (RK ? 0 : 3))) c3 = false;
-                        }
-                    }
                     float4 n;
                     n.x = c0 ? t0 : o.x; n.y = c1 ? t1 : o.y; n.z = c2 ? t2 : o.z; n.w = c3 ? t3 : o.w;
                     const int ch = (c0 || c1 || c2 || c3) ? 1 : 0;
@@ -625,20 +675,17 @@ __global__ void __launch_bounds__((NU + 2) * 32, (NU <= 4 ? 2 : 1)) k_sweep_patc
                     tprev[r] = n;
                     told[r] = j;
                 }
-                // ---- (6) last plane of the patch -> warp wu+1 / tile U+1
+                // ---- (7) last plane of the patch -> warp wu+1 (shared ring) / tile U+1 (global mailbox); predicated, no branch
                 {
                     const int row = a - (R - 1);
-                    if (row >= 0 && row < nrows) {
-                        if (!last_w) {
-                            const unsigned ao = a_uout + (unsigned)(row & (DU - 1)) * 1024;
-                            const unsigned tg = (unsigned)(row + 1);
-                            sts_u4(ao, __float_as_uint(nlast.x), tg, __float_as_uint(nlast.y), tg);
-                            sts_u4(ao + 512, __float_as_uint(nlast.z), tg, __float_as_uint(nlast.w), tg);
-                        } else if (has_down) {
-                            st_mail2(mu_out + (size_t)row * 128, tag_g, nlast.x, nlast.y);
-                            st_mail2(mu_out + (size_t)row * 128 + 64, tag_g, nlast.z, nlast.w);
-                        }
-                    }
+                    const bool inr = (unsigned)row < (unsigned)ulim;
+                    const unsigned ao = a_uout + (unsigned)(row & (DU - 1)) * 1024;
+                    const unsigned tg = (unsigned)(row + 1);
+                    sts_u4_if(ao, __float_as_uint(nlast.x), tg, __float_as_uint(nlast.y), tg, inr && !last_w);
+                    sts_u4_if(ao + 512, __float_as_uint(nlast.z), tg, __float_as_uint(nlast.w), tg, inr && !last_w);
+                    const int og = (inr && last_w && has_down) ? 1 : 0;
+                    st_mail2_if(mu_out + (long long)row * 128, tag_g, nlast.x, nlast.y, og);
+                    st_mail2_if(mu_out + (long long)row * 128 + 64, tag_g, nlast.z, nlast.w, og);
                 }
 #if TTCR_T5_STEP_TRACE
                 if (tr) tr[3] = TTCR_T5_CLOCK();
@@ -646,28 +693,15 @@ __global__ void __launch_bounds__((NU + 2) * 32, (NU <= 4 ? 2 : 1)) k_sweep_patc
 #pragma unroll
                 for (int r = 0; r < R; ++r) { jp[r] = jn[r]; h[r] = hn[r]; sl[r] = sn[r]; }
                 up = un;
-                ++a;
-            };
-
-            if (nch > 0) {
-                wait_chunk(g0);
-                cT = (g0 % NCH) * L::CHB_T;
-                cS = (g0 % NCH) * L::CHB_S;
-                load_old(cT + (RJ ? C - 1 : 0) * L::TROW, cS + (RJ ? C - 1 : 0) * L::SROW, jp, h, sl, up);
-            }
-            dead = __any_sync(0xffffffffu, dead);
-            for (cidx = 0; cidx < nch && !dead; ++cidx) {
-                slow = edge || (wz_cnt > 0 && a + C > wz_lo && a <= wz_hi);
-                if constexpr (C >= 1) step(IntC<0>{});
-                if constexpr (C >= 2) step(IntC<1>{});
-                if constexpr (C >= 3) step(IntC<2>{});
-                if constexpr (C >= 4) step(IntC<3>{});
-                dead = __any_sync(0xffffffffu, dead);
-                if (p.trace && threadIdx.x == 0) {
-                    const int q = nrows / 4;
-                    if (a - C < q && a >= q) p.trace[tile * 8 + 2] = gtime();
-                    if (a - C < 2 * q && a >= 2 * q) p.trace[tile * 8 + 3] = gtime();
-                    if (a - C < 3 * q && a >= 3 * q) p.trace[tile * 8 + 4] = gtime();
+                if ((a & (C - 1)) == C - 1) {   // end of a chunk
+                    dead = __any_sync(0xffffffffu, dead);
+                    if (dead) break;
+                    if (p.trace && threadIdx.x == 0) {
+                        const int q = nrows / 4, a1 = a + 1;
+                        if (a1 - C < q && a1 >= q) p.trace[tile * 8 + 2] = gtime();
+                        if (a1 - C < 2 * q && a1 >= 2 * q) p.trace[tile * 8 + 3] = gtime();
+                        if (a1 - C < 3 * q && a1 >= 3 * q) p.trace[tile * 8 + 4] = gtime();
+                    }
                 }
             }
             gc = g0 + nch;
