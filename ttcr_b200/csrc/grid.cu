@@ -456,7 +456,8 @@ class Grid final : public GridBase {
         s.sweep_ev_used = 0;
         CK(cudaEventRecord(s.e0, s.stream));
         CK(cudaMemcpyAsync(s.d_pts, s.h_pts, 4 * ntx * sizeof(T), cudaMemcpyHostToDevice, s.stream));
-        k_reinit_l1<T><<<nblocks(ne), 256, 0, s.stream>>>(s.tt[0], d_);
+        // Node3Dn::reinit: every node +MAX; the slots that are no node hold +MAX anyway, so this is a plain fill
+        k_fill16<T><<<nblocks(ne / (16 / sizeof(T)), 256, 148 * 32), 256, 0, s.stream>>>(s.tt[0], ne, Lim<T>::max());
         CK(cudaMemsetAsync(s.mask[0], 0, ne / 8, s.stream));
         CK(cudaMemsetAsync(s.mask[1], 0, ne / 8, s.stream));
         k_init_fsm<T><<<1, 32, 0, s.stream>>>(g_, d_, s.d_pts, s.d_pts + 3 * ntx, (int)ntx, npts, s.tt[0], slo_[0], s.mask[0],
@@ -479,8 +480,15 @@ class Grid final : public GridBase {
                     if (!((dbg_dirs >> dir) & 1)) continue;   // debugging aid: run a subset of the sweep directions
                     const int want = make_view(d_, dir).layout;
                     if (want != cur) {
-                        const dim3 grid((d_.nk + 31) / 32, (d_.nj + 31) / 32, d_.ni);
-                        k_relayout<T><<<grid, dim3(32, 8), 0, s.stream>>>(s.tt[cur], cur, s.tt[want], d_);
+                        static const bool old_relayout = getenv("TTCR_B200_OLD_RELAYOUT") != nullptr;
+                        if (old_relayout) {
+                            const dim3 grid((d_.nk + 31) / 32, (d_.nj + 31) / 32, d_.ni);
+                            k_relayout<T><<<grid, dim3(32, 8), 0, s.stream>>>(s.tt[cur], cur, s.tt[want], d_);
+                        } else {
+                            constexpr int RB = 128;
+                            const dim3 grid(d_.kpad / 32, (d_.q + RB - 1) / RB, d_.ni);
+                            k_relayout2<T, RB><<<grid, dim3(32, 8), 0, s.stream>>>(s.tt[cur], cur, s.tt[want], d_);
+                        }
                         s.st.launches += 1;
                         cur = want;
                     }

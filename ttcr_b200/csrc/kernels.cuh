@@ -113,6 +113,43 @@ __global__ void k_relayout(const T* __restrict__ src, int src_layout, T* __restr
     }
 }
 
+// L1 <-> L2 without shared memory: for a fixed lane k the two layouts differ by a shift of nk-1-2k rows, so a
+// destination row reads, lane by lane, source rows two apart; a block walks a band of RB destination rows of one
+// 32-lane column, and the 128-byte source lines it touches (RB+62 of them) are reused through L1.
+// grid: (kpad/32, ceil(Q/RB), ni), block: (32, 8).
+template <typename T, int RB>
+__global__ void __launch_bounds__(256) k_relayout2(const T* __restrict__ src, int src_layout, T* __restrict__ dst, Dims d) {
+    const int k = blockIdx.x * 32 + threadIdx.x;
+    const int i = blockIdx.z;
+    const int r0 = blockIdx.y * RB;
+    if (k >= d.nk) return;
+    const int shift = d.nk - 1 - 2 * k;                 // L2 row = L1 row + shift
+    const size_t plane = (size_t)i * d.qs + GUARD;
+#pragma unroll 4
+    for (int y = threadIdx.y; y < RB; y += 8) {
+        const int rd = r0 + y;                           // destination row
+        if (rd >= d.q) break;
+        const int rs = src_layout ? rd + shift : rd - shift;   // source row (src L2 -> dst L1: L2 row = L1 row + shift)
+        const int j = src_layout ? rd - k : rd + k - (d.nk - 1);
+        if (j >= 0 && j < d.nj) dst[(plane + rd) * d.kpad + k] = src[(plane + rs) * d.kpad + k];
+    }
+}
+
+// 16-byte fill (n elements, n * sizeof(T) a multiple of 16)
+template <typename T>
+__global__ void k_fill16(T* __restrict__ p, size_t n, T v) {
+    constexpr int V = 16 / sizeof(T);
+    struct alignas(16) Pack { T x[V]; };
+    Pack pk;
+#pragma unroll
+    for (int e = 0; e < V; ++e) pk.x[e] = v;
+    Pack* const q = reinterpret_cast<Pack*>(p);
+    const size_t m = n / V;
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < m; i += stride) q[i] = pk;
+}
+
 // ---------------------------------------------------------------------------------------
 // Grid3Drcfs::setSlowness (Grid3Drcfs.h:88-171): node slowness = mean of the adjacent cells.
 // Summation order as in the source: k outer, j, i inner; j outer, k inner on x faces.
