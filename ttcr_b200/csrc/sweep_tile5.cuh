@@ -535,7 +535,6 @@ __global__ void __launch_bounds__((NU + 2) * 32, (NU <= 4 ? 2 : 1)) k_sweep_patc
             constexpr int RT0 = (RJ ? C - 1 : 0) * L::TROW, RS0 = (RJ ? C - 1 : 0) * L::SROW;
             constexpr int DRT = RJ ? -L::TROW : L::TROW, DRS = RJ ? -L::SROW : L::SROW;
             unsigned oT = 0, oS = 0;   // byte offsets (slot + row) of the NEXT step's old values
-            int cidx = 0;              // chunk the next step's old values come from
             const float QNAN = __int_as_float(0x7fc00000);
             const int ulim = nrows;    // rows 0 .. nrows-1 of the last plane are handed on
 
@@ -548,7 +547,13 @@ __global__ void __launch_bounds__((NU + 2) * 32, (NU <= 4 ? 2 : 1)) k_sweep_patc
             dead = __any_sync(0xffffffffu, dead);
             const int nsteps_w = dead ? 0 : nch * C;
 
-            for (int a = 0; a < nsteps_w; ++a) {
+            unsigned oTc = oT, oSc = oS;   // slot offsets (row 0) of the chunk after the current one, once it has landed
+            bool dead_u = false;
+            static_assert(C >= 2 && (C & (C - 1)) == 0, "steps per chunk: a power of two, at least 2");
+
+            // One march step.  Exactly one (rarely or every C-th time taken) branch: everything that is not the plain update
+            // -- words not there yet, a chunk boundary coming up, frozen nodes / last planes -- sits behind it.
+            auto step = [&](const int a) {
 #if TTCR_T5_STEP_TRACE
                 long long* const tr = (trace_on && (unsigned)(a - p.trace_a0) < 128u)
                                           ? p.trace + (size_t)p.ntiles * 8 + ((wu * 128 + (a - p.trace_a0)) * 4) : nullptr;
@@ -564,7 +569,7 @@ __global__ void __launch_bounds__((NU + 2) * 32, (NU <= 4 ? 2 : 1)) k_sweep_patc
                 uint2 xv[R];
 #pragma unroll
                 for (int r = 0; r < R; ++r) xv[r] = lds_u2(av + r * 8);
-                int nxp = lds_i(a_nxprog);
+                const int nxp = lds_i(a_nxprog);
                 // ---- (2) lane l-1's previous result
                 float km0[R];
 #pragma unroll
@@ -573,13 +578,15 @@ __global__ void __launch_bounds__((NU + 2) * 32, (NU <= 4 ? 2 : 1)) k_sweep_patc
                 // can leave the wait below at different times; reporting at the end of a step would let a producer overwrite
                 // a slot that a late lane is still polling.)
                 if (lane == 0) sts_i(a_myprog, a);
-                // ---- (3) one test for everything that comes from other warps; the wait itself is out of line
-                {
-                    unsigned bad = need_u ? ((xa.y ^ tag) | (xa.w ^ tag) | (xb.y ^ tag) | (xb.w ^ tag)) : 0u;
+                // ---- (3) the one branch
+                unsigned bad = need_u ? ((xa.y ^ tag) | (xa.w ^ tag) | (xb.y ^ tag) | (xb.w ^ tag)) : 0u;
 #pragma unroll
-                    for (int r = 0; r < R; ++r) bad |= xv[r].y ^ tag;
-                    if (nxp < nx_need) bad |= 1u;
-                    if (bad) {
+                for (int r = 0; r < R; ++r) bad |= xv[r].y ^ tag;
+                if (nxp < nx_need) bad |= 1u;
+                const bool f_bound = (a & (C - 1)) == C - 2;                        // time to make sure the next chunk has landed
+                const bool f_slow = edge || (unsigned)(a - wz_lo) < (unsigned)wz_cnt;
+                if (bad != 0 || f_bound || f_slow) {
+                    if (bad) {   // the wait itself is out of line
                         const int rc = t5_wait_words<R>(ar, av, a_nxprog, a_dead, tag, need_u ? 1 : 0, nx_need, spin_cycles);
                         xa = lds_u4(ar); xb = lds_u4(ar + 512);
 #pragma unroll
@@ -597,6 +604,45 @@ __global__ void __launch_bounds__((NU + 2) * 32, (NU <= 4 ? 2 : 1)) k_sweep_patc
                             atomicMax(&q[7], a + 1);                          // ... and their step
                         }
                     }
+                    if (f_bound) {   // warp-uniform
+                        const int cn = a / C + 1;
+                        if (cn < nch) {
+                            const unsigned g = g0 + (unsigned)cn;
+                            wait_chunk(g);
+                            oTc = (g % NCH) * L::CHB_T + RT0;
+                            oSc = (g % NCH) * L::CHB_S + RS0;
+                        }   // (after the last chunk: a harmless re-read of the last slot)
+                        dead_u = __any_sync(0xffffffffu, dead);   // (uniform: leaves the loop for the whole warp)
+                        if (p.trace && threadIdx.x == 0) {
+                            const int q = nrows / 4, a1 = (a / C + 1) * C;
+                            if (a1 - C < q && a1 >= q) p.trace[tile * 8 + 2] = gtime();
+                            if (a1 - C < 2 * q && a1 >= 2 * q) p.trace[tile * 8 + 3] = gtime();
+                            if (a1 - C < 3 * q && a1 >= 3 * q) p.trace[tile * 8 + 4] = gtime();
+                        }
+                    }
+                    if (f_slow) {
+                        // last planes of the grid, rows that may hold frozen nodes.  A node that must not change gets NaN
+                        // slowness: its update is NaN and fails `t < old` like every non-node slot.
+#pragma unroll
+                        for (int r = 0; r < R; ++r) {
+                            unsigned fm = ((unsigned)(a - wz_lo) < (unsigned)wz_cnt) ? (fzmask >> (r * 4)) & 15u : 0u;
+                            if (fm) {
+                                const long long eb = e0[r] + (long long)(a - r) * w.sm;
+                                unsigned fz = 0;
+                                if ((fm & 1u) && frozen_bit(frozen, eb + (RK ? 3 : 0))) fz |= 1u;
+                                if ((fm & 2u) && frozen_bit(frozen, eb + (RK ? 2 : 1))) fz |= 2u;
+                                if ((fm & 4u) && frozen_bit(frozen, eb + (RK ? 1 : 2))) fz |= 4u;
+                                if ((fm & 8u) && frozen_bit(frozen, eb + (RK ? 0 : 3))) fz |= 8u;
+                                fm = fz;
+                            }
+                            if (u0w + r > ulast) fm = 15u;
+                            if (fm & 1u) sl[r].x = QNAN;
+                            if (fm & 2u) sl[r].y = QNAN;
+                            if (fm & 4u) sl[r].z = QNAN;
+                            if (fm & 8u) sl[r].w = QNAN;
+                            if (r == R - 1 && u0w + r >= ulast) up = make_float4(MAXV, MAXV, MAXV, MAXV);   // no (u+1) plane
+                        }
+                    }
                 }
 #if TTCR_T5_STEP_TRACE
                 if (tr) tr[1] = TTCR_T5_CLOCK();
@@ -605,16 +651,9 @@ __global__ void __launch_bounds__((NU + 2) * 32, (NU <= 4 ? 2 : 1)) k_sweep_patc
                 float4 jn[R], sn[R], un;
                 float hn[R];
                 {
-                    const int an = a + 1;
-                    if ((an & (C - 1)) != 0) {
-                        oT += (unsigned)DRT; oS += (unsigned)DRS;
-                    } else if (an < nsteps_w) {
-                        cidx = an / C;
-                        const unsigned g = g0 + (unsigned)cidx;
-                        wait_chunk(g);
-                        oT = (g % NCH) * L::CHB_T + RT0;
-                        oS = (g % NCH) * L::CHB_S + RS0;
-                    }   // (after the last chunk: a harmless re-read)
+                    const bool first = ((a + 1) & (C - 1)) == 0;   // the next step opens a chunk
+                    oT = first ? oTc : oT + (unsigned)DRT;
+                    oS = first ? oSc : oS + (unsigned)DRS;
                     load_old(oT, oS, jn, hn, sn, un);
                 }
                 float4 um = make_float4(__uint_as_float(xa.x), __uint_as_float(xa.z), __uint_as_float(xb.x), __uint_as_float(xb.z));
@@ -624,33 +663,10 @@ __global__ void __launch_bounds__((NU + 2) * 32, (NU <= 4 ? 2 : 1)) k_sweep_patc
                     if (lane == 0) km0[r] = __uint_as_float(xv[r].x);
                     if (kill) h[r] = MAXV;
                 }
-                // ---- (5) rare: last planes of the grid, rows that may hold frozen nodes.  A node that must not change gets
-                //          NaN slowness: its update is NaN and fails `t < old` like every non-node slot.
-                if (edge || (unsigned)(a - wz_lo) < (unsigned)wz_cnt) {
-#pragma unroll
-                    for (int r = 0; r < R; ++r) {
-                        unsigned fm = ((unsigned)(a - wz_lo) < (unsigned)wz_cnt) ? (fzmask >> (r * 4)) & 15u : 0u;
-                        if (fm) {
-                            const long long eb = e0[r] + (long long)(a - r) * w.sm;
-                            unsigned fz = 0;
-                            if ((fm & 1u) && frozen_bit(frozen, eb + (RK ? 3 : 0))) fz |= 1u;
-                            if ((fm & 2u) && frozen_bit(frozen, eb + (RK ? 2 : 1))) fz |= 2u;
-                            if ((fm & 4u) && frozen_bit(frozen, eb + (RK ? 1 : 2))) fz |= 4u;
-                            if ((fm & 8u) && frozen_bit(frozen, eb + (RK ? 0 : 3))) fz |= 8u;
-                            fm = fz;
-                        }
-                        if (u0w + r > ulast) fm = 15u;
-                        if (fm & 1u) sl[r].x = QNAN;
-                        if (fm & 2u) sl[r].y = QNAN;
-                        if (fm & 4u) sl[r].z = QNAN;
-                        if (fm & 8u) sl[r].w = QNAN;
-                        if (r == R - 1 && u0w + r >= ulast) up = make_float4(MAXV, MAXV, MAXV, MAXV);   // no (u+1) plane
-                    }
-                }
 #if TTCR_T5_STEP_TRACE
                 if (tr) tr[2] = TTCR_T5_CLOCK();
 #endif
-                // ---- (6) update, last plane first (plane r reads the previous-step result of plane r-1); branch free
+                // ---- (5) update, last plane first (plane r reads the previous-step result of plane r-1); branch free
                 float4 nlast;
 #pragma unroll
                 for (int r = R - 1; r >= 0; --r) {
@@ -675,7 +691,7 @@ __global__ void __launch_bounds__((NU + 2) * 32, (NU <= 4 ? 2 : 1)) k_sweep_patc
                     tprev[r] = n;
                     told[r] = j;
                 }
-                // ---- (7) last plane of the patch -> warp wu+1 (shared ring) / tile U+1 (global mailbox); predicated, no branch
+                // ---- (6) last plane of the patch -> warp wu+1 (shared ring) / tile U+1 (global mailbox); predicated, no branch
                 {
                     const int row = a - (R - 1);
                     const bool inr = (unsigned)row < (unsigned)ulim;
@@ -693,16 +709,10 @@ __global__ void __launch_bounds__((NU + 2) * 32, (NU <= 4 ? 2 : 1)) k_sweep_patc
 #pragma unroll
                 for (int r = 0; r < R; ++r) { jp[r] = jn[r]; h[r] = hn[r]; sl[r] = sn[r]; }
                 up = un;
-                if ((a & (C - 1)) == C - 1) {   // end of a chunk
-                    dead = __any_sync(0xffffffffu, dead);
-                    if (dead) break;
-                    if (p.trace && threadIdx.x == 0) {
-                        const int q = nrows / 4, a1 = a + 1;
-                        if (a1 - C < q && a1 >= q) p.trace[tile * 8 + 2] = gtime();
-                        if (a1 - C < 2 * q && a1 >= 2 * q) p.trace[tile * 8 + 3] = gtime();
-                        if (a1 - C < 3 * q && a1 >= 3 * q) p.trace[tile * 8 + 4] = gtime();
-                    }
-                }
+            };
+            for (int a = 0; a < nsteps_w && !dead_u; a += 2) {   // nsteps_w is a multiple of C, hence even
+                step(a);
+                step(a + 1);
             }
             gc = g0 + nch;
             if (lane == 0) sts_i(a_myprog, 1 << 29);   // release anybody still waiting for this warp
