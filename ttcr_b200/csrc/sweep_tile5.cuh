@@ -66,6 +66,7 @@ struct Tile5Params {
     long long* trace;
     int trace_a0, trace_tile;   // per-step clocks: first step and tile of the window (debug)
     int* dbg;                   // [tile][NU + 2][16]: what every warp was waiting for when a march was given up
+    int pf_chunks;              // L2 prefetch distance of the loader, in chunks (0 = off)
 };
 
 constexpr int t5_round128(int x) { return (x + 127) / 128 * 128; }
@@ -158,6 +159,10 @@ __device__ __forceinline__ void st_mail2_if(unsigned long long* p, unsigned tag,
         "@q st.relaxed.gpu.global.v2.b64 [%0], {x, y};\n\t}" ::"l"(p),
         "r"(__float_as_uint(a)), "r"(tag), "r"(__float_as_uint(b)), "r"(on)
         : "memory");
+}
+// TMA prefetch of a box into L2 (no shared-memory slot needed: L2 is the deep buffer of the march)
+__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* map, int x, int y, int z) {
+    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(map), "r"(x), "r"(y), "r"(z) : "memory");
 }
 template <bool REV> __device__ __forceinline__ float4 ord4(float4 v) { return REV ? make_float4(v.w, v.z, v.y, v.x) : v; }
 
@@ -293,7 +298,7 @@ __global__ void __launch_bounds__((NU + 2) * 32, (NU <= 4 ? 2 : 1)) k_sweep_patc
                     {
                         const long long t0 = clock64();
                         while (lds_i(a_prog0) < a - DU + 1 || lds_i(a_progl) < a - DV + 1) {
-                            __nanosleep(100);
+                            __nanosleep(200);
                             if (lds_i(a_dead)) { dead = true; break; }
                             if (clock64() - t0 > spin_cycles) { give_up(30, a); dead = true; break; }
                         }
@@ -375,34 +380,43 @@ __global__ void __launch_bounds__((NU + 2) * 32, (NU <= 4 ? 2 : 1)) k_sweep_patc
             long long t0 = clock64();
             bool dead = false;
             int c = 0;
-            while (c < nch) {
-                if (c < NCH || lds_i(a_wprog) >= (c - NCH + 1) * C) {
+            // One uniform loop for the whole warp (lanes spinning separately would issue 8 instruction streams and steal
+            // the issue slots of the compute warps on this scheduler): look, issue where a slot is free, sleep.
+            for (;;) {
+                const bool todo = c < nch;
+                if (!__any_sync(0xffffffffu, todo)) break;
+                const bool go = todo && (c < NCH || lds_i(a_wprog) >= (c - NCH + 1) * C);
+                if (go) {
                     const unsigned g = gc + (unsigned)c;
                     const unsigned slot = g % NCH;
                     const unsigned mb = a_bar + 8 * slot;
                     mbar_expect_tx(mb, (R + 1) * L::TPL + R * L::SPL);
                     tma_load_3d(a_ring + slot * L::CHB_T, &tmT, xT, yT + c * dyc, zT, mb);
                     tma_load_3d(a_ring + NCH * L::CHB_T + slot * L::CHB_S, &tmS, xS, yS + c * dyc, zS, mb);
+                    if (c + p.pf_chunks < nch && p.pf_chunks > 0) {   // pull a later chunk from DRAM into L2 now
+                        tma_prefetch_3d(&tmT, xT, yT + (c + p.pf_chunks) * dyc, zT);
+                        tma_prefetch_3d(&tmS, xS, yS + (c + p.pf_chunks) * dyc, zS);
+                    }
                     ++c;
+                }
+                if (__any_sync(0xffffffffu, go)) {
                     t0 = clock64();
-                } else {
-                    __nanosleep(200);   // a chunk is C steps of slack: do not steal issue slots from the compute warps
-                    if (lds_i(a_dead)) { dead = true; }
-                    else if (clock64() - t0 > spin_cycles) dead = true;
-                    if (dead) {
+                    continue;   // somebody made progress: look again at once (another slot may be free)
+                }
+                __nanosleep(250);   // a chunk is C steps of slack
+                if (lds_i(a_dead) || clock64() - t0 > spin_cycles) {
+                    if (todo) {
                         int* const q = p.dbg + ((size_t)tile * (NU + 2) + NU + 1) * 16 + (wu & 1) * 8;
                         const int pg = lds_i(a_wprog);
                         const unsigned ur = sbase + L::OFF_U + wu * L::URING + (unsigned)(pg & (DU - 1)) * 1024;
                         q[0] = 50; q[1] = c; q[2] = pg; q[3] = wu; q[4] = lds_i(ur + 4);          // tag of lane 0, word 0
                         q[5] = lds_i(ur + 16 * 13 + 4); q[6] = lds_i(ur + 512 + 16 * 31 + 12);    // lane 13 word 0, lane 31 word 3
                         q[7] = lds_i(sbase + L::OFF_V + wu * L::VRING + (unsigned)(pg & (DV - 1)) * (R * 8) + 4);
+                        if (!lds_i(a_dead) && atomicCAS(&p.ctrl[1], 0, 50) == 0) { p.ctrl[2] = tile; p.ctrl[3] = c; p.ctrl[4] = pg; p.ctrl[5] = wu; }
                     }
-                    if (dead) {
-                        if (atomicCAS(&p.ctrl[1], 0, 50) == 0) { p.ctrl[2] = tile; p.ctrl[3] = c; p.ctrl[4] = lds_i(a_wprog); p.ctrl[5] = wu; }
-                        sts_i(a_dead, 1);
-                        dead = true;
-                        break;
-                    }
+                    sts_i(a_dead, 1);
+                    dead = true;
+                    break;
                 }
             }
             // a march that was given up may leave copies in flight: they must land before the CTA goes on
@@ -810,6 +824,7 @@ inline int tile5_launch(TileState& s, Tile5State& s5, const TileOptions& o, int 
         mail.serial = s5.serial = 1;
     }
     p.order = s5.d_order; p.partial = s5.d_partial; p.dbg = s5.d_dbg;
+    p.pf_chunks = getenv("TTCR_B200_PF") ? atoi(getenv("TTCR_B200_PF")) : 0;
     const int key = 5000000 + PU * 100000 + w.vlo;   // the order depends on the tile height and on where the lanes start
     if (s5.order_key != key || s5.ntiles != p.ntiles) {
         // ticket order: a linear extension of (U-1,V) < (U,V), (U,V-1) < (U,V), sorted by estimated start time
