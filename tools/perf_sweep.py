@@ -35,7 +35,8 @@ def check():
         for kernel, opts in ((1, {}), (2, {}), (2, {"tile_warps": 4, "tile_urows": 2, "tile_rows": 2, "tile_depth": 4}),
                              (3, {}), (3, {"tile_warps": 4, "tile_rows": 2}), (3, {"tile_rows": 16, "ctas_per_sm": 1}),
                              (4, {}), (4, {"tile_warps": 16}), (4, {"tile_depth": 4, "ctas_per_sm": 1}),
-                             (5, {"tile_warps": 4}), (5, {"tile_warps": 8}), (5, {"tile_urows": 2, "ctas_per_sm": 1})):
+                             (5, {"tile_warps": 4}), (5, {"tile_warps": 8}), (5, {"tile_warps": 8, "tile_depth": 16}),
+                             (5, {"tile_urows": 2, "ctas_per_sm": 1})):
             g = Grid3d(x, y, z, cell_slowness=0, tt_from_rp=False, weno=0, dtype=dtype)
             g.set_option("kernel", kernel)
             for k, v in opts.items():
@@ -62,7 +63,7 @@ def timing(sizes):
         g = Grid3d(x, x, x, cell_slowness=0, tt_from_rp=False, weno=0, dtype=np.float32)
         g.set_slowness(s)
         print(f"--- {n}^3 device bytes {g.device_bytes() / 2**30:.2f} GiB", flush=True)
-        combos = [dict(kernel=5, tile_warps=w, tile_urows=r, ctas_per_sm=c) for w, r, c in ((8, 1, 0), (4, 1, 0), (4, 1, 1), (4, 2, 0))]
+        combos = [dict(kernel=5, tile_warps=w, tile_urows=r, tile_depth=dp) for w, r, dp in ((8, 1, 8), (8, 1, 16), (4, 1, 8), (4, 2, 8))]
         combos += [dict(kernel=4, tile_warps=8, tile_depth=4, ctas_per_sm=0)]
         for src in ([0.0, 0.0, 0.0],):
             for c in combos:

@@ -71,29 +71,32 @@ struct Tile5Params {
 
 constexpr int t5_round128(int x) { return (x + 127) / 128 * 128; }
 
-template <int NU, int R, int C, int NCH, int DU_>
+template <int NU, int R, int C, int NCH, int DU_, int NG>
 struct Tile5Layout {
     static constexpr int PU = NU * R;
     static constexpr int TW = 132;                                   // floats per traveltime row: 128 + 4
     static constexpr int TROW = TW * 4, SROW = 128 * 4;
     static constexpr int TPL = C * TROW, SPL = C * SROW;             // bytes per plane of a box
-    static constexpr int CHB_T = t5_round128((R + 1) * TPL), CHB_S = R * SPL;
-    static constexpr int WARP_BYTES = NCH * (CHB_T + CHB_S);
+    // The NU warps form NG ring groups of GW warps (GP planes): one TMA box pair per group and chunk (issuing a
+    // UTMALDG costs the loader ~400 cycles, so one pair per WARP starves the march), planes skewed by the tensor map.
+    static constexpr int GW = NU / NG, GP = GW * R;
+    static constexpr int CHB_T = t5_round128((GP + 1) * TPL), CHB_S = GP * SPL;
+    static constexpr int GROUP_BYTES = NCH * (CHB_T + CHB_S);
     static constexpr int DU = DU_;                                   // rows per U ring
     static constexpr int URING = DU * 1024;
     static constexpr int DV = 64;                                    // macro-steps per V ring
     static constexpr int VRING = DV * R * 8;
-    static constexpr int OFF_RING = 0;                               // NU x [T slots][S slots]
-    static constexpr int OFF_U = OFF_RING + NU * WARP_BYTES;         // NU U rings (ring w = input of warp w)
+    static constexpr int OFF_RING = 0;                               // NG x [T slots][S slots]
+    static constexpr int OFF_U = OFF_RING + NG * GROUP_BYTES;        // NU U rings (ring w = input of warp w)
     static constexpr int OFF_V = OFF_U + NU * URING;                 // NU V rings
-    static constexpr int OFF_BAR = OFF_V + NU * VRING;               // NU x NCH mbarriers
-    static constexpr int OFF_PROG = OFF_BAR + NU * NCH * 8;          // NU progress counters
+    static constexpr int OFF_BAR = OFF_V + NU * VRING;               // NG x NCH mbarriers
+    static constexpr int OFF_PROG = OFF_BAR + NG * NCH * 8;          // NU progress counters
     static constexpr int OFF_FLG = OFF_PROG + NU * 4;                // dead, tile
     static constexpr int OFF_RED = (OFF_FLG + 8 + 7) / 8 * 8;
     static constexpr int BYTES = OFF_RED + NU * 8;
-    static_assert(CHB_S % 128 == 0 && WARP_BYTES % 128 == 0 && URING % 128 == 0, "TMA destinations must stay 128-byte aligned");
+    static_assert(NU % NG == 0 && CHB_S % 128 == 0 && GROUP_BYTES % 128 == 0 && URING % 128 == 0, "TMA destinations must stay 128-byte aligned");
     static_assert(DV >= NU * R + DU + 8, "V ring too shallow for the skew between the warps");
-    static_assert(R + C + 4 <= GUARD, "guard rows too few");
+    static_assert(GP + C + 4 <= GUARD, "guard rows too few");
 };
 
 // ---- shared / global access helpers ---------------------------------------------------------------
@@ -186,13 +189,13 @@ __device__ __noinline__ int t5_wait_words(unsigned ar, unsigned av, unsigned a_n
 }
 
 // RJ: the sweep runs the row axis downwards, RK: the lane axis (boxes arrive in memory order).
-template <int NU, int R, int C, int NCH, int DU_, bool RJ, bool RK>
+template <int NU, int R, int C, int NCH, int DU_, int NG, bool RJ, bool RK>
 __global__ void __launch_bounds__((NU + 2) * 32, (NU <= 4 ? 2 : 1)) k_sweep_patch(const __grid_constant__ CUtensorMap tmT,
                                                                   const __grid_constant__ CUtensorMap tmS, Tile5Params p,
                                                                   Tile5Mail mail, float* __restrict__ tt,
                                                                   const uint32_t* __restrict__ frozen, float dx) {
-    using L = Tile5Layout<NU, R, C, NCH, DU_>;
-    constexpr int PU = L::PU, DU = L::DU, DV = L::DV;
+    using L = Tile5Layout<NU, R, C, NCH, DU_, NG>;
+    constexpr int PU = L::PU, DU = L::DU, DV = L::DV, GW = L::GW, GP = L::GP;
     constexpr int MG = Tile5Mail::MARGIN;
     constexpr int G = 2;   // rows of mailbox loads the importer keeps in flight (deeper = more stale polls = larger lag)
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -205,10 +208,10 @@ __global__ void __launch_bounds__((NU + 2) * 32, (NU <= 4 ? 2 : 1)) k_sweep_patc
     const unsigned a_prog = sbase + L::OFF_PROG;
     const unsigned serial = mail.serial;
     const long long spin_cycles = p.spin_limit << 9;
-    unsigned gc = 0;   // chunks this warp has consumed since the kernel started: slot gc % NCH, parity (gc / NCH) & 1
+    unsigned gc = 0;   // chunks this warp's ring group has been sent since the kernel started: slot gc % NCH, parity (gc / NCH) & 1
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < NU * NCH; ++i) mbar_init(sbase + L::OFF_BAR + 8 * i, 1);
+        for (int i = 0; i < NG * NCH; ++i) mbar_init(sbase + L::OFF_BAR + 8 * i, 1);
         fence_mbar_init();
     }
 
@@ -236,6 +239,13 @@ __global__ void __launch_bounds__((NU + 2) * 32, (NU <= 4 ? 2 : 1)) k_sweep_patc
         const int nsteps = nrows + R - 1;                      // macro-steps (plane r runs r rows behind plane 0)
         const int nchunks = (nsteps + C - 1) / C;
         const int nA = nchunks * C;                            // macro-steps executed (the surplus ones touch no node)
+        // A ring group's boxes are indexed by s = step + (plane of the group): warp wg reads box row a + wg*R at step a
+        auto group_chunks = [&](int grp_) {   // boxes sent to ring group grp_: up to the last row its last marching warp reads
+            const int first_plane = u0 + grp_ * GP;
+            if (first_plane > w.nu - 1) return 0;
+            const int wl_rel = min(GW - 1, (w.nu - 1 - first_plane) / R);
+            return (nA + wl_rel * R + C - 1) / C;
+        };
         const bool has_u = U > 0, has_v = V > 0;
         const bool has_right = v0 + 128 < w.vhi;
         const bool has_down = U + 1 < p.nU;
@@ -360,23 +370,31 @@ __global__ void __launch_bounds__((NU + 2) * 32, (NU <= 4 ? 2 : 1)) k_sweep_patc
             // skew is in the tensor map, see make_tile5_map).  T box: local rows cC - r + 1 .. of plane r = 0 .. R
             // (the "next old row" of every plane at every step of the chunk), S box: local rows cC - r .. of plane
             // r = 0 .. R-1.  Chunk c may be issued once the warp has finished chunk c - NCH (same ring slot).
-            const int wu = lane;
-            const int u0w = u0 + wu * R;
-            const int nch = (wu < NU && u0w <= w.nu - 1) ? nchunks : 0;
-            const unsigned a_ring = sbase + L::OFF_RING + wu * L::WARP_BYTES;
-            const unsigned a_bar = sbase + L::OFF_BAR + wu * NCH * 8;
+            const int wu = lane;                               // (here: the ring group this lane feeds)
+            const int u0w = u0 + wu * GP;                      // first plane of the group
+            const int nch = wu < NG ? group_chunks(wu) : 0;
+            const unsigned a_ring = sbase + L::OFF_RING + (wu < NG ? wu : 0) * L::GROUP_BYTES;
+            const unsigned a_bar = sbase + L::OFF_BAR + (wu < NG ? wu : 0) * NCH * 8;
             const bool minus_map = (w.ri != 0) == (w.rj != 0);
             const int xT = RK ? p.d.kpad - 132 - v0 : v0;
             const int xS = RK ? p.d.kpad - 128 - v0 : v0;
-            const int zT = w.ri ? p.d.ni - 1 - (u0w + R) : u0w;
-            const int zS = w.ri ? p.d.ni - 1 - (u0w + R - 1) : u0w;
-            const int rT0 = w.ri ? R : 0, rS0 = w.ri ? R - 1 : 0;
+            const int zT = w.ri ? p.d.ni - 1 - (u0w + GP) : u0w;
+            const int zS = w.ri ? p.d.ni - 1 - (u0w + GP - 1) : u0w;
+            const int rT0 = w.ri ? GP : 0, rS0 = w.ri ? GP - 1 : 0;
             const int yT0 = RJ ? GUARD + (w.nm - 1) - (m_first - rT0 + C) : GUARD + m_first - rT0 + 1;
             const int yS0 = RJ ? GUARD + (w.nm - 1) - (m_first - rS0 + C - 1) : GUARD + m_first - rS0;
             const int yT = minus_map ? yT0 + zT : yT0 - zT + p.d.ni;   // the "plus" map is based ni rows below the array
             const int yS = minus_map ? yS0 + zS : yS0 - zS + p.d.ni;
             const int dyc = RJ ? -C : C;                       // rows per chunk in memory direction
-            const unsigned a_wprog = a_prog + 4 * (wu < NU ? wu : 0);
+            // readers of the group's ring: its warps that march (wfirst .. wlast)
+            const int wfirst = (wu < NG ? wu : 0) * GW;
+            const int wlast = wfirst + max(0, min(GW - 1, (w.nu - 1 - u0w) / R));
+            const unsigned a_wprog = a_prog + 4 * wlast;
+            auto ring_progress = [&]() {   // box rows below this index have been read by everybody
+                int m = 1 << 30;
+                for (int ww = wfirst; ww <= wlast; ++ww) m = min(m, lds_i(a_prog + 4 * ww) + (ww - wfirst) * R);
+                return m;
+            };
             long long t0 = clock64();
             bool dead = false;
             int c = 0;
@@ -385,12 +403,13 @@ __global__ void __launch_bounds__((NU + 2) * 32, (NU <= 4 ? 2 : 1)) k_sweep_patc
             for (;;) {
                 const bool todo = c < nch;
                 if (!__any_sync(0xffffffffu, todo)) break;
-                const bool go = todo && (c < NCH || lds_i(a_wprog) >= (c - NCH + 1) * C);
+                // chunk c - NCH is read for the last time while step (c-NCH+1)*C - 2 prefetches its successor's operands
+                const bool go = todo && (c < NCH || ring_progress() >= (c - NCH + 1) * C - 1);
                 if (go) {
                     const unsigned g = gc + (unsigned)c;
                     const unsigned slot = g % NCH;
                     const unsigned mb = a_bar + 8 * slot;
-                    mbar_expect_tx(mb, (R + 1) * L::TPL + R * L::SPL);
+                    mbar_expect_tx(mb, (GP + 1) * L::TPL + GP * L::SPL);
                     tma_load_3d(a_ring + slot * L::CHB_T, &tmT, xT, yT + c * dyc, zT, mb);
                     tma_load_3d(a_ring + NCH * L::CHB_T + slot * L::CHB_S, &tmS, xS, yS + c * dyc, zS, mb);
                     if (c + p.pf_chunks < nch && p.pf_chunks > 0) {   // pull a later chunk from DRAM into L2 now
@@ -408,10 +427,10 @@ __global__ void __launch_bounds__((NU + 2) * 32, (NU <= 4 ? 2 : 1)) k_sweep_patc
                     if (todo) {
                         int* const q = p.dbg + ((size_t)tile * (NU + 2) + NU + 1) * 16 + (wu & 1) * 8;
                         const int pg = lds_i(a_wprog);
-                        const unsigned ur = sbase + L::OFF_U + wu * L::URING + (unsigned)(pg & (DU - 1)) * 1024;
+                        const unsigned ur = sbase + L::OFF_U + wlast * L::URING + (unsigned)(pg & (DU - 1)) * 1024;
                         q[0] = 50; q[1] = c; q[2] = pg; q[3] = wu; q[4] = lds_i(ur + 4);          // tag of lane 0, word 0
                         q[5] = lds_i(ur + 16 * 13 + 4); q[6] = lds_i(ur + 512 + 16 * 31 + 12);    // lane 13 word 0, lane 31 word 3
-                        q[7] = lds_i(sbase + L::OFF_V + wu * L::VRING + (unsigned)(pg & (DV - 1)) * (R * 8) + 4);
+                        q[7] = lds_i(sbase + L::OFF_V + wlast * L::VRING + (unsigned)(pg & (DV - 1)) * (R * 8) + 4);
                         if (!lds_i(a_dead) && atomicCAS(&p.ctrl[1], 0, 50) == 0) { p.ctrl[2] = tile; p.ctrl[3] = c; p.ctrl[4] = pg; p.ctrl[5] = wu; }
                     }
                     sts_i(a_dead, 1);
@@ -443,16 +462,17 @@ __global__ void __launch_bounds__((NU + 2) * 32, (NU <= 4 ? 2 : 1)) k_sweep_patc
             const int mail_v_out = (lane == 31 && has_right) ? 1 : 0;
             const unsigned tag_g = serial;
             // ---- ring addresses
-            const unsigned a_ring = sbase + L::OFF_RING + wu * L::WARP_BYTES;
-            const unsigned a_bar = sbase + L::OFF_BAR + wu * NCH * 8;
+            const int grp = wu / GW, wg = wu - grp * GW;       // ring group and position in it
+            const unsigned a_ring = sbase + L::OFF_RING + grp * L::GROUP_BYTES;
+            const unsigned a_bar = sbase + L::OFF_BAR + grp * NCH * 8;
             const int colT = RK ? 128 - 4 * lane : 4 * lane;   // column of the float4 in a 132-float row (memory order)
             const int colH = RK ? colT - 1 : colT + 4;         // column of lane v+4
             const int colS = RK ? 124 - 4 * lane : 4 * lane;
             unsigned aT[R + 1], aS[R];
 #pragma unroll
-            for (int r = 0; r <= R; ++r) aT[r] = a_ring + (w.ri ? R - r : r) * L::TPL + colT * 4;
+            for (int r = 0; r <= R; ++r) aT[r] = a_ring + (w.ri ? GP - (wg * R + r) : wg * R + r) * L::TPL + colT * 4;
 #pragma unroll
-            for (int r = 0; r < R; ++r) aS[r] = a_ring + NCH * L::CHB_T + (w.ri ? R - 1 - r : r) * L::SPL + colS * 4;
+            for (int r = 0; r < R; ++r) aS[r] = a_ring + NCH * L::CHB_T + (w.ri ? GP - 1 - (wg * R + r) : wg * R + r) * L::SPL + colS * 4;
             const int dH = (colH - colT) * 4;
             const unsigned a_uin = sbase + L::OFF_U + wu * L::URING + lane * 16;
             const unsigned a_uout = sbase + L::OFF_U + (wu + 1) * L::URING + lane * 16;   // not used by the last warp
@@ -548,20 +568,29 @@ __global__ void __launch_bounds__((NU + 2) * 32, (NU <= 4 ? 2 : 1)) k_sweep_patc
             // row i of a chunk slot sits at byte offset (RJ ? C-1-i : i) * row bytes: boxes arrive in memory order
             constexpr int RT0 = (RJ ? C - 1 : 0) * L::TROW, RS0 = (RJ ? C - 1 : 0) * L::SROW;
             constexpr int DRT = RJ ? -L::TROW : L::TROW, DRS = RJ ? -L::SROW : L::SROW;
+            const int soff = wg * R;   // this warp reads box row (step + soff) of its group's ring
+            const int nchunks_g = group_chunks(grp);
             unsigned oT = 0, oS = 0;   // byte offsets (slot + row) of the NEXT step's old values
             const float QNAN = __int_as_float(0x7fc00000);
             const int ulim = nrows;    // rows 0 .. nrows-1 of the last plane are handed on
 
             if (nch > 0) {
-                wait_chunk(g0);
-                oT = (g0 % NCH) * L::CHB_T + RT0;
-                oS = (g0 % NCH) * L::CHB_S + RS0;
+                const unsigned g = g0 + (unsigned)(soff / C);
+                wait_chunk(g);
+                oT = (g % NCH) * L::CHB_T + (unsigned)(RT0 + (soff % C) * DRT);
+                oS = (g % NCH) * L::CHB_S + (unsigned)(RS0 + (soff % C) * DRS);
                 load_old(oT, oS, jp, h, sl, up);
             }
             dead = __any_sync(0xffffffffu, dead);
             const int nsteps_w = dead ? 0 : nch * C;
 
             unsigned oTc = oT, oSc = oS;   // slot offsets (row 0) of the chunk after the current one, once it has landed
+            if (nch > 0 && (soff & (C - 1)) == C - 1) {   // the first step is the last row of its chunk
+                const unsigned g = g0 + (unsigned)(soff / C) + 1;
+                wait_chunk(g);
+                oTc = (g % NCH) * L::CHB_T + RT0;
+                oSc = (g % NCH) * L::CHB_S + RS0;
+            }
             bool dead_u = false;
             static_assert(C >= 2 && (C & (C - 1)) == 0, "steps per chunk: a power of two, at least 2");
 
@@ -597,7 +626,8 @@ __global__ void __launch_bounds__((NU + 2) * 32, (NU <= 4 ? 2 : 1)) k_sweep_patc
 #pragma unroll
                 for (int r = 0; r < R; ++r) bad |= xv[r].y ^ tag;
                 if (nxp < nx_need) bad |= 1u;
-                const bool f_bound = (a & (C - 1)) == C - 2;                        // time to make sure the next chunk has landed
+                const int sb = a + soff;                                             // box row of this step
+                const bool f_bound = (sb & (C - 1)) == C - 2;                       // time to make sure the next chunk has landed
                 const bool f_slow = edge || (unsigned)(a - wz_lo) < (unsigned)wz_cnt;
                 if (bad != 0 || f_bound || f_slow) {
                     if (bad) {   // the wait itself is out of line
@@ -619,8 +649,8 @@ __global__ void __launch_bounds__((NU + 2) * 32, (NU <= 4 ? 2 : 1)) k_sweep_patc
                         }
                     }
                     if (f_bound) {   // warp-uniform
-                        const int cn = a / C + 1;
-                        if (cn < nch) {
+                        const int cn = sb / C + 1;
+                        if (cn < nchunks_g) {
                             const unsigned g = g0 + (unsigned)cn;
                             wait_chunk(g);
                             oTc = (g % NCH) * L::CHB_T + RT0;
@@ -665,7 +695,7 @@ __global__ void __launch_bounds__((NU + 2) * 32, (NU <= 4 ? 2 : 1)) k_sweep_patc
                 float4 jn[R], sn[R], un;
                 float hn[R];
                 {
-                    const bool first = ((a + 1) & (C - 1)) == 0;   // the next step opens a chunk
+                    const bool first = ((sb + 1) & (C - 1)) == 0;   // the next step opens a chunk
                     oT = first ? oTc : oT + (unsigned)DRT;
                     oS = first ? oSc : oS + (unsigned)DRS;
                     load_old(oT, oS, jn, hn, sn, un);
@@ -728,7 +758,7 @@ __global__ void __launch_bounds__((NU + 2) * 32, (NU <= 4 ? 2 : 1)) k_sweep_patc
                 step(a);
                 step(a + 1);
             }
-            gc = g0 + nch;
+            gc = g0 + (unsigned)nchunks_g;   // what the loader sent to the group
             if (lane == 0) sts_i(a_myprog, 1 << 29);   // release anybody still waiting for this warp
             double dacc = (double)acc;
 #pragma unroll
@@ -773,11 +803,11 @@ inline void tile5_free(Tile5State& s) {
     s = Tile5State{};
 }
 
-template <int NU, int R, int C, int NCH, int DU_>
+template <int NU, int R, int C, int NCH, int DU_, int NG>
 inline int tile5_launch(TileState& s, Tile5State& s5, const TileOptions& o, int sm_count, const SweepView& w, const Dims& d,
                         float* tt, const float* slo, const uint32_t* frozen, const FrozenBox& fb, float dx, double* d_change,
                         cudaStream_t st) {
-    using L = Tile5Layout<NU, R, C, NCH, DU_>;
+    using L = Tile5Layout<NU, R, C, NCH, DU_, NG>;
     constexpr int PU = L::PU;
     Tile5Params p;
     p.w = w; p.d = d; p.fb = fb;
@@ -854,8 +884,8 @@ inline int tile5_launch(TileState& s, Tile5State& s5, const TileOptions& o, int 
         return cache.back().m;
     };
     const bool minus = (w.ri != 0) == (w.rj != 0);
-    const CUtensorMap tmT = get_map(tt, minus, L::TW, C, R + 1);
-    const CUtensorMap tmS = get_map(slo, minus, 128, C, R);
+    const CUtensorMap tmT = get_map(tt, minus, L::TW, C, L::GP + 1);
+    const CUtensorMap tmS = get_map(slo, minus, 128, C, L::GP);
     TCK(cudaMemsetAsync(s.d_ctrl, 0, sizeof(int), st));
     // (the four variants share one function-pointer type, so they are set up together, once)
     static int occ_cache = 0;
@@ -866,10 +896,10 @@ inline int tile5_launch(TileState& s, Tile5State& s5, const TileOptions& o, int 
             TCK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, (NU + 2) * 32, L::BYTES));
             return occ;
         };
-        int occ = prep(k_sweep_patch<NU, R, C, NCH, DU_, false, false>);
-        occ = std::min(occ, prep(k_sweep_patch<NU, R, C, NCH, DU_, false, true>));
-        occ = std::min(occ, prep(k_sweep_patch<NU, R, C, NCH, DU_, true, false>));
-        occ = std::min(occ, prep(k_sweep_patch<NU, R, C, NCH, DU_, true, true>));
+        int occ = prep(k_sweep_patch<NU, R, C, NCH, DU_, NG, false, false>);
+        occ = std::min(occ, prep(k_sweep_patch<NU, R, C, NCH, DU_, NG, false, true>));
+        occ = std::min(occ, prep(k_sweep_patch<NU, R, C, NCH, DU_, NG, true, false>));
+        occ = std::min(occ, prep(k_sweep_patch<NU, R, C, NCH, DU_, NG, true, true>));
         if (occ < 1) throw std::runtime_error("tile5 kernel does not fit on an SM");
         occ_cache = occ;
     }
@@ -878,9 +908,9 @@ inline int tile5_launch(TileState& s, Tile5State& s5, const TileOptions& o, int 
     const int grid = std::min(p.ntiles, occ * sm_count);
     auto launch = [&](auto kern) { kern<<<grid, (NU + 2) * 32, L::BYTES, st>>>(tmT, tmS, p, mail, tt, frozen, dx); };
     if (w.rj) {
-        if (w.rk) launch(k_sweep_patch<NU, R, C, NCH, DU_, true, true>); else launch(k_sweep_patch<NU, R, C, NCH, DU_, true, false>);
+        if (w.rk) launch(k_sweep_patch<NU, R, C, NCH, DU_, NG, true, true>); else launch(k_sweep_patch<NU, R, C, NCH, DU_, NG, true, false>);
     } else {
-        if (w.rk) launch(k_sweep_patch<NU, R, C, NCH, DU_, false, true>); else launch(k_sweep_patch<NU, R, C, NCH, DU_, false, false>);
+        if (w.rk) launch(k_sweep_patch<NU, R, C, NCH, DU_, NG, false, true>); else launch(k_sweep_patch<NU, R, C, NCH, DU_, NG, false, false>);
     }
     k_sum_partials<<<1, 256, 0, st>>>(s5.d_partial, p.ntiles * NU, d_change);
     TCK(cudaMemcpyAsync(s.h_abort, s.d_ctrl + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -927,11 +957,11 @@ template <>
 inline int tile5_sweep<float>(TileState& s, Tile5State& s5, const TileOptions& o, int sm_count, const SweepView& w,
                               const Dims& d, float* tt, const float* slo, const uint32_t* frozen, const FrozenBox& fb, float dx,
                               double* d_change, cudaStream_t st) {
-    // <compute warps, planes per thread, steps per TMA chunk, ring slots, rows per U ring>
-    if (o.rows >= 2) return tile5_launch<4, 2, 2, 3, 8>(s, s5, o, sm_count, w, d, tt, slo, frozen, fb, dx, d_change, st);
-    if (o.warps <= 4) return tile5_launch<4, 1, 4, 3, 8>(s, s5, o, sm_count, w, d, tt, slo, frozen, fb, dx, d_change, st);
-    if (o.depth >= 16) return tile5_launch<8, 1, 4, 3, 8>(s, s5, o, sm_count, w, d, tt, slo, frozen, fb, dx, d_change, st);
-    return tile5_launch<8, 1, 4, 3, 4>(s, s5, o, sm_count, w, d, tt, slo, frozen, fb, dx, d_change, st);
+    // <compute warps, planes per thread, steps per TMA chunk, ring slots, rows per U ring, ring groups>
+    if (o.rows >= 2) return tile5_launch<4, 2, 2, 3, 8, 4>(s, s5, o, sm_count, w, d, tt, slo, frozen, fb, dx, d_change, st);
+    if (o.warps <= 4) return tile5_launch<4, 1, 4, 4, 8, 1>(s, s5, o, sm_count, w, d, tt, slo, frozen, fb, dx, d_change, st);
+    if (o.depth >= 16) return tile5_launch<8, 1, 4, 5, 4, 1>(s, s5, o, sm_count, w, d, tt, slo, frozen, fb, dx, d_change, st);
+    return tile5_launch<8, 1, 4, 5, 4, 2>(s, s5, o, sm_count, w, d, tt, slo, frozen, fb, dx, d_change, st);
 }
 
 }  // namespace ttcrb200
