@@ -197,7 +197,7 @@ __global__ void __launch_bounds__((NU + 2) * 32, (NU <= 4 ? 2 : 1)) k_sweep_patc
     using L = Tile5Layout<NU, R, C, NCH, DU_, NG>;
     constexpr int PU = L::PU, DU = L::DU, DV = L::DV, GW = L::GW, GP = L::GP;
     constexpr int MG = Tile5Mail::MARGIN;
-    constexpr int G = 2;   // rows of mailbox loads the importer keeps in flight (deeper = more stale polls = larger lag)
+    constexpr int G = 2;   // rows of mailbox loads the importer keeps in flight (3 and 4 measured slower: more stale polls)
     extern __shared__ __align__(128) unsigned char smem_raw[];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -960,7 +960,7 @@ inline int tile5_sweep<float>(TileState& s, Tile5State& s5, const TileOptions& o
     // <compute warps, planes per thread, steps per TMA chunk, ring slots, rows per U ring, ring groups>
     if (o.rows >= 2) return tile5_launch<4, 2, 2, 3, 8, 4>(s, s5, o, sm_count, w, d, tt, slo, frozen, fb, dx, d_change, st);
     if (o.warps <= 4) return tile5_launch<4, 1, 4, 4, 8, 1>(s, s5, o, sm_count, w, d, tt, slo, frozen, fb, dx, d_change, st);
-    if (o.depth >= 16) return tile5_launch<8, 1, 4, 5, 4, 1>(s, s5, o, sm_count, w, d, tt, slo, frozen, fb, dx, d_change, st);
+    if (o.depth >= 16) return tile5_launch<8, 1, 4, 4, 8, 2>(s, s5, o, sm_count, w, d, tt, slo, frozen, fb, dx, d_change, st);
     return tile5_launch<8, 1, 4, 5, 4, 2>(s, s5, o, sm_count, w, d, tt, slo, frozen, fb, dx, d_change, st);
 }
 
