@@ -223,3 +223,25 @@ def interp(ncx, ncy, ncz, dx, tt_flat, rx, xmin=0.0, ymin=0.0, zmin=0.0, dtype=n
     f.argtypes = [C.c_size_t] * 3 + [ct] * 4 + [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
     f(ncx, ncy, ncz, dx, xmin, ymin, zmin, tt.ctypes.data, rx.ctypes.data, rx.shape[0], out.ctypes.data)
     return out
+
+
+def tt_from_rp(ncx, ncy, ncz, dx, tt_flat, s_node_flat, tx, t0, rx, xmin=0.0, ymin=0.0, zmin=0.0, dtype=np.float64):
+    """Grid3Drn::getTraveltimeFromRaypath (Grid3Drn.h:1103-1243) at receiver points, from a solved field."""
+    sfx, ct = _sfx(dtype)
+    lib = _load()
+    tt = np.ascontiguousarray(tt_flat, dtype=dtype).ravel()
+    sl = np.ascontiguousarray(s_node_flat, dtype=dtype).ravel()
+    tx = np.ascontiguousarray(np.asarray(tx, dtype=dtype).reshape(-1, 3))
+    t0 = np.ascontiguousarray(np.broadcast_to(np.asarray(t0, dtype=dtype), (tx.shape[0],)))
+    rx = np.ascontiguousarray(np.asarray(rx, dtype=dtype).reshape(-1, 3))
+    out = np.empty(rx.shape[0], dtype=dtype)
+    f = getattr(lib, "fsmo_tt_from_rp" + sfx)
+    f.restype = C.c_int
+    f.argtypes = [C.c_size_t] * 3 + [ct] * 4 + [C.c_void_p] * 4 + [C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p]
+    rc = f(ncx, ncy, ncz, dx, xmin, ymin, zmin, tt.ctypes.data, sl.ctypes.data, tx.ctypes.data, t0.ctypes.data, tx.shape[0],
+           rx.ctypes.data, rx.shape[0], out.ctypes.data)
+    if rc == 1:
+        raise RuntimeError("Error while computing raypaths: going outside grid")
+    if rc:
+        raise RuntimeError("raypath did not reach a source")
+    return out

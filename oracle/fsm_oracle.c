@@ -3,7 +3,8 @@
  * Plain-C, flat-array (SoA) CPU restatement of the reference's 3D rectilinear
  * fast-sweeping path: Grid3Drnfs / Grid3Drcfs drivers, Grid3Drn::sweep,
  * update_node, sweep_weno3, update_node_weno3, weno3_upwind, initFSM,
- * getTraveltime (file:line citations in fsm_oracle_impl.h).
+ * getTraveltime, getTraveltimeFromRaypath / grad / computeSlowness (file:line citations in
+ * fsm_oracle_impl.h).
  *
  * It is the checker for the CUDA path: only tests/, __graft_entry__.smoke() and
  * bench.py's cpu_baseline / --impl reference legs may load it.  The product
@@ -29,20 +30,28 @@
 
 #define REAL double
 #define SFX _d
+#define FABS fabs
+#define SQRT sqrt
 #define REAL_MAX DBL_MAX
 #define REAL_EPS DBL_EPSILON
 #include "fsm_oracle_impl.h"
 #undef REAL
 #undef SFX
+#undef FABS
+#undef SQRT
 #undef REAL_MAX
 #undef REAL_EPS
 
 #define REAL float
 #define SFX _f
+#define FABS fabsf
+#define SQRT sqrtf
 #define REAL_MAX FLT_MAX
 #define REAL_EPS FLT_EPSILON
 #include "fsm_oracle_impl.h"
 #undef REAL
 #undef SFX
+#undef FABS
+#undef SQRT
 #undef REAL_MAX
 #undef REAL_EPS

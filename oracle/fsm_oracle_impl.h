@@ -394,6 +394,207 @@ void FN(fsmo_interp)(size_t ncx, size_t ncy, size_t ncz, REAL dx, REAL xmin, REA
     }
 }
 
+/* ---- receiver traveltimes along raypaths: Grid3Drn::getTraveltimeFromRaypath, Grid3Drn.h:1103-1243 -----------
+ * with its helpers grad (4th-order centred differences of interpolated traveltimes, :1032-1100; note the x axis
+ * starts its stencil at pt.x - dx, the other two at pt - d/2), getIJK (:239-243) and computeSlowness (:2451-2676,
+ * processVel == false: slowness interpolated with Interpolator::linear / bilinear / trilinear, Interpolator.h:37-85).
+ * Mixed precision is the reference's: REAL variables, double literals. */
+static REAL FN(tt_at_)(size_t ncx, size_t ncy, size_t ncz, REAL dx, REAL xmin, REAL ymin, REAL zmin, const REAL *tt,
+                       REAL px, REAL py, REAL pz) {
+    REAL rx[3] = {px, py, pz}, out;
+    FN(fsmo_interp)(ncx, ncy, ncz, dx, xmin, ymin, zmin, tt, rx, 1, &out);
+    return out;
+}
+
+static REAL FN(slow_at_)(size_t ncx, size_t ncy, size_t ncz, REAL dx, REAL xmin, REAL ymin, REAL zmin, const REAL *sl,
+                         REAL px, REAL py, REAL pz) {
+    const size_t nnx = ncx + 1, nny = ncy + 1, nnz = ncz + 1;
+    const double small = 1.e-4, small2 = small * small;
+    ptrdiff_t onX = -1, onY = -1, onZ = -1;
+    /* the reference scans all nodes of an axis for |p - (min + n d)| < small2; only the nodes around p can match */
+    {
+        const ptrdiff_t c = (ptrdiff_t)floor((double)(px - xmin) / (double)dx);
+        for (ptrdiff_t n = c - 1 < 0 ? 0 : c - 1; n <= c + 2 && n < (ptrdiff_t)nnx; ++n)
+            if (FABS(px - (xmin + n * dx)) < small2) { onX = n; break; }
+    }
+    {
+        const ptrdiff_t c = (ptrdiff_t)floor((double)(py - ymin) / (double)dx);
+        for (ptrdiff_t n = c - 1 < 0 ? 0 : c - 1; n <= c + 2 && n < (ptrdiff_t)nny; ++n)
+            if (FABS(py - (ymin + n * dx)) < small2) { onY = n; break; }
+    }
+    {
+        const ptrdiff_t c = (ptrdiff_t)floor((double)(pz - zmin) / (double)dx);
+        for (ptrdiff_t n = c - 1 < 0 ? 0 : c - 1; n <= c + 2 && n < (ptrdiff_t)nnz; ++n)
+            if (FABS(pz - (zmin + n * dx)) < small2) { onZ = n; break; }
+    }
+#define SN(ii, jj, kk) sl[((size_t)(kk) * nny + (size_t)(jj)) * nnx + (size_t)(ii)]
+    if (onX != -1 && onY != -1 && onZ != -1) return SN(onX, onY, onZ);
+    const unsigned i = (unsigned)(small + (px - xmin) / dx);
+    const unsigned j = (unsigned)(small + (py - ymin) / dx);
+    const unsigned k = (unsigned)(small + (pz - zmin) / dx);
+    REAL x[3], y[3], z[3], s[8];
+    if (onX != -1 && onY != -1) {
+        s[0] = SN(onX, onY, k); s[1] = SN(onX, onY, k + 1);
+        x[0] = pz; x[1] = zmin + k * dx; x[2] = zmin + (k + 1) * dx;
+        return (s[0] * (x[2] - x[0]) + s[1] * (x[0] - x[1])) / (x[2] - x[1]);
+    } else if (onX != -1 && onZ != -1) {
+        s[0] = SN(onX, j, onZ); s[1] = SN(onX, j + 1, onZ);
+        x[0] = py; x[1] = ymin + j * dx; x[2] = ymin + (j + 1) * dx;
+        return (s[0] * (x[2] - x[0]) + s[1] * (x[0] - x[1])) / (x[2] - x[1]);
+    } else if (onY != -1 && onZ != -1) {
+        s[0] = SN(i, onY, onZ); s[1] = SN(i + 1, onY, onZ);
+        x[0] = px; x[1] = xmin + i * dx; x[2] = xmin + (i + 1) * dx;
+        return (s[0] * (x[2] - x[0]) + s[1] * (x[0] - x[1])) / (x[2] - x[1]);
+    } else if (onX != -1 || onY != -1 || onZ != -1) {
+        if (onX != -1) {
+            s[0] = SN(onX, j, k); s[1] = SN(onX, j, k + 1); s[2] = SN(onX, j + 1, k); s[3] = SN(onX, j + 1, k + 1);
+            x[0] = py; y[0] = pz; x[1] = ymin + j * dx; y[1] = zmin + k * dx; x[2] = ymin + (j + 1) * dx; y[2] = zmin + (k + 1) * dx;
+        } else if (onY != -1) {
+            s[0] = SN(i, onY, k); s[1] = SN(i, onY, k + 1); s[2] = SN(i + 1, onY, k); s[3] = SN(i + 1, onY, k + 1);
+            x[0] = px; y[0] = pz; x[1] = xmin + i * dx; y[1] = zmin + k * dx; x[2] = xmin + (i + 1) * dx; y[2] = zmin + (k + 1) * dx;
+        } else {
+            s[0] = SN(i, j, onZ); s[1] = SN(i, j + 1, onZ); s[2] = SN(i + 1, j, onZ); s[3] = SN(i + 1, j + 1, onZ);
+            x[0] = px; y[0] = py; x[1] = xmin + i * dx; y[1] = ymin + j * dx; x[2] = xmin + (i + 1) * dx; y[2] = ymin + (j + 1) * dx;
+        }
+        return (s[0] * (x[2] - x[0]) * (y[2] - y[0]) + s[1] * (x[2] - x[0]) * (y[0] - y[1]) + s[2] * (x[0] - x[1]) * (y[2] - y[0]) +
+                s[3] * (x[0] - x[1]) * (y[0] - y[1])) /
+               ((x[2] - x[1]) * (y[2] - y[1]));
+    }
+    s[0] = SN(i, j, k); s[1] = SN(i, j, k + 1); s[2] = SN(i, j + 1, k); s[3] = SN(i, j + 1, k + 1);
+    s[4] = SN(i + 1, j, k); s[5] = SN(i + 1, j, k + 1); s[6] = SN(i + 1, j + 1, k); s[7] = SN(i + 1, j + 1, k + 1);
+    x[0] = px; y[0] = py; z[0] = pz;
+    x[1] = xmin + i * dx; y[1] = ymin + j * dx; z[1] = zmin + k * dx;
+    x[2] = xmin + (i + 1) * dx; y[2] = ymin + (j + 1) * dx; z[2] = zmin + (k + 1) * dx;
+#undef SN
+    return (s[0] * (x[2] - x[0]) * (y[2] - y[0]) * (z[2] - z[0]) + s[1] * (x[2] - x[0]) * (y[2] - y[0]) * (z[0] - z[1]) +
+            s[2] * (x[2] - x[0]) * (y[0] - y[1]) * (z[2] - z[0]) + s[3] * (x[2] - x[0]) * (y[0] - y[1]) * (z[0] - z[1]) +
+            s[4] * (x[0] - x[1]) * (y[2] - y[0]) * (z[2] - z[0]) + s[5] * (x[0] - x[1]) * (y[2] - y[0]) * (z[0] - z[1]) +
+            s[6] * (x[0] - x[1]) * (y[0] - y[1]) * (z[2] - z[0]) + s[7] * (x[0] - x[1]) * (y[0] - y[1]) * (z[0] - z[1])) /
+           ((x[2] - x[1]) * (y[2] - y[1]) * (z[2] - z[1]));
+}
+
+/* one axis of grad(): stencil points p1..p4 (first = p - off), shifted inwards at the grid faces */
+static void FN(stencil_)(REAL p, REAL off, REAL d, REAL lo, REAL hi, REAL q[4]) {
+    REAL p1 = p - off;
+    REAL p2 = p1 + 0.5 * d, p3 = p1 + 1.5 * d, p4 = p1 + 2.0 * d;
+    if (p1 <= lo) {
+        p1 = lo; p2 = p1 + 0.5 * d; p3 = p1 + 1.5 * d; p4 = p1 + 2.0 * d;
+    } else if (p4 >= hi) {
+        p4 = hi; p3 = p4 - 0.5 * d; p2 = p4 - 1.5 * d; p1 = p4 - 2.0 * d;
+    }
+    q[0] = p1; q[1] = p2; q[2] = p3; q[3] = p4;
+}
+
+static int FN(sgn_)(REAL v) { return v > 0 ? 1 : (v < 0 ? -1 : 0); }   /* boost::math::sign */
+
+/* returns 0, or 1 when a ray leaves the grid (the reference throws), 2 when it does not reach a source */
+int FN(fsmo_tt_from_rp)(size_t ncx, size_t ncy, size_t ncz, REAL dx, REAL xmin, REAL ymin, REAL zmin, const REAL *tt,
+                        const REAL *sl, const REAL *tx, const REAL *t0, size_t ntx, const REAL *rx, size_t nrx, REAL *out) {
+    const double small2 = 1.e-8;
+    const REAL xmax = xmin + ncx * dx, ymax = ymin + ncy * dx, zmax = zmin + ncz * dx;   /* Grid3Drn ctor, :63-65 */
+    const REAL k1 = 1. / 24., k2 = 9. / 8.;
+    const REAL maxDist = SQRT(dx * dx + dx * dx + dx * dx);
+#define TTAT(a, b, c) FN(tt_at_)(ncx, ncy, ncz, dx, xmin, ymin, zmin, tt, a, b, c)
+#define SLAT(a, b, c) FN(slow_at_)(ncx, ncy, ncz, dx, xmin, ymin, zmin, sl, a, b, c)
+#define DIST(ax, ay, az, bx, by, bz) SQRT(((ax) - (bx)) * ((ax) - (bx)) + ((ay) - (by)) * ((ay) - (by)) + ((az) - (bz)) * ((az) - (bz)))
+    for (size_t r = 0; r < nrx; ++r) {
+        const REAL Rx = rx[3 * r], Ry = rx[3 * r + 1], Rz = rx[3 * r + 2];
+        REAL ttr = 0.0;
+        int done = 0;
+        for (size_t ns = 0; ns < ntx; ++ns)
+            if (Rx == tx[3 * ns] && Ry == tx[3 * ns + 1] && Rz == tx[3 * ns + 2]) { ttr = t0[ns]; done = 1; break; }
+        if (done) { out[r] = ttr; continue; }
+        REAL px = Rx, py = Ry, pz = Rz;   /* prev_pt */
+        REAL cx = Rx, cy = Ry, cz = Rz;   /* curr_pt */
+        REAL s1 = SLAT(cx, cy, cz), s2;
+        int reached = 0;
+        size_t guard = 0;
+        const size_t guard_max = 16 * (ncx + ncy + ncz) + 1024;
+        while (!reached) {
+            if (++guard > guard_max) return 2;
+            REAL q[4], gx, gy, gz;
+            FN(stencil_)(cx, dx, dx, xmin, xmax, q);          /* x: first point at pt.x - dx (sic) */
+            gx = (k1 * TTAT(q[0], cy, cz) - k2 * TTAT(q[1], cy, cz) + k2 * TTAT(q[2], cy, cz) - k1 * TTAT(q[3], cy, cz)) / dx;
+            FN(stencil_)(cy, dx / 2.0, dx, ymin, ymax, q);
+            gy = (k1 * TTAT(cx, q[0], cz) - k2 * TTAT(cx, q[1], cz) + k2 * TTAT(cx, q[2], cz) - k1 * TTAT(cx, q[3], cz)) / dx;
+            FN(stencil_)(cz, dx / 2.0, dx, zmin, zmax, q);
+            gz = (k1 * TTAT(cx, cy, q[0]) - k2 * TTAT(cx, cy, q[1]) + k2 * TTAT(cx, cy, q[2]) - k1 * TTAT(cx, cy, q[3])) / dx;
+            gx *= (REAL)-1.0; gy *= (REAL)-1.0; gz *= (REAL)-1.0;
+            {
+                /* one step against the gradient, to the next grid plane */
+                ptrdiff_t i = (ptrdiff_t)(small2 + (cx - xmin) / dx);
+                ptrdiff_t j = (ptrdiff_t)(small2 + (cy - ymin) / dx);
+                ptrdiff_t k = (ptrdiff_t)(small2 + (cz - zmin) / dx);
+                REAL xp = xmin + dx * (i + (FN(sgn_)(gx) > 0.0 ? 1.0 : 0.0));
+                REAL yp = ymin + dx * (j + (FN(sgn_)(gy) > 0.0 ? 1.0 : 0.0));
+                REAL zp = zmin + dx * (k + (FN(sgn_)(gz) > 0.0 ? 1.0 : 0.0));
+                if (FABS(xp - cx) < small2) xp += dx * FN(sgn_)(gx);
+                if (FABS(yp - cy) < small2) yp += dx * FN(sgn_)(gy);
+                if (FABS(zp - cz) < small2) zp += dx * FN(sgn_)(gz);
+                const REAL ax = gx != 0.0 ? (xp - cx) / gx : REAL_MAX;
+                const REAL ay = gy != 0.0 ? (yp - cy) / gy : REAL_MAX;
+                const REAL az = gz != 0.0 ? (zp - cz) / gz : REAL_MAX;
+                if (ax < ay && ax < az) {
+                    cx += ax * gx; cy += ax * gy; cz += ax * gz; cx = xp;
+                } else if (ay < az) {
+                    cx += ay * gx; cy += ay * gy; cz += ay * gz; cy = yp;
+                } else {
+                    cx += az * gx; cy += az * gy; cz += az * gz; cz = zp;
+                }
+                if (cx < xmin || cx > xmax || cy < ymin || cy > ymax || cz < zmin || cz > zmax) return 1;
+                s2 = SLAT(cx, cy, cz);
+                ttr += 0.5 * (s1 + s2) * DIST(px, py, pz, cx, cy, cz);
+                s1 = s2;
+                px = cx; py = cy; pz = cz;
+                /* are we close enough to one of the Tx points?  (the reference does not leave this loop early) */
+                for (size_t ns = 0; ns < ntx; ++ns) {
+                    const REAL Tx = tx[3 * ns], Ty = tx[3 * ns + 1], Tz = tx[3 * ns + 2];
+                    const REAL dist = DIST(cx, cy, cz, Tx, Ty, Tz);
+                    if (dist < maxDist) {
+                        gx = Tx - cx; gy = Ty - cy; gz = Tz - cz;
+                        /* the construction of pass 0 once more, towards Tx */
+                        ptrdiff_t i2 = (ptrdiff_t)(small2 + (cx - xmin) / dx);
+                        ptrdiff_t j2 = (ptrdiff_t)(small2 + (cy - ymin) / dx);
+                        ptrdiff_t k2i = (ptrdiff_t)(small2 + (cz - zmin) / dx);
+                        REAL xq = xmin + dx * (i2 + (FN(sgn_)(gx) > 0.0 ? 1.0 : 0.0));
+                        REAL yq = ymin + dx * (j2 + (FN(sgn_)(gy) > 0.0 ? 1.0 : 0.0));
+                        REAL zq = zmin + dx * (k2i + (FN(sgn_)(gz) > 0.0 ? 1.0 : 0.0));
+                        if (FABS(xq - cx) < small2) xq += dx * FN(sgn_)(gx);
+                        if (FABS(yq - cy) < small2) yq += dx * FN(sgn_)(gy);
+                        if (FABS(zq - cz) < small2) zq += dx * FN(sgn_)(gz);
+                        const REAL bx = gx != 0.0 ? (xq - cx) / gx : REAL_MAX;
+                        const REAL by = gy != 0.0 ? (yq - cy) / gy : REAL_MAX;
+                        const REAL bz = gz != 0.0 ? (zq - cz) / gz : REAL_MAX;
+                        if (bx < by && bx < bz) {
+                            cx += bx * gx; cy += bx * gy; cz += bx * gz; cx = xq;
+                        } else if (by < bz) {
+                            cx += by * gx; cy += by * gy; cz += by * gz; cy = yq;
+                        } else {
+                            cx += bz * gx; cy += bz * gy; cz += bz * gz; cz = zq;
+                        }
+                        if (DIST(cx, cy, cz, px, py, pz) > dist || (cx == Tx && cy == Ty && cz == Tz)) {
+                            s2 = SLAT(Tx, Ty, Tz);
+                            ttr += t0[ns] + 0.5 * (s1 + s2) * DIST(px, py, pz, Tx, Ty, Tz);
+                        } else {
+                            s2 = SLAT(cx, cy, cz);
+                            ttr += 0.5 * (s1 + s2) * DIST(px, py, pz, cx, cy, cz);
+                            s1 = s2;
+                            s2 = SLAT(Tx, Ty, Tz);
+                            ttr += t0[ns] + 0.5 * (s1 + s2) * DIST(cx, cy, cz, Tx, Ty, Tz);
+                        }
+                        reached = 1;
+                    }
+                }
+            }
+        }
+        out[r] = ttr;
+    }
+#undef TTAT
+#undef SLAT
+#undef DIST
+    return 0;
+}
+
 #undef NIDX
 #undef FN
 #undef CAT

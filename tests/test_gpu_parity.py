@@ -172,7 +172,7 @@ def test_errors_match_reference_behaviour():
         g.raytrace(np.array([[9.5, 0, 0]]), np.array([[1.0, 1, 1]]))
     with pytest.raises(ValueError, match="Thread number"):
         g.get_grid_traveltimes(3)
-    g2 = Grid3d(x, x, x, cell_slowness=0, tt_from_rp=True)
+    g2 = Grid3d(x, x, x, cell_slowness=0, tt_from_rp=True, interp_vel=1)
     g2.set_slowness(np.ones((9, 9, 9)))
     with pytest.raises(NotImplementedError):
         g2.raytrace(np.array([[1.0, 1, 1]]), np.array([[2.0, 2, 2]]))
@@ -191,3 +191,36 @@ def test_builder_from_vtr(tmp_path):
     tt = grid.raytrace(g["src"], g["rcv"])
     assert np.array_equal(tt, g["tt_rcv"])
     assert np.array_equal(grid.get_grid_traveltimes(), g["tt_grid"])
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("weno", [0, 1])
+def test_tt_from_raypath_vs_oracle(oracle, dtype, weno):
+    """tt_from_rp=1 (the reference's default): Grid3Drn::getTraveltimeFromRaypath on the device is bit-identical to the
+    oracle restatement (itself bit-identical to the reference in double and float, tests/test_oracle.py), for one and
+    for two source points, receivers inside cells, on faces, edges and nodes."""
+    from ttcr_b200 import Grid3d
+    n = 33
+    x = np.linspace(0.0, 20.0, n)
+    X, Y, Z = np.meshgrid(x, x, x, indexing="ij")
+    s = ((1 + 0.3 * np.sin(0.7 * X) * np.cos(0.9 * Y)) / (1 + 0.1 * Z)).astype(dtype)
+    xt = x.astype(dtype)
+    dx = float(xt[1] - xt[0])
+    rng = np.random.default_rng(1)
+    for src, t0 in ((np.array([[3.3, 7.1, 12.9]]), np.array([0.0])),
+                    (np.array([[x[4], x[9], x[20]], [15.2, 3.3, 8.8]]), np.array([0.1, 0.3]))):
+        rcv = np.vstack([rng.uniform(1.5, 18.5, (60, 3)), [[x[5], x[7], 3.3], [x[5], 2.2, x[9]], [1.1, x[3], x[4]],
+                                                           [x[10], x[11], x[12]], src[0], [x[2], 5.5, 7.7]]])
+        g = Grid3d(x, x, x, cell_slowness=0, tt_from_rp=True, weno=weno, dtype=dtype)
+        tt = g.raytrace(np.column_stack([t0, src]), rcv, s, aggregate_src=True)
+        field, ni, nw = oracle.solve(n - 1, n - 1, n - 1, dx, oracle.to_cxx(s), src.astype(dtype), t0, weno=bool(weno), dtype=dtype)
+        if dtype == np.float64:
+            ref = oracle.tt_from_rp(n - 1, n - 1, n - 1, dx, field, oracle.to_cxx(s), src, t0, rcv, dtype=dtype)
+            assert np.array_equal(tt, ref)
+        else:
+            # fp32 fields differ in the last bits between the GPU and the CPU sweeps, so walk the GPU's own field
+            gf = oracle.to_cxx(g.get_grid_traveltimes())
+            ref = oracle.tt_from_rp(n - 1, n - 1, n - 1, dx, gf, oracle.to_cxx(s), src, t0, rcv, dtype=dtype)
+            assert np.array_equal(tt, ref)
+            ref2 = oracle.tt_from_rp(n - 1, n - 1, n - 1, dx, field, oracle.to_cxx(s), src, t0, rcv, dtype=dtype)
+            assert np.max(np.abs(tt - ref2) / np.maximum(ref2, dx * s.min())) < (2e-3 if weno else 1e-4)

@@ -93,3 +93,29 @@ def test_oracle_errors(oracle):
         oracle.solve(2, 2, 2, 1.0, np.ones(26), [[0.0, 0, 0]])
     with pytest.raises(ValueError):
         oracle.cell_to_node(np.ones(7), 2, 2, 2)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("weno", [False, True])
+def test_tt_from_raypath_restatement_is_bit_identical_to_reference(oracle, dtype, weno):
+    """Grid3Drn::getTraveltimeFromRaypath (+ grad, computeSlowness): the restatement walks the reference's own field and
+    must return the reference's own receiver times, bit for bit, in double and in float"""
+    O = oracle
+    if not O.have_ref():
+        pytest.skip("needs oracle/_ref (built from /root/reference); the golden raypath times cover the GPU box")
+    n = 33
+    x = np.linspace(0.0, 20.0, n)
+    X, Y, Z = np.meshgrid(x, x, x, indexing="ij")
+    s = ((1 + 0.3 * np.sin(0.7 * X) * np.cos(0.9 * Y)) / (1 + 0.1 * Z)).astype(dtype)
+    xt = x.astype(dtype)
+    dx = float(xt[1] - xt[0])
+    rng = np.random.default_rng(1)
+    for src, t0 in ((np.array([[3.3, 7.1, 12.9]]), 0.0), (np.array([[x[4], x[9], x[20]], [15.2, 3.3, 8.8]]), np.array([0.1, 0.3]))):
+        rcv = np.vstack([rng.uniform(1.5, 18.5, (60, 3)), [[x[5], x[7], 3.3], [x[5], 2.2, x[9]], [1.1, x[3], x[4]],
+                                                           [x[10], x[11], x[12]], src[0], [x[2], 5.5, 7.7]]])
+        g = O.RefGrid(n - 1, n - 1, n - 1, dx, weno=weno, dtype=dtype, tt_from_rp=True)
+        g.set_slowness(O.to_cxx(s))
+        tref, _ = g.raytrace(src, t0, rcv)
+        t = O.tt_from_rp(n - 1, n - 1, n - 1, dx, g.get_tt(), O.to_cxx(s), src, t0, rcv, dtype=dtype)
+        g.close()
+        assert np.array_equal(t.astype(np.float64), tref)

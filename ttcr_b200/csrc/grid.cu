@@ -22,6 +22,7 @@
 #include "kernels.cuh"
 #include "sweep_tile.cuh"
 #include "sweep_tile3.cuh"
+#include "raypath.cuh"
 #include "sweep_tile5.cuh"
 
 namespace ttcrb200 {
@@ -71,8 +72,8 @@ template <typename T>
 class Grid final : public GridBase {
    public:
     Grid(uint32_t ncx, uint32_t ncy, uint32_t ncz, double dx, double xmin, double ymin, double zmin, double eps,
-         int maxit, bool weno, bool ttrp, bool /*interp_vel*/, size_t nslots, bool translate, bool cell, int device)
-        : maxit_(maxit), weno_(weno), ttrp_(ttrp), cell_(cell), translate_(translate) {
+         int maxit, bool weno, bool ttrp, bool interp_vel, size_t nslots, bool translate, bool cell, int device)
+        : maxit_(maxit), weno_(weno), ttrp_(ttrp), cell_(cell), translate_(translate), intvel_(interp_vel) {
         if (ncx < 1 || ncy < 1 || ncz < 1) throw Err(TTCR_B200_ERR_INVALID, "grid must have at least one cell per axis");
         if (nslots < 1) throw Err(TTCR_B200_ERR_INVALID, "n_slots must be >= 1");
         if ((double)(ncx + 1) * (ncy + 1) * (ncz + 1) > 4294967295.0)
@@ -221,21 +222,43 @@ class Grid final : public GridBase {
         vrx.assign((const T*)rx, (const T*)rx + 3 * nrx);
         translate_pts(vrx);
         check_pts(vrx);
-        if (nrx && ttrp_)
+        if (nrx && ttrp_ && intvel_)
             throw Err(TTCR_B200_ERR_UNSUPPORTED,
-                      "tt_from_rp=1 (traveltimes integrated along raypaths, Grid3Drn.h:1103-1243) is not part of the "
-                      "B200 FSM path yet; construct the grid with tt_from_rp=0");
+                      "tt_from_rp=1 with interp_vel=1 (slowness along the raypath from interpolated velocity, Grid3Drn.h:2489-2669) "
+                      "is not part of the B200 path; use interp_vel=0");
+        ensure_pts(s, 4 * ntx + 5 * nrx);   // Tx, t0 | Rx, traveltimes, status (before the solve: it uploads Tx into this buffer)
         solve_device(s, vtx, vt0);
         if (nrx) {
-            ensure_pts(s, 4 * nrx);
-            std::memcpy(s.h_pts, vrx.data(), 3 * nrx * sizeof(T));
-            CK(cudaMemcpyAsync(s.d_pts, s.h_pts, 3 * nrx * sizeof(T), cudaMemcpyHostToDevice, s.stream));
-            T* d_out = s.d_pts + 3 * nrx;
-            k_interp<T><<<(unsigned)((nrx + 127) / 128), 128, 0, s.stream>>>(g_, d_, s.tt[0], s.d_pts, (int)nrx, d_out);
+            T* const h_rx = s.h_pts + 4 * ntx;
+            T* const d_rx = s.d_pts + 4 * ntx;
+            std::memcpy(h_rx, vrx.data(), 3 * nrx * sizeof(T));
+            CK(cudaMemcpyAsync(d_rx, h_rx, 3 * nrx * sizeof(T), cudaMemcpyHostToDevice, s.stream));
+            T* d_out = d_rx + 3 * nrx;
+            if (ttrp_) {
+                // Grid3D.h:493-501 with tt_from_rp: traveltimes integrated along the raypaths (raypath.cuh)
+                k_tt_from_rp<T><<<(unsigned)((nrx + 63) / 64), 64, 0, s.stream>>>(g_, d_, s.tt[0], slo_[0], s.d_pts, s.d_pts + 3 * ntx, (int)ntx,
+                                                                                 d_rx, (int)nrx, d_out, d_out + nrx);
+            } else {
+                k_interp<T><<<(unsigned)((nrx + 127) / 128), 128, 0, s.stream>>>(g_, d_, s.tt[0], d_rx, (int)nrx, d_out);
+            }
             CK(cudaGetLastError());
-            CK(cudaMemcpyAsync(s.h_pts + 3 * nrx, d_out, nrx * sizeof(T), cudaMemcpyDeviceToHost, s.stream));
+            CK(cudaMemcpyAsync(h_rx + 3 * nrx, d_out, (ttrp_ ? 2 : 1) * nrx * sizeof(T), cudaMemcpyDeviceToHost, s.stream));
             CK(cudaStreamSynchronize(s.stream));
-            std::memcpy(tt, s.h_pts + 3 * nrx, nrx * sizeof(T));
+            std::memcpy(tt, h_rx + 3 * nrx, nrx * sizeof(T));
+            if (ttrp_) {
+                const T* st = h_rx + 4 * nrx;
+                for (size_t n = 0; n < nrx; ++n) {
+                    if (st[n] == T(0)) continue;
+                    std::ostringstream msg;
+                    if (st[n] == T(1))
+                        msg << "Error while computing raypaths: going outside grid \n                Rx: " << vrx[3 * n] << " " << vrx[3 * n + 1] << " "
+                            << vrx[3 * n + 2] << "\n                Tx: " << vtx[0] << " " << vtx[1] << " " << vtx[2] << "\n";
+                    else
+                        msg << "Error while computing raypaths: the ray from Rx " << vrx[3 * n] << " " << vrx[3 * n + 1] << " " << vrx[3 * n + 2]
+                            << " did not reach a source point";
+                    throw Err(TTCR_B200_ERR_RUNTIME, msg.str());
+                }
+            }
         }
     }
 
@@ -546,7 +569,7 @@ class Grid final : public GridBase {
     T origin_[3];
     T epsilon_;
     int maxit_;
-    bool weno_, ttrp_, cell_, translate_;
+    bool weno_, ttrp_, cell_, translate_, intvel_;
     bool have_slowness_ = false;
     int dev_ = 0, sm_count_ = 148;
     int kernel_ = TTCR_B200_KERNEL_AUTO;

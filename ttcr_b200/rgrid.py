@@ -16,8 +16,10 @@ Differences, all deliberate:
   the per-element loops of rgrid.pyx:559-566 / :428-435 are gone.
 * ``n_threads`` is the number of solver *slots* (one traveltime field + one CUDA stream each;
   the reference's one-source-per-thread fan-out, ttcr/Grid3D.h:810-853).
-* ``compute_L`` / ``compute_M`` / ``return_rays`` and ``tt_from_rp=True`` raise
-  ``NotImplementedError``: they belong to the post-solve stages.
+* ``tt_from_rp=True`` (the reference's default: receiver traveltimes integrated along the raypaths,
+  ttcr/Grid3Drn.h:1103-1243) runs on the device, one thread per receiver, bit-identical to the reference.
+* ``compute_L`` / ``compute_M`` / ``return_rays`` raise ``NotImplementedError``: they belong to the
+  post-solve stages.
 """
 from __future__ import annotations
 
