@@ -68,6 +68,26 @@ public:
         check(ttcr_b200_raytrace(h, tx.data(), t0.data(), Tx.size(), rx.data(), Rx.size(), traveltimes.data(), threadNo));
     }
 
+    // Grid3D::raytrace(Tx, t0, Rx, traveltimes, r_data, threadNo) (Grid3D.h:127-132, :545-586): traveltimes and raypaths
+    void raytrace(const std::vector<sxyz<T1>>& Tx, const std::vector<T1>& t0, const std::vector<sxyz<T1>>& Rx,
+                  std::vector<T1>& traveltimes, std::vector<std::vector<sxyz<T1>>>& r_data, const size_t threadNo = 0) const override {
+        std::vector<T1> tx = flatten(Tx), rx = flatten(Rx);
+        traveltimes.resize(Rx.size());
+        std::vector<size_t> npts(Rx.size(), 0);
+        check(ttcr_b200_raytrace_rays(h, tx.data(), t0.data(), Tx.size(), rx.data(), Rx.size(), traveltimes.data(), npts.data(),
+                                      threadNo));
+        size_t total = 0;
+        for (size_t n : npts) total += n;
+        std::vector<T1> xyz(3 * total);
+        check(ttcr_b200_get_rays(h, threadNo, xyz.data()));
+        r_data.resize(Rx.size());
+        size_t o = 0;
+        for (size_t n = 0; n < Rx.size(); ++n) {
+            r_data[n].resize(npts[n]);
+            for (size_t k = 0; k < npts[n]; ++k, o += 3) r_data[n][k] = sxyz<T1>(xyz[o], xyz[o + 1], xyz[o + 2]);
+        }
+    }
+
     // Grid3D::raytrace(vector<vector<sxyz>>&, ...) (Grid3D.h:172-175, :810-853) is NOT virtual: called
     // through a Grid3D*, the reference's own fan-out (ctpl pool / std::thread blocks) runs and calls the
     // single-source override above concurrently with distinct threadNo, which the library supports (one

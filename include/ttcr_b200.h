@@ -104,10 +104,20 @@ int ttcr_b200_get_slowness(ttcr_b200_grid* g, void* out, int order);
 /* Replaces: Grid3D::raytrace(Tx,t0,Rx,traveltimes,threadNo) (Grid3D.h:115-119, :470-502) ->
  * Grid3Drnfs::raytrace (Grid3Drnfs.h:84-155).  tx_xyz: ntx x 3, rx_xyz: nrx x 3 (row major),
  * t0: ntx, tt_out: nrx (may be NULL when nrx == 0).  All Tx points belong to ONE source.
- * Receiver traveltimes are Grid3Drn::getTraveltime (trilinear, Grid3Drn.h:794-930).
+ * Receiver traveltimes are Grid3Drn::getTraveltime (trilinear, Grid3Drn.h:794-930) when the grid was created
+ * with tt_from_rp = 0, else Grid3Drn::getTraveltimeFromRaypath (Grid3Drn.h:1103-1243), as Grid3D.h:493-501.
  * TTCR_B200_ERR_RUNTIME if a point is outside the grid (checkPts, Grid3Drn.h:771-790). */
 int ttcr_b200_raytrace(ttcr_b200_grid* g, const void* tx_xyz, const void* t0, size_t ntx,
                        const void* rx_xyz, size_t nrx, void* tt_out, size_t slot);
+
+/* Replaces: Grid3D::raytrace(Tx,t0,Rx,traveltimes,r_data,threadNo) (Grid3D.h:545-586) -> Grid3Drnfs::raytrace, then
+ * Grid3Drn::getRaypath per receiver (Grid3Drn.h:1339-1500): traveltimes integrated along the raypaths AND the raypaths.
+ * ray_npts (nrx values): number of points of every ray (first = the receiver, last = the source point reached).  The
+ * points themselves stay on the slot; fetch them with ttcr_b200_get_rays into a buffer of 3 * sum(ray_npts) elements
+ * (std::vector<std::vector<sxyz<T>>> flattened: ray after ray, x y z per point). */
+int ttcr_b200_raytrace_rays(ttcr_b200_grid* g, const void* tx_xyz, const void* t0, size_t ntx, const void* rx_xyz,
+                            size_t nrx, void* tt_out, size_t* ray_npts, size_t slot);
+int ttcr_b200_get_rays(ttcr_b200_grid* g, size_t slot, void* xyz_out);
 
 /* Replaces: Grid3D::raytrace(vector<vector<sxyz>>&Tx, vector<vector<T>>&t0, vector<vector<sxyz>>&Rx,
  * vector<vector<T>>&tt) (Grid3D.h:172-175, :810-853).  Source s owns Tx points
@@ -129,7 +139,8 @@ int ttcr_b200_get_niter(ttcr_b200_grid* g, size_t slot, int* niter, int* niterw)
 
 /* Replaces: Grid3D::setTraveltimeFromRaypath / setUsePool (Grid3D.h:287,302-309) and tuning knobs.
  * keys: "tt_from_rp" (0/1), "kernel" (TTCR_B200_KERNEL_*), "tile_rows" (flag chunk, rows),
- *       "ctas_per_sm", "use_pool" (accepted, ignored). */
+ *       "ctas_per_sm", "plane_graph" / "plane_pdl" (0/1: replay the plane-per-launch sweeps of the WENO stage from a
+ *       captured CUDA graph / chain them by programmatic dependent launch), "use_pool" (accepted, ignored). */
 int ttcr_b200_set_option(ttcr_b200_grid* g, const char* key, double value);
 
 /* Replaces: Grid3D::getNthreads (Grid3D.h:309). */

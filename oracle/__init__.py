@@ -71,6 +71,9 @@ def _load_ref():
         lib.ttcr_ref_raytrace.argtypes = [C.c_void_p, dp, dp, C.c_size_t, dp, C.c_size_t, dp, C.c_size_t, dp]
         lib.ttcr_ref_raytrace_multi.argtypes = [C.c_void_p, C.c_size_t, dp, dp, dp, C.c_size_t, dp, dp]
         lib.ttcr_ref_get_tt.argtypes = [C.c_void_p, dp, C.c_size_t]
+        if hasattr(lib, "ttcr_ref_raytrace_rays"):
+            lib.ttcr_ref_raytrace_rays.argtypes = [C.c_void_p, dp, dp, C.c_size_t, dp, C.c_size_t, dp, C.c_size_t, C.c_void_p, dp,
+                                                   C.c_size_t]
         lib.ttcr_ref_get_niter.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
         _ref = lib
     return _ref
@@ -136,6 +139,19 @@ class RefGrid:
         self._chk(self._lib.ttcr_ref_raytrace(self._h, _dp(tx), _dp(t0), tx.shape[0], _dp(rx), rx.shape[0],
                                               _dp(tt), thread_no, C.byref(sec)))
         return tt, sec.value
+
+    def raytrace_rays(self, tx, t0, rx, thread_no=0, cap=4096):
+        """Grid3D::raytrace(..., r_data, threadNo): returns (tt at rx, list of (npts, 3) arrays)"""
+        tx = np.ascontiguousarray(tx, dtype=np.float64).reshape(-1, 3)
+        t0 = np.ascontiguousarray(np.broadcast_to(np.asarray(t0, dtype=np.float64), (tx.shape[0],)))
+        rx = np.ascontiguousarray(rx, dtype=np.float64).reshape(-1, 3)
+        tt = np.empty(rx.shape[0])
+        npts = np.zeros(rx.shape[0], dtype=np.uintp)
+        xyz = np.zeros((rx.shape[0], cap, 3))
+        self._chk(self._lib.ttcr_ref_raytrace_rays(self._h, _dp(tx), _dp(t0), tx.shape[0], _dp(rx), rx.shape[0], _dp(tt),
+                                                   thread_no, npts.ctypes.data, _dp(xyz), cap))
+        assert npts.max(initial=0) <= cap
+        return tt, [xyz[i, :int(n)].copy() for i, n in enumerate(npts)]
 
     def raytrace_multi(self, tx, t0, rx):
         """one Tx point per source; same receivers for all; the reference's own thread fan-out."""
@@ -245,3 +261,29 @@ def tt_from_rp(ncx, ncy, ncz, dx, tt_flat, s_node_flat, tx, t0, rx, xmin=0.0, ym
     if rc:
         raise RuntimeError("raypath did not reach a source")
     return out
+
+
+def raypaths(ncx, ncy, ncz, dx, tt_flat, s_node_flat, tx, t0, rx, xmin=0.0, ymin=0.0, zmin=0.0, dtype=np.float64, cap=4096):
+    """Grid3Drn::getRaypath (Grid3Drn.h:1339-1500) from a solved field: (traveltimes, list of (npts, 3) float64 arrays)."""
+    sfx, ct = _sfx(dtype)
+    lib = _load()
+    tt = np.ascontiguousarray(tt_flat, dtype=dtype).ravel()
+    sl = np.ascontiguousarray(s_node_flat, dtype=dtype).ravel()
+    tx = np.ascontiguousarray(np.asarray(tx, dtype=dtype).reshape(-1, 3))
+    t0 = np.ascontiguousarray(np.broadcast_to(np.asarray(t0, dtype=dtype), (tx.shape[0],)))
+    rx = np.ascontiguousarray(np.asarray(rx, dtype=dtype).reshape(-1, 3))
+    out = np.empty(rx.shape[0], dtype=dtype)
+    npts = np.zeros(rx.shape[0], dtype=np.uintp)
+    xyz = np.zeros((rx.shape[0], cap, 3), dtype=dtype)
+    f = getattr(lib, "fsmo_raypaths" + sfx)
+    f.restype = C.c_int
+    f.argtypes = [C.c_size_t] * 3 + [ct] * 4 + [C.c_void_p] * 4 + [C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p,
+                                                                  C.c_void_p, C.c_size_t]
+    rc = f(ncx, ncy, ncz, dx, xmin, ymin, zmin, tt.ctypes.data, sl.ctypes.data, tx.ctypes.data, t0.ctypes.data, tx.shape[0],
+           rx.ctypes.data, rx.shape[0], out.ctypes.data, xyz.ctypes.data, npts.ctypes.data, cap)
+    if rc == 1:
+        raise RuntimeError("Error while computing raypaths: going outside grid")
+    if rc:
+        raise RuntimeError("raypath did not reach a source")
+    assert npts.max(initial=0) <= cap
+    return out, [xyz[i, :int(n)].astype(np.float64) for i, n in enumerate(npts)]

@@ -488,8 +488,11 @@ static void FN(stencil_)(REAL p, REAL off, REAL d, REAL lo, REAL hi, REAL q[4]) 
 static int FN(sgn_)(REAL v) { return v > 0 ? 1 : (v < 0 ? -1 : 0); }   /* boost::math::sign */
 
 /* returns 0, or 1 when a ray leaves the grid (the reference throws), 2 when it does not reach a source */
-int FN(fsmo_tt_from_rp)(size_t ncx, size_t ncy, size_t ncz, REAL dx, REAL xmin, REAL ymin, REAL zmin, const REAL *tt,
-                        const REAL *sl, const REAL *tx, const REAL *t0, size_t ntx, const REAL *rx, size_t nrx, REAL *out) {
+/* rays == NULL: traveltimes only.  Otherwise Grid3Drn::getRaypath (Grid3Drn.h:1339-1500, the same walk with
+ * r_data.push_back): ray r gets npts[r] points, the first `cap` of which are stored at rays + 3 * cap * r. */
+int FN(fsmo_raypaths)(size_t ncx, size_t ncy, size_t ncz, REAL dx, REAL xmin, REAL ymin, REAL zmin, const REAL *tt,
+                      const REAL *sl, const REAL *tx, const REAL *t0, size_t ntx, const REAL *rx, size_t nrx, REAL *out,
+                      REAL *rays, size_t *npts, size_t cap) {
     const double small2 = 1.e-8;
     const REAL xmax = xmin + ncx * dx, ymax = ymin + ncy * dx, zmax = zmin + ncz * dx;   /* Grid3Drn ctor, :63-65 */
     const REAL k1 = 1. / 24., k2 = 9. / 8.;
@@ -501,9 +504,12 @@ int FN(fsmo_tt_from_rp)(size_t ncx, size_t ncy, size_t ncz, REAL dx, REAL xmin, 
         const REAL Rx = rx[3 * r], Ry = rx[3 * r + 1], Rz = rx[3 * r + 2];
         REAL ttr = 0.0;
         int done = 0;
+        size_t np_ = 0;
+#define PUSH(a, b, c) do { if (rays && np_ < cap) { REAL *q_ = rays + 3 * (cap * r + np_); q_[0] = (a); q_[1] = (b); q_[2] = (c); } ++np_; } while (0)
+        PUSH(Rx, Ry, Rz);
         for (size_t ns = 0; ns < ntx; ++ns)
             if (Rx == tx[3 * ns] && Ry == tx[3 * ns + 1] && Rz == tx[3 * ns + 2]) { ttr = t0[ns]; done = 1; break; }
-        if (done) { out[r] = ttr; continue; }
+        if (done) { out[r] = ttr; if (npts) npts[r] = np_; continue; }
         REAL px = Rx, py = Ry, pz = Rz;   /* prev_pt */
         REAL cx = Rx, cy = Ry, cz = Rz;   /* curr_pt */
         REAL s1 = SLAT(cx, cy, cz), s2;
@@ -546,6 +552,7 @@ int FN(fsmo_tt_from_rp)(size_t ncx, size_t ncy, size_t ncz, REAL dx, REAL xmin, 
                 ttr += 0.5 * (s1 + s2) * DIST(px, py, pz, cx, cy, cz);
                 s1 = s2;
                 px = cx; py = cy; pz = cz;
+                PUSH(cx, cy, cz);
                 /* are we close enough to one of the Tx points?  (the reference does not leave this loop early) */
                 for (size_t ns = 0; ns < ntx; ++ns) {
                     const REAL Tx = tx[3 * ns], Ty = tx[3 * ns + 1], Tz = tx[3 * ns + 2];
@@ -575,12 +582,15 @@ int FN(fsmo_tt_from_rp)(size_t ncx, size_t ncy, size_t ncz, REAL dx, REAL xmin, 
                         if (DIST(cx, cy, cz, px, py, pz) > dist || (cx == Tx && cy == Ty && cz == Tz)) {
                             s2 = SLAT(Tx, Ty, Tz);
                             ttr += t0[ns] + 0.5 * (s1 + s2) * DIST(px, py, pz, Tx, Ty, Tz);
+                            PUSH(Tx, Ty, Tz);
                         } else {
                             s2 = SLAT(cx, cy, cz);
                             ttr += 0.5 * (s1 + s2) * DIST(px, py, pz, cx, cy, cz);
+                            PUSH(cx, cy, cz);
                             s1 = s2;
                             s2 = SLAT(Tx, Ty, Tz);
                             ttr += t0[ns] + 0.5 * (s1 + s2) * DIST(cx, cy, cz, Tx, Ty, Tz);
+                            PUSH(Tx, Ty, Tz);
                         }
                         reached = 1;
                     }
@@ -588,11 +598,18 @@ int FN(fsmo_tt_from_rp)(size_t ncx, size_t ncy, size_t ncz, REAL dx, REAL xmin, 
             }
         }
         out[r] = ttr;
+        if (npts) npts[r] = np_;
+#undef PUSH
     }
 #undef TTAT
 #undef SLAT
 #undef DIST
     return 0;
+}
+
+int FN(fsmo_tt_from_rp)(size_t ncx, size_t ncy, size_t ncz, REAL dx, REAL xmin, REAL ymin, REAL zmin, const REAL *tt,
+                        const REAL *sl, const REAL *tx, const REAL *t0, size_t ntx, const REAL *rx, size_t nrx, REAL *out) {
+    return FN(fsmo_raypaths)(ncx, ncy, ncz, dx, xmin, ymin, zmin, tt, sl, tx, t0, ntx, rx, nrx, out, NULL, NULL, 0);
 }
 
 #undef NIDX

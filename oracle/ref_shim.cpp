@@ -40,6 +40,8 @@ struct Base {
                           const double* rx, size_t nrx, double* tt, size_t th) = 0;
     virtual void raytrace_multi(size_t nsrc, const double* tx, const double* t0,
                                 const double* rx, size_t nrx, double* tt) = 0;
+    virtual void raytrace_rays(const double* tx, const double* t0, size_t ntx, const double* rx, size_t nrx, double* tt,
+                               size_t th, size_t* npts, double* xyz, size_t cap) = 0;
     virtual void get_tt(double* out, size_t th) = 0;
     virtual void niter(int* a, int* b) = 0;
     virtual size_t nnodes() = 0;
@@ -76,6 +78,27 @@ struct Impl : Base {
         for (size_t i = 0; i < ntx; ++i) vt0[i] = T(t0[i]);
         base().raytrace(Tx, vt0, Rx, vtt, th);
         for (size_t i = 0; i < nrx; ++i) tt[i] = double(vtt[i]);
+    }
+    // Grid3D::raytrace(Tx,t0,Rx,traveltimes,r_data,threadNo) (Grid3D.h:545-586): ray n gets npts[n] points, the first
+    // `cap` of them stored at xyz + 3 * cap * n
+    void raytrace_rays(const double* tx, const double* t0, size_t ntx, const double* rx, size_t nrx, double* tt, size_t th,
+                       size_t* npts, double* xyz, size_t cap) override {
+        std::vector<ttcr::sxyz<T>> Tx, Rx;
+        pts(tx, ntx, Tx);
+        pts(rx, nrx, Rx);
+        std::vector<T> vt0(ntx), vtt(nrx);
+        for (size_t i = 0; i < ntx; ++i) vt0[i] = T(t0[i]);
+        std::vector<std::vector<ttcr::sxyz<T>>> r_data;
+        base().raytrace(Tx, vt0, Rx, vtt, r_data, th);
+        for (size_t i = 0; i < nrx; ++i) {
+            tt[i] = double(vtt[i]);
+            npts[i] = r_data[i].size();
+            for (size_t k = 0; k < r_data[i].size() && k < cap; ++k) {
+                xyz[3 * (cap * i + k)] = double(r_data[i][k].x);
+                xyz[3 * (cap * i + k) + 1] = double(r_data[i][k].y);
+                xyz[3 * (cap * i + k) + 2] = double(r_data[i][k].z);
+            }
+        }
     }
     // one Tx point per source, same receivers for every source; fan-out is the
     // reference's own (ttcr/Grid3D.h:810-853: thread pool / std::thread blocks)
@@ -163,6 +186,10 @@ int ttcr_ref_raytrace(void* h, const double* tx, const double* t0, size_t ntx, c
     int rc = guard([&] { static_cast<Base*>(h)->raytrace(tx, t0, ntx, rx, nrx, tt, thread_no); });
     if (seconds) *seconds = std::chrono::duration<double>(std::chrono::high_resolution_clock::now() - t_0).count();
     return rc;
+}
+int ttcr_ref_raytrace_rays(void* h, const double* tx, const double* t0, size_t ntx, const double* rx, size_t nrx, double* tt,
+                           size_t thread_no, size_t* npts, double* xyz, size_t cap) {
+    return guard([&] { static_cast<Base*>(h)->raytrace_rays(tx, t0, ntx, rx, nrx, tt, thread_no, npts, xyz, cap); });
 }
 int ttcr_ref_raytrace_multi(void* h, size_t nsrc, const double* tx, const double* t0,
                             const double* rx, size_t nrx, double* tt, double* seconds) {

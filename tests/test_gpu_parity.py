@@ -224,3 +224,40 @@ def test_tt_from_raypath_vs_oracle(oracle, dtype, weno):
             assert np.array_equal(tt, ref)
             ref2 = oracle.tt_from_rp(n - 1, n - 1, n - 1, dx, field, oracle.to_cxx(s), src, t0, rcv, dtype=dtype)
             assert np.max(np.abs(tt - ref2) / np.maximum(ref2, dx * s.min())) < (2e-3 if weno else 1e-4)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_raypaths_vs_oracle(oracle, dtype):
+    """return_rays=True: the points of Grid3Drn::getRaypath, walked on the device over the device's own field, are
+    bit-identical to the oracle restatement's (itself bit-identical to the reference, tests/test_oracle.py); sources
+    with several Tx points, receivers on nodes / faces / the source, one source per receiver group, translated grids."""
+    from ttcr_b200 import Grid3d
+    n = 33
+    x = np.linspace(0.0, 20.0, n)
+    X, Y, Z = np.meshgrid(x, x, x, indexing="ij")
+    s = ((1 + 0.3 * np.sin(0.7 * X) * np.cos(0.9 * Y)) / (1 + 0.1 * Z)).astype(dtype)
+    dx = float(x.astype(dtype)[1] - x.astype(dtype)[0])
+    rng = np.random.default_rng(2)
+    for src, t0 in ((np.array([[3.3, 7.1, 12.9]]), np.array([0.0])),
+                    (np.array([[x[4], x[9], x[20]], [15.2, 3.3, 8.8]]), np.array([0.1, 0.3]))):
+        rcv = np.vstack([rng.uniform(1.5, 18.5, (40, 3)), [[x[5], x[7], 3.3], [x[10], x[11], x[12]], src[0]]])
+        for ttrp in (False, True):     # the rays overload does not look at tt_from_rp (Grid3D.h:545-586)
+            g = Grid3d(x, x, x, cell_slowness=0, tt_from_rp=ttrp, weno=1, dtype=dtype)
+            tt, rays = g.raytrace(np.column_stack([t0, src]), rcv, s, aggregate_src=True, return_rays=True)
+            gf = oracle.to_cxx(g.get_grid_traveltimes())
+            tref, rref = oracle.raypaths(n - 1, n - 1, n - 1, dx, gf, oracle.to_cxx(s), src, t0, rcv, dtype=dtype)
+            assert np.array_equal(tt, tref)
+            assert len(rays) == rcv.shape[0]
+            for a, b in zip(rays, rref):
+                assert a.dtype == np.float64 and a.shape == b.shape and np.array_equal(a, b)
+            assert np.array_equal(rays[0][0], rcv[0].astype(dtype).astype(np.float64))
+            assert rays[-1].shape == (1, 3)
+    # several sources (one per receiver): rays come back in the order of rcv
+    g = Grid3d(x, x, x, cell_slowness=0, weno=0, dtype=dtype)
+    src = np.array([[3.3, 7.1, 12.9], [15.2, 3.3, 8.8], [3.3, 7.1, 12.9]])
+    rcv = np.array([[10.0, 10.0, 10.0], [5.5, 6.5, 7.5], [12.2, 1.1, 4.4]])
+    tt, rays = g.raytrace(src, rcv, s, return_rays=True)
+    for i in range(3):
+        t1, r1 = g.raytrace(src[i:i + 1], rcv[i:i + 1], return_rays=True)
+        assert tt[i] == t1[0] and np.array_equal(rays[i], r1[0])
+        assert np.array_equal(rays[i][-1], src[i].astype(dtype).astype(np.float64))

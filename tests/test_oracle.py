@@ -119,3 +119,30 @@ def test_tt_from_raypath_restatement_is_bit_identical_to_reference(oracle, dtype
         t = O.tt_from_rp(n - 1, n - 1, n - 1, dx, g.get_tt(), O.to_cxx(s), src, t0, rcv, dtype=dtype)
         g.close()
         assert np.array_equal(t.astype(np.float64), tref)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_raypath_restatement_is_bit_identical_to_reference(oracle, dtype):
+    """Grid3Drn::getRaypath (the rays overload of Grid3D::raytrace): same points, same count, same traveltimes"""
+    O = oracle
+    if not O.have_ref():
+        pytest.skip("needs oracle/_ref (built from /root/reference)")
+    n = 33
+    x = np.linspace(0.0, 20.0, n)
+    X, Y, Z = np.meshgrid(x, x, x, indexing="ij")
+    s = ((1 + 0.3 * np.sin(0.7 * X) * np.cos(0.9 * Y)) / (1 + 0.1 * Z)).astype(dtype)
+    dx = float(x.astype(dtype)[1] - x.astype(dtype)[0])
+    rng = np.random.default_rng(2)
+    for src, t0 in ((np.array([[3.3, 7.1, 12.9]]), 0.0), (np.array([[x[4], x[9], x[20]], [15.2, 3.3, 8.8]]), np.array([0.1, 0.3]))):
+        rcv = np.vstack([rng.uniform(1.5, 18.5, (40, 3)), [[x[5], x[7], 3.3], [x[10], x[11], x[12]], src[0]]])
+        g = O.RefGrid(n - 1, n - 1, n - 1, dx, weno=True, dtype=dtype, tt_from_rp=False)
+        g.set_slowness(O.to_cxx(s))
+        tref, rref = g.raytrace_rays(src, t0, rcv)
+        t, r = O.raypaths(n - 1, n - 1, n - 1, dx, g.get_tt(), O.to_cxx(s), src, t0, rcv, dtype=dtype)
+        g.close()
+        assert np.array_equal(t.astype(np.float64), tref)
+        assert len(r) == len(rref)
+        for a, b in zip(r, rref):
+            assert a.shape == b.shape and np.array_equal(a, b)
+        assert r[-1].shape == (1, 3)      # a receiver on the source: the ray is that point alone
+        assert min(len(a) for a in r[:-1]) >= 2

@@ -22,7 +22,7 @@ SYMBOLS = (
     "ttcr_b200_create", "ttcr_b200_destroy", "ttcr_b200_last_error", "ttcr_b200_set_slowness",
     "ttcr_b200_set_slowness_device", "ttcr_b200_get_tt_device", "ttcr_b200_get_slowness", "ttcr_b200_raytrace", "ttcr_b200_raytrace_multi", "ttcr_b200_get_tt",
     "ttcr_b200_get_niter", "ttcr_b200_set_option", "ttcr_b200_n_slots", "ttcr_b200_solve",
-    "ttcr_b200_get_stats", "ttcr_b200_device_bytes", "ttcr_b200_version",
+    "ttcr_b200_get_stats", "ttcr_b200_device_bytes", "ttcr_b200_version", "ttcr_b200_raytrace_rays", "ttcr_b200_get_rays",
 )
 
 
@@ -65,6 +65,8 @@ def load() -> C.CDLL:
     lib.ttcr_b200_get_tt_device.argtypes = [vp, vp, sz, i32]
     lib.ttcr_b200_get_slowness.argtypes = [vp, vp, i32]
     lib.ttcr_b200_raytrace.argtypes = [vp, vp, vp, sz, vp, sz, vp, sz]
+    lib.ttcr_b200_raytrace_rays.argtypes = [vp, vp, vp, sz, vp, sz, vp, vp, sz]
+    lib.ttcr_b200_get_rays.argtypes = [vp, sz, vp]
     lib.ttcr_b200_raytrace_multi.argtypes = [vp, sz, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.ttcr_b200_get_tt.argtypes = [vp, vp, sz, i32]
     lib.ttcr_b200_get_niter.argtypes = [vp, sz, C.POINTER(i32), C.POINTER(i32)]

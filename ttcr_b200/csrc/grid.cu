@@ -61,6 +61,9 @@ struct GridBase {
                           size_t slot) = 0;
     virtual void raytrace_multi(size_t nsrc, const size_t* tx_off, const void* tx, const void* t0,
                                 const size_t* rx_off, const void* rx, void* tt, int* niter, int* niterw) = 0;
+    virtual void raytrace_rays(const void* tx, const void* t0, size_t ntx, const void* rx, size_t nrx, void* tt, size_t* npts,
+                               size_t slot) = 0;
+    virtual void get_rays(size_t slot, void* xyz) = 0;
     virtual void get_tt(void* out, size_t slot, int order) = 0;
     virtual void stats(size_t slot, ttcr_b200_stats* out) = 0;
     virtual void set_option(const std::string& key, double v) = 0;
@@ -118,6 +121,7 @@ class Grid final : public GridBase {
                 CK(cudaMemsetAsync(s.mask[l], 0, ne / 8, s.stream));
             }
             CK(cudaMalloc(&s.d_change, sizeof(double)));
+            CK(cudaMalloc(&s.d_fb, sizeof(FrozenBox)));
             CK(cudaMallocHost(&s.h_change, sizeof(double)));
             tile_alloc(s.tile, d_, bytes_);
             CK(cudaStreamSynchronize(s.stream));
@@ -134,6 +138,10 @@ class Grid final : public GridBase {
             for (int l = 0; l < 2; ++l) { free_field(s.tt[l]); cudaFree(s.mask[l]); }
             for (auto e : s.sweep_ev) cudaEventDestroy(e);
             cudaFree(s.d_change); cudaFreeHost(s.h_change);
+            cudaFree(s.d_fb);
+            for (auto& a : s.pgraph)
+                for (auto& b : a)
+                    if (b.exec) cudaGraphExecDestroy(b.exec);
             cudaFree(s.d_pts); cudaFreeHost(s.h_pts);
             tile_free(s.tile);
             tile5_free(s.tile5);
@@ -214,41 +222,70 @@ class Grid final : public GridBase {
     }
 
     void raytrace(const void* tx, const void* t0, size_t ntx, const void* rx, size_t nrx, void* tt, size_t slot) override {
+        raytrace_impl(tx, t0, ntx, rx, nrx, tt, slot, nullptr);
+    }
+
+    // Grid3D::raytrace(Tx,t0,Rx,traveltimes,r_data,threadNo) (Grid3D.h:545-586): traveltimes AND raypaths, both from
+    // Grid3Drn::getRaypath (Grid3Drn.h:1339-1500), whatever tt_from_rp says.  The points stay on the slot until get_rays.
+    void raytrace_rays(const void* tx, const void* t0, size_t ntx, const void* rx, size_t nrx, void* tt, size_t* npts,
+                       size_t slot) override {
+        raytrace_impl(tx, t0, ntx, rx, nrx, tt, slot, npts);
+    }
+
+    void get_rays(size_t slot, void* xyz) override {
+        Slot& s = slot_at(slot);
+        if (!s.rays.empty()) std::memcpy(xyz, s.rays.data(), s.rays.size() * sizeof(T));
+    }
+
+    void raytrace_impl(const void* tx, const void* t0, size_t ntx, const void* rx, size_t nrx, void* tt, size_t slot, size_t* npts) {
         CK(cudaSetDevice(dev_));
         Slot& s = slot_at(slot);
+        const bool want_rays = npts != nullptr;
+        const bool walk = ttrp_ || want_rays;
         std::vector<T> vtx, vt0, vrx;
         prepare_tx(tx, t0, ntx, vtx, vt0);
         // checkPts(Rx) before any work, as Grid3Drnfs.h:89-90
         vrx.assign((const T*)rx, (const T*)rx + 3 * nrx);
         translate_pts(vrx);
         check_pts(vrx);
-        if (nrx && ttrp_ && intvel_)
+        if (nrx && walk && intvel_)
             throw Err(TTCR_B200_ERR_UNSUPPORTED,
-                      "tt_from_rp=1 with interp_vel=1 (slowness along the raypath from interpolated velocity, Grid3Drn.h:2489-2669) "
-                      "is not part of the B200 path; use interp_vel=0");
+                      "raypaths with interp_vel=1 (slowness along the raypath from interpolated velocity, Grid3Drn.h:2489-2669) "
+                      "are not part of the B200 path; use interp_vel=0");
         ensure_pts(s, 4 * ntx + 5 * nrx);   // Tx, t0 | Rx, traveltimes, status (before the solve: it uploads Tx into this buffer)
         solve_device(s, vtx, vt0);
+        s.rays.clear();
         if (nrx) {
             T* const h_rx = s.h_pts + 4 * ntx;
             T* const d_rx = s.d_pts + 4 * ntx;
             std::memcpy(h_rx, vrx.data(), 3 * nrx * sizeof(T));
             CK(cudaMemcpyAsync(d_rx, h_rx, 3 * nrx * sizeof(T), cudaMemcpyHostToDevice, s.stream));
             T* d_out = d_rx + 3 * nrx;
-            if (ttrp_) {
+            const unsigned rp_blocks = (unsigned)((nrx + 63) / 64);
+            int* d_rn = nullptr;
+            unsigned long long* d_off = nullptr;
+            if (want_rays) {   // counts and offsets of the ray points
+                CK(cudaMallocAsync(&d_rn, nrx * sizeof(int), s.stream));
+                CK(cudaMallocAsync(&d_off, nrx * sizeof(unsigned long long), s.stream));
+            }
+            if (walk) {
                 // Grid3D.h:493-501 with tt_from_rp: traveltimes integrated along the raypaths (raypath.cuh)
-                k_tt_from_rp<T><<<(unsigned)((nrx + 63) / 64), 64, 0, s.stream>>>(g_, d_, s.tt[0], slo_[0], s.d_pts, s.d_pts + 3 * ntx, (int)ntx,
-                                                                                 d_rx, (int)nrx, d_out, d_out + nrx);
+                k_tt_from_rp<T><<<rp_blocks, 64, 0, s.stream>>>(g_, d_, s.tt[0], slo_[0], s.d_pts, s.d_pts + 3 * ntx, (int)ntx, d_rx, (int)nrx,
+                                                                d_out, d_out + nrx, d_rn, nullptr, nullptr);
             } else {
                 k_interp<T><<<(unsigned)((nrx + 127) / 128), 128, 0, s.stream>>>(g_, d_, s.tt[0], d_rx, (int)nrx, d_out);
             }
             CK(cudaGetLastError());
-            CK(cudaMemcpyAsync(h_rx + 3 * nrx, d_out, (ttrp_ ? 2 : 1) * nrx * sizeof(T), cudaMemcpyDeviceToHost, s.stream));
+            CK(cudaMemcpyAsync(h_rx + 3 * nrx, d_out, (walk ? 2 : 1) * nrx * sizeof(T), cudaMemcpyDeviceToHost, s.stream));
+            std::vector<int> rn(want_rays ? nrx : 0);
+            if (want_rays) CK(cudaMemcpyAsync(rn.data(), d_rn, nrx * sizeof(int), cudaMemcpyDeviceToHost, s.stream));
             CK(cudaStreamSynchronize(s.stream));
             std::memcpy(tt, h_rx + 3 * nrx, nrx * sizeof(T));
-            if (ttrp_) {
+            if (walk) {
                 const T* st = h_rx + 4 * nrx;
                 for (size_t n = 0; n < nrx; ++n) {
                     if (st[n] == T(0)) continue;
+                    if (want_rays) { cudaFreeAsync(d_rn, s.stream); cudaFreeAsync(d_off, s.stream); }
                     std::ostringstream msg;
                     if (st[n] == T(1))
                         msg << "Error while computing raypaths: going outside grid \n                Rx: " << vrx[3 * n] << " " << vrx[3 * n + 1] << " "
@@ -258,6 +295,26 @@ class Grid final : public GridBase {
                             << " did not reach a source point";
                     throw Err(TTCR_B200_ERR_RUNTIME, msg.str());
                 }
+            }
+            if (want_rays) {
+                // second pass of the same walk, now storing the points at their offsets
+                std::vector<unsigned long long> off(nrx);
+                unsigned long long total = 0;
+                for (size_t n = 0; n < nrx; ++n) { off[n] = total; total += (unsigned long long)rn[n]; npts[n] = (size_t)rn[n]; }
+                T* d_xyz = nullptr;
+                CK(cudaMallocAsync(&d_xyz, std::max<size_t>(1, 3 * total) * sizeof(T), s.stream));
+                CK(cudaMemcpyAsync(d_off, off.data(), nrx * sizeof(unsigned long long), cudaMemcpyHostToDevice, s.stream));
+                k_tt_from_rp<T><<<rp_blocks, 64, 0, s.stream>>>(g_, d_, s.tt[0], slo_[0], s.d_pts, s.d_pts + 3 * ntx, (int)ntx, d_rx, (int)nrx,
+                                                                d_out, d_out + nrx, d_rn, d_off, d_xyz);
+                CK(cudaGetLastError());
+                s.rays.resize(3 * total);
+                CK(cudaMemcpyAsync(s.rays.data(), d_xyz, 3 * total * sizeof(T), cudaMemcpyDeviceToHost, s.stream));
+                CK(cudaFreeAsync(d_xyz, s.stream));
+                CK(cudaFreeAsync(d_rn, s.stream));
+                CK(cudaFreeAsync(d_off, s.stream));
+                CK(cudaStreamSynchronize(s.stream));
+                if (translate_)   // Grid3D.h:578-584: r_data += origin
+                    for (size_t n = 0; n < s.rays.size(); n += 3) { s.rays[n] += origin_[0]; s.rays[n + 1] += origin_[1]; s.rays[n + 2] += origin_[2]; }
             }
         }
     }
@@ -310,6 +367,8 @@ class Grid final : public GridBase {
         else if (key == "tile_urows") tile_opt_.rows = std::max(1, std::min(4, (int)v));
         else if (key == "tile_depth") tile_opt_.depth = (int)v;
         else if (key == "spin_limit") tile_opt_.spin_limit = (long long)v;
+        else if (key == "plane_graph") plane_graph_ = v != 0;
+        else if (key == "plane_pdl") plane_pdl_ = v != 0;
         else if (key == "use_pool") {}
         else if (key == "maxit") maxit_ = (int)v;
         else throw Err(TTCR_B200_ERR_INVALID, "unknown option '" + key + "'");
@@ -329,6 +388,10 @@ class Grid final : public GridBase {
         TileState tile;
         Tile5State tile5;
         ttcr_b200_stats st{};
+        FrozenBox* d_fb = nullptr;           // the source's frozen box, for k_sweep_plane (launch arguments stay source independent)
+        struct PlaneGraph { cudaGraphExec_t exec = nullptr; bool pdl = false; };
+        PlaneGraph pgraph[8][2];             // captured plane launches of a direction: [dir][first order | WENO]
+        std::vector<T> rays;                 // points of the last raytrace_rays call, ray after ray (x,y,z)
         std::vector<cudaEvent_t> sweep_ev;   // pairs of events around the directional sweeps
         size_t sweep_ev_used = 0;
     };
@@ -437,17 +500,57 @@ class Grid final : public GridBase {
             s.st.launches += nl; s.st.sweep_launches += nl;
             return;
         }
-        const dim3 block(32, 8);
+        // One launch per wavefront plane (the OpenCL design, Grid3Drn_OpenCL.h:839-848).  Launch bound: the np launches of
+        // a direction are captured once per slot into a CUDA graph (their arguments do not depend on the source) and
+        // replayed, optionally chained by programmatic dependent launch so that plane p+1 is resident when p drains.
         const int np = w.nu + w.nm - 1;
-        for (int p = 0; p < np; ++p) {
-            const int u_lo = std::max(0, p - w.nm + 1), u_hi = std::min(w.nu - 1, p);
-            const dim3 grid(d_.kpad / 32, (u_hi - u_lo + 1 + 7) / 8);
-            if (weno_stage)
-                k_sweep_plane<T, true><<<grid, block, 0, s.stream>>>(w, d_, tt, slo_[w.layout], s.mask[w.layout], fb, p,
-                                                                    u_lo, u_hi, g_.dx, s.d_change);
-            else
-                k_sweep_plane<T, false><<<grid, block, 0, s.stream>>>(w, d_, tt, slo_[w.layout], s.mask[w.layout], fb, p,
-                                                                     u_lo, u_hi, g_.dx, s.d_change);
+        auto launch_all = [&]() {
+            const dim3 block(32, 8);
+            const T* slo = slo_[w.layout];
+            const uint32_t* mask = s.mask[w.layout];
+            const FrozenBox* fbp = s.d_fb;
+            T dx = g_.dx;
+            double* chg = s.d_change;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            at[0].val.programmaticStreamSerializationAllowed = 1;
+            for (int p = 0; p < np; ++p) {
+                int u_lo = std::max(0, p - w.nm + 1), u_hi = std::min(w.nu - 1, p);
+                cudaLaunchConfig_t cfg{};
+                cfg.gridDim = dim3(d_.kpad / 32, (u_hi - u_lo + 1 + 7) / 8);
+                cfg.blockDim = block;
+                cfg.dynamicSmemBytes = 0;
+                cfg.stream = s.stream;
+                cfg.attrs = at;
+                cfg.numAttrs = (plane_pdl_ && p > 0) ? 1 : 0;
+                if (weno_stage)
+                    CK(cudaLaunchKernelEx(&cfg, k_sweep_plane<T, true>, w, d_, tt, slo, mask, fbp, p, u_lo, u_hi, dx, chg));
+                else
+                    CK(cudaLaunchKernelEx(&cfg, k_sweep_plane<T, false>, w, d_, tt, slo, mask, fbp, p, u_lo, u_hi, dx, chg));
+            }
+        };
+        if (plane_graph_) {
+            auto& pg = s.pgraph[dir][weno_stage ? 1 : 0];
+            if (pg.exec && pg.pdl != plane_pdl_) { cudaGraphExecDestroy(pg.exec); pg.exec = nullptr; }
+            if (!pg.exec) {
+                cudaGraph_t gr = nullptr;
+                CK(cudaStreamBeginCapture(s.stream, cudaStreamCaptureModeThreadLocal));
+                try {
+                    launch_all();
+                } catch (...) {
+                    cudaStreamEndCapture(s.stream, &gr);
+                    if (gr) cudaGraphDestroy(gr);
+                    throw;
+                }
+                CK(cudaStreamEndCapture(s.stream, &gr));
+                const cudaError_t e = cudaGraphInstantiate(&pg.exec, gr, 0);
+                cudaGraphDestroy(gr);
+                CK(e);
+                pg.pdl = plane_pdl_;
+            }
+            CK(cudaGraphLaunch(pg.exec, s.stream));
+        } else {
+            launch_all();
         }
         s.st.launches += np; s.st.sweep_launches += np;
     }
@@ -478,6 +581,7 @@ class Grid final : public GridBase {
 
         s.sweep_ev_used = 0;
         CK(cudaEventRecord(s.e0, s.stream));
+        CK(cudaMemcpyAsync(s.d_fb, &fb, sizeof(FrozenBox), cudaMemcpyHostToDevice, s.stream));   // (pageable: staged before the call returns)
         CK(cudaMemcpyAsync(s.d_pts, s.h_pts, 4 * ntx * sizeof(T), cudaMemcpyHostToDevice, s.stream));
         // Node3Dn::reinit: every node +MAX; the slots that are no node hold +MAX anyway, so this is a plain fill
         k_fill16<T><<<nblocks(ne / (16 / sizeof(T)), 256, 148 * 32), 256, 0, s.stream>>>(s.tt[0], ne, Lim<T>::max());
@@ -571,6 +675,9 @@ class Grid final : public GridBase {
     int maxit_;
     bool weno_, ttrp_, cell_, translate_, intvel_;
     bool have_slowness_ = false;
+    // plane-per-launch sweeps (WENO stage, small grids): replay a captured graph / chain the planes by PDL
+    bool plane_graph_ = getenv("TTCR_B200_PLANE_GRAPH") ? atoi(getenv("TTCR_B200_PLANE_GRAPH")) != 0 : true;
+    bool plane_pdl_ = getenv("TTCR_B200_PLANE_PDL") ? atoi(getenv("TTCR_B200_PLANE_PDL")) != 0 : false;
     int dev_ = 0, sm_count_ = 148;
     int kernel_ = TTCR_B200_KERNEL_AUTO;
     TileOptions tile_opt_{};
@@ -673,6 +780,21 @@ int ttcr_b200_raytrace(ttcr_b200_grid* g, const void* tx, const void* t0, size_t
                        size_t slot) {
     NEED(g);
     return guard([&] { g->impl->raytrace(tx, t0, ntx, rx, nrx, tt, slot); });
+}
+
+int ttcr_b200_raytrace_rays(ttcr_b200_grid* g, const void* tx, const void* t0, size_t ntx, const void* rx, size_t nrx, void* tt,
+                            size_t* ray_npts, size_t slot) {
+    NEED(g);
+    return guard([&] {
+        if (nrx && !ray_npts) throw Err(TTCR_B200_ERR_INVALID, "ray_npts must not be NULL");
+        size_t dummy = 0;
+        g->impl->raytrace_rays(tx, t0, ntx, rx, nrx, tt, ray_npts ? ray_npts : &dummy, slot);
+    });
+}
+
+int ttcr_b200_get_rays(ttcr_b200_grid* g, size_t slot, void* xyz_out) {
+    NEED(g);
+    return guard([&] { g->impl->get_rays(slot, xyz_out); });
 }
 int ttcr_b200_raytrace_multi(ttcr_b200_grid* g, size_t nsrc, const size_t* tx_off, const void* tx, const void* t0,
                              const size_t* rx_off, const void* rx, void* tt, int* niter, int* niterw) {

@@ -332,8 +332,15 @@ struct FrozenBox {   // conservative bounding box (true i,j,k) of all frozen nod
 
 template <typename T, bool WENO>
 __global__ void __launch_bounds__(256) k_sweep_plane(SweepView w, Dims d, T* __restrict__ tt, const T* __restrict__ slo,
-                                                     const uint32_t* __restrict__ frozen, FrozenBox fb, int p,
+                                                     const uint32_t* __restrict__ frozen, const FrozenBox* __restrict__ fbp, int p,
                                                      int u_lo, int u_hi, T dx, double* __restrict__ change) {
+    // Programmatic dependent launch (grid.cu launches the planes of a sweep with programmatic stream serialisation):
+    // let plane p+1 be scheduled now, and touch memory only when plane p-1 has completed and flushed.  Both are no-ops
+    // in a plain launch.  The frozen box sits in device memory so that the launch arguments of a plane do not depend
+    // on the source: the planes of a sweep are captured once into a CUDA graph and replayed.
+    asm volatile("griddepcontrol.launch_dependents;");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    const FrozenBox fb = *fbp;
     const int v = blockIdx.x * 32 + threadIdx.x;
     const int u = u_lo + blockIdx.y * 8 + threadIdx.y;
     const int m = p - u;

@@ -177,17 +177,29 @@ __device__ __forceinline__ T rp_dist(T ax, T ay, T az, T bx, T by, T bz) {
 template <typename T>
 __global__ void k_tt_from_rp(Geom<T> g, Dims d, const T* __restrict__ tt_l1, const T* __restrict__ s_l1, const T* __restrict__ tx,
                              const T* __restrict__ t0, int ntx, const T* __restrict__ rx, int nrx, T* __restrict__ out,
-                             T* __restrict__ status) {
+                             T* __restrict__ status, int* __restrict__ ray_n, const unsigned long long* __restrict__ ray_off,
+                             T* __restrict__ ray_xyz) {
+    // ray_n != nullptr: the points of the raypath are wanted too (Grid3Drn::getRaypath, Grid3Drn.h:1339-1500: the same walk
+    // with r_data.push_back).  First launch with ray_xyz == nullptr counts them, the second one (ray_off = exclusive prefix
+    // sum of the counts) stores them.
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= nrx) return;
+    int npt = 0;
+    T* const rp = ray_xyz ? ray_xyz + 3 * ray_off[r] : nullptr;
+    auto push = [&](T x, T y, T z) {
+        if (rp) { rp[3 * npt] = x; rp[3 * npt + 1] = y; rp[3 * npt + 2] = z; }
+        ++npt;
+    };
     const T dx = g.dx;
     const T k1 = 1. / 24., k2 = 9. / 8.;
     const T maxDist = rp_sqrt(dx * dx + dx * dx + dx * dx);
     const T Rx = rx[3 * r], Ry = rx[3 * r + 1], Rz = rx[3 * r + 2];
+    push(Rx, Ry, Rz);
     for (int ns = 0; ns < ntx; ++ns)
         if (Rx == tx[3 * ns] && Ry == tx[3 * ns + 1] && Rz == tx[3 * ns + 2]) {
             out[r] = t0[ns];
             status[r] = T(0);
+            if (ray_n) ray_n[r] = npt;
             return;
         }
     T ttr = 0.0;
@@ -197,7 +209,7 @@ __global__ void k_tt_from_rp(Geom<T> g, Dims d, const T* __restrict__ tt_l1, con
     bool reached = false;
     const long long guard_max = 16ll * (g.ncx + g.ncy + g.ncz) + 1024;
     for (long long it = 0; !reached; ++it) {
-        if (it >= guard_max) { out[r] = ttr; status[r] = T(2); return; }
+        if (it >= guard_max) { out[r] = ttr; status[r] = T(2); if (ray_n) ray_n[r] = npt; return; }
         T q[4], gx, gy, gz;
         rp_stencil(cx, dx, dx, g.xmin, g.xmax, q);   // x: first point at pt.x - dx (sic, Grid3Drn.h:1041)
         gx = (k1 * rp_tt_at(g, d, tt_l1, q[0], cy, cz) - k2 * rp_tt_at(g, d, tt_l1, q[1], cy, cz) + k2 * rp_tt_at(g, d, tt_l1, q[2], cy, cz) -
@@ -213,12 +225,14 @@ __global__ void k_tt_from_rp(Geom<T> g, Dims d, const T* __restrict__ tt_l1, con
         if (cx < g.xmin || cx > g.xmax || cy < g.ymin || cy > g.ymax || cz < g.zmin || cz > g.zmax) {
             out[r] = ttr;
             status[r] = T(1);
+            if (ray_n) ray_n[r] = npt;
             return;
         }
         s2 = rp_slow_at(g, d, s_l1, cx, cy, cz);
         ttr += 0.5 * (s1 + s2) * rp_dist(px, py, pz, cx, cy, cz);
         s1 = s2;
         px = cx; py = cy; pz = cz;
+        push(cx, cy, cz);
         // close enough to one of the Tx points?  (the reference does not leave this loop early)
         for (int ns = 0; ns < ntx; ++ns) {
             const T Tx = tx[3 * ns], Ty = tx[3 * ns + 1], Tz = tx[3 * ns + 2];
@@ -228,12 +242,15 @@ __global__ void k_tt_from_rp(Geom<T> g, Dims d, const T* __restrict__ tt_l1, con
                 if (rp_dist(cx, cy, cz, px, py, pz) > dist || (cx == Tx && cy == Ty && cz == Tz)) {
                     s2 = rp_slow_at(g, d, s_l1, Tx, Ty, Tz);
                     ttr += t0[ns] + 0.5 * (s1 + s2) * rp_dist(px, py, pz, Tx, Ty, Tz);
+                    push(Tx, Ty, Tz);
                 } else {
                     s2 = rp_slow_at(g, d, s_l1, cx, cy, cz);
                     ttr += 0.5 * (s1 + s2) * rp_dist(px, py, pz, cx, cy, cz);
+                    push(cx, cy, cz);
                     s1 = s2;
                     s2 = rp_slow_at(g, d, s_l1, Tx, Ty, Tz);
                     ttr += t0[ns] + 0.5 * (s1 + s2) * rp_dist(cx, cy, cz, Tx, Ty, Tz);
+                    push(Tx, Ty, Tz);
                 }
                 reached = true;
             }
@@ -241,6 +258,7 @@ __global__ void k_tt_from_rp(Geom<T> g, Dims d, const T* __restrict__ tt_l1, con
     }
     out[r] = ttr;
     status[r] = T(0);
+    if (ray_n) ray_n[r] = npt;
 }
 
 }  // namespace ttcrb200

@@ -18,8 +18,10 @@ Differences, all deliberate:
   the reference's one-source-per-thread fan-out, ttcr/Grid3D.h:810-853).
 * ``tt_from_rp=True`` (the reference's default: receiver traveltimes integrated along the raypaths,
   ttcr/Grid3Drn.h:1103-1243) runs on the device, one thread per receiver, bit-identical to the reference.
-* ``compute_L`` / ``compute_M`` / ``return_rays`` raise ``NotImplementedError``: they belong to the
-  post-solve stages.
+* ``return_rays=True`` returns the raypaths of ``Grid3Drn::getRaypath`` (ttcr/Grid3Drn.h:1339-1500), walked on the
+  device (two passes: count, then store), bit-identical to the reference.
+* ``compute_L`` / ``compute_M`` raise ``NotImplementedError`` (for the FSM the reference itself rejects
+  ``compute_L``, rgrid.pyx:915-916; M matrices belong to the post-solve stages).
 """
 from __future__ import annotations
 
@@ -275,8 +277,8 @@ class _Grid3d:
             raise NotImplementedError("compute_L defined only for grids with slowness defined for cells")
         if compute_L:
             raise NotImplementedError("compute_L defined for the FSM")   # rgrid.pyx:915-916
-        if compute_M or return_rays:
-            raise NotImplementedError("raypaths / M matrices are post-solve stages outside the B200 FSM path")
+        if compute_M:
+            raise NotImplementedError("M matrices are a post-solve stage outside the B200 FSM path")
 
         evID = None
         if source.shape[1] == 5:
@@ -335,6 +337,19 @@ class _Grid3d:
                 iRx.append(ii); vRx.append(rcv[ii, :])
 
         tt = np.zeros((rcv.shape[0],), dtype=self.dtype)
+        if return_rays:
+            # rgrid.pyx:1072-1084, :1110-1121: one array (npts, 3) per receiver, in the order of rcv.  Sources run one
+            # after the other on one slot (the walk is a few microseconds per receiver next to the solve).
+            if thread_no is not None:
+                assert nTx == 1
+            slot = 0 if thread_no is None else int(thread_no)
+            rays = [None] * rcv.shape[0]
+            for n in range(nTx):
+                t, r = self._raytrace_one(vTx[n], vt0[n], vRx[n], slot, rays=True)
+                tt[iRx[n]] = t
+                for i, ir in enumerate(iRx[n]):
+                    rays[int(ir)] = r[i]
+            return tt, rays
         if self._n_threads == 1 or thread_no is not None or nTx == 1:
             if thread_no is not None:
                 assert nTx == 1
@@ -357,11 +372,20 @@ class _Grid3d:
                 tt[iRx[n]] = out[int(rx_off[n]):int(rx_off[n + 1])]
         return tt
 
-    def _raytrace_one(self, tx, t0, rx, slot):
+    def _raytrace_one(self, tx, t0, rx, slot, rays=False):
         tx = np.ascontiguousarray(tx, dtype=self.dtype)
         t0 = np.ascontiguousarray(t0, dtype=self.dtype)
         rx = np.ascontiguousarray(rx, dtype=self.dtype)
         out = np.empty(rx.shape[0], dtype=self.dtype)
+        if rays:
+            npts = np.zeros(rx.shape[0], dtype=np.uintp)
+            self._chk(self._lib.ttcr_b200_raytrace_rays(self._h, tx.ctypes.data, t0.ctypes.data, tx.shape[0], rx.ctypes.data,
+                                                        rx.shape[0], out.ctypes.data, npts.ctypes.data, slot))
+            xyz = np.empty((int(npts.sum()), 3), dtype=self.dtype)
+            self._chk(self._lib.ttcr_b200_get_rays(self._h, slot, xyz.ctypes.data))
+            ends = np.cumsum(npts).astype(np.int64)
+            # the reference hands back float64 arrays whatever the grid's dtype (rgrid.pyx:1076: np.empty((n, 3)))
+            return out, [xyz[int(e - n):int(e)].astype(np.float64) for n, e in zip(npts, ends)]
         self._chk(self._lib.ttcr_b200_raytrace(self._h, tx.ctypes.data, t0.ctypes.data, tx.shape[0], rx.ctypes.data,
                                                rx.shape[0], out.ctypes.data, slot))
         return out
