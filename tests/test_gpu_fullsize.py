@@ -126,3 +126,23 @@ def test_config5_1024_runs_and_is_consistent():
     assert err / cnt < 1e-2
     ex_r = [float(np.arccosh(1.0 + 0.01 * np.sum((r - src[0]) ** 2) / (2.0 * (1 + 0.1 * src[0, 2]) * (1 + 0.1 * r[2]))) / 0.1) for r in rcv]
     assert np.allclose(tt, ex_r, rtol=1e-2)
+
+
+def test_pipelined_model_import_round_trip():
+    """A >= 64 MiB node model in numpy order is copied and imported chunk by chunk (Grid::set_slowness_any); what comes back
+    from get_slowness is the array that went in, pinned or pageable, and a set_slowness that follows immediately wins."""
+    import torch
+    from ttcr_b200 import Grid3d
+    n = (260, 250, 270)          # chunk boundaries that do not divide ni
+    rng = np.random.default_rng(5)
+    s = rng.uniform(0.2, 1.0, n).astype(np.float32)
+    x, y, z = (np.arange(m, dtype=np.float64) for m in n)
+    g = Grid3d(x, y, z, cell_slowness=0, tt_from_rp=False, weno=0, dtype=np.float32)
+    g.set_slowness(s)
+    assert np.array_equal(g.get_slowness(), s)
+    sp = torch.from_numpy(s[::-1].copy()).pin_memory()
+    g.set_slowness(sp.numpy())
+    g.set_slowness(s * np.float32(2))
+    assert np.array_equal(g.get_slowness(), s * np.float32(2))
+    g.set_slowness(sp.numpy())
+    assert np.array_equal(g.get_slowness(), sp.numpy())

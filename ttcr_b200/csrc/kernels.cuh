@@ -49,9 +49,11 @@ __device__ __forceinline__ size_t lin_index(const Dims& d, int order, int i, int
 
 // one thread per slot of the destination layout (coalesced stores, gathered loads)
 template <typename T>
-__global__ void k_import(const T* __restrict__ lin, int order, T* __restrict__ dst, int layout, Dims d) {
-    const size_t n = d.elems();
-    size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void k_import(const T* __restrict__ lin, int order, T* __restrict__ dst, int layout, Dims d, int i0 = 0, int i1 = -1) {
+    // planes i0 <= i < i1 of the destination (default: all); a model arriving from the host is imported chunk by chunk
+    // behind its own copy (Grid::set_slowness_any)
+    const size_t n = (size_t)(i1 < 0 ? d.ni : i1) * d.qs * d.kpad;
+    size_t e = (size_t)i0 * d.qs * d.kpad + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     for (; e < n; e += stride) {
         const int k = (int)(e % d.kpad);
@@ -330,19 +332,12 @@ struct FrozenBox {   // conservative bounding box (true i,j,k) of all frozen nod
     int ilo, ihi, jlo, jhi, klo, khi;
 };
 
+// The update of node (u, p - u, v) of wavefront plane p in oriented coordinates, first order (Grid3Drn.h:2902-2959) or
+// WENO (:3078-3484); returns the decrease of its traveltime (0 if the slot is no node, frozen or unchanged).
 template <typename T, bool WENO>
-__global__ void __launch_bounds__(256) k_sweep_plane(SweepView w, Dims d, T* __restrict__ tt, const T* __restrict__ slo,
-                                                     const uint32_t* __restrict__ frozen, const FrozenBox* __restrict__ fbp, int p,
-                                                     int u_lo, int u_hi, T dx, double* __restrict__ change) {
-    // Programmatic dependent launch (grid.cu launches the planes of a sweep with programmatic stream serialisation):
-    // let plane p+1 be scheduled now, and touch memory only when plane p-1 has completed and flushed.  Both are no-ops
-    // in a plain launch.  The frozen box sits in device memory so that the launch arguments of a plane do not depend
-    // on the source: the planes of a sweep are captured once into a CUDA graph and replayed.
-    asm volatile("griddepcontrol.launch_dependents;");
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-    const FrozenBox fb = *fbp;
-    const int v = blockIdx.x * 32 + threadIdx.x;
-    const int u = u_lo + blockIdx.y * 8 + threadIdx.y;
+__device__ __forceinline__ double plane_node(const SweepView& w, const Dims& d, T* __restrict__ tt, const T* __restrict__ slo,
+                                             const uint32_t* __restrict__ frozen, const FrozenBox& fb, int p, int u, int u_hi, int v,
+                                             T dx) {
     const int m = p - u;
     const int jo = m - v + w.joff;   // oriented j
     const int ko = v - w.vlo;        // oriented k
@@ -391,8 +386,66 @@ __global__ void __launch_bounds__(256) k_sweep_plane(SweepView w, Dims d, T* __r
             }
         }
     }
+    return delta;
+}
+
+template <typename T, bool WENO>
+__global__ void __launch_bounds__(256) k_sweep_plane(SweepView w, Dims d, T* __restrict__ tt, const T* __restrict__ slo,
+                                                     const uint32_t* __restrict__ frozen, const FrozenBox* __restrict__ fbp, int p,
+                                                     int u_lo, int u_hi, T dx, double* __restrict__ change) {
+    // Programmatic dependent launch (grid.cu launches the planes of a sweep with programmatic stream serialisation):
+    // let plane p+1 be scheduled now, and touch memory only when plane p-1 has completed and flushed.  Both are no-ops
+    // in a plain launch.  The frozen box sits in device memory so that the launch arguments of a plane do not depend
+    // on the source: the planes of a sweep are captured once into a CUDA graph and replayed.
+    asm volatile("griddepcontrol.launch_dependents;");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    const FrozenBox fb = *fbp;
+    const int v = blockIdx.x * 32 + threadIdx.x;
+    const int u = u_lo + blockIdx.y * 8 + threadIdx.y;
+    double delta = plane_node<T, WENO>(w, d, tt, slo, frozen, fb, p, u, u_hi, v, dx);
     // block reduction of the L1 change (Grid3Drnfs.h:144-150; tt only ever decreases, so the
     // per-sweep decreases telescope to sum |times - tt| of the iteration)
+    for (int o = 16; o > 0; o >>= 1) delta += __shfl_xor_sync(0xffffffffu, delta, o);
+    if (threadIdx.x == 0 && delta != 0.0) atomicAdd(change, delta);
+}
+
+// All wavefront planes of a directional sweep in ONE cooperative launch: the grid walks the planes and meets at a
+// grid-wide barrier after each (a kernel boundary costs ~3 us even inside a CUDA graph, the barrier well under 1 us).
+// Plane p is cut into the same (32 lanes x 8 planes of u) blocks as k_sweep_plane's grid; CTA c takes blocks c, c + G, ...
+// `bar` is a monotone arrival counter owned by the launch (zeroed by the host before it): after plane p every CTA has
+// added 1, so the release value is (p + 1) * G.  The fence before the arrival publishes the CTA's stores, the acquire
+// load after it (plus the CTA barrier) makes everybody else's visible, L1 included.
+template <typename T, bool WENO>
+__global__ void __launch_bounds__(256) k_sweep_planes_coop(SweepView w, Dims d, T* __restrict__ tt, const T* __restrict__ slo,
+                                                           const uint32_t* __restrict__ frozen, const FrozenBox* __restrict__ fbp,
+                                                           T dx, double* __restrict__ change, unsigned* __restrict__ bar) {
+    const FrozenBox fb = *fbp;
+    const int np = w.nu + w.nm - 1;
+    const int vb = d.kpad / 32;
+    const bool leader = threadIdx.x == 0 && threadIdx.y == 0;
+    double delta = 0.0;
+    for (int p = 0; p < np; ++p) {
+        const int u_lo = max(0, p - w.nm + 1), u_hi = min(w.nu - 1, p);
+        const int nblk = vb * ((u_hi - u_lo + 1 + 7) / 8);
+        for (int b = blockIdx.x; b < nblk; b += gridDim.x) {
+            const int by = b / vb, bx = b - by * vb;
+            delta += plane_node<T, WENO>(w, d, tt, slo, frozen, fb, p, u_lo + by * 8 + (int)threadIdx.y, u_hi, bx * 32 + (int)threadIdx.x, dx);
+        }
+        if (p + 1 < np) {
+            __syncthreads();
+            if (leader) {
+                __threadfence();
+                atomicAdd(bar, 1u);
+                const unsigned want = (unsigned)(p + 1) * gridDim.x;
+                unsigned seen;
+                do {
+                    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(bar) : "memory");
+                } while (seen < want);
+                __threadfence();
+            }
+            __syncthreads();
+        }
+    }
     for (int o = 16; o > 0; o >>= 1) delta += __shfl_xor_sync(0xffffffffu, delta, o);
     if (threadIdx.x == 0 && delta != 0.0) atomicAdd(change, delta);
 }
