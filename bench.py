@@ -289,6 +289,30 @@ def main():
     h2d = int(s_np.nbytes + src4.astype(np.float32).nbytes + rcv.astype(np.float32).nbytes)
     d2h = int(tt.astype(np.float32).nbytes)
 
+    # ---- side measurement (1 GPU, not the headline): two independent sources solved concurrently on two slots of one
+    # grid (configs[3]'s situation: many sources per GPU); aggregate node-sweeps per second of the pair
+    pair = None
+    if world == 1 and n <= 512:
+        try:
+            g2 = Grid3d(x, x, x, n_threads=2, cell_slowness=0, method="FSM", tt_from_rp=0, eps=1e-5, maxit=50, weno=0,
+                        dtype=np.float32, device=local_rank)
+            g2.set_slowness(s_np)
+            two = np.vstack([src[0], source_for_rank(x, 1)[0]])
+            g2.raytrace_sources(two, rcv)
+            torch.cuda.synchronize()
+            t2 = time.perf_counter()
+            reps = max(2, min(args.steps, 5))
+            sw2 = 0
+            for _ in range(reps):
+                g2.raytrace_sources(two, rcv)
+                sw2 += g2.get_stats(0)["sweeps"] + g2.get_stats(1)["sweeps"]
+            torch.cuda.synchronize()
+            pair = {"sources": 2, "value": float(n) ** 3 * sw2 / (time.perf_counter() - t2) / 1e6, "unit": UNIT,
+                    "note": "two slots / CUDA streams of one grid, wall clock around raytrace_sources()"}
+            g2.close()
+        except Exception as e:
+            pair = {"error": str(e)}
+
     # ---- reduce over ranks: whole-job node-sweeps, max time ------------------------------------------
     nodes = float(n) ** 3
     mine = torch.tensor([nodes * sweeps, dev_ms, wall_ms, nodes * e2e_sweeps, e2e_ms, sweep_ms, float(sweeps),
@@ -327,7 +351,8 @@ def main():
             "detail": {"niter": st["niter"], "sweeps_per_step": st["sweeps"], "solve_ms_last": st["solve_ms"],
                        "sweep_ms_per_step": sweep_ms / args.steps, "wall_ms_per_step": mx[2] / args.steps,
                        "mnode_iters_per_s": value / 8.0, "kernel": st["kernel"],
-                       "device_bytes": g.device_bytes(), "launches_per_step": launches / args.steps},
+                       "device_bytes": g.device_bytes(), "launches_per_step": launches / args.steps,
+                       "concurrent_sources": pair},
         }
         if not args.no_cpu_baseline:
             try:

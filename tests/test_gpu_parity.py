@@ -264,3 +264,27 @@ def test_raypaths_vs_oracle(oracle, dtype):
         t1, r1 = g.raytrace(src[i:i + 1], rcv[i:i + 1], return_rays=True)
         assert tt[i] == t1[0] and np.array_equal(rays[i], r1[0])
         assert np.array_equal(rays[i][-1], src[i].astype(dtype).astype(np.float64))
+
+
+@pytest.mark.parametrize("n_threads", [1, 2, 3])
+def test_raytrace_sources_matches_single_solves(n_threads):
+    """the source fan-out over slots (ttcr_b200_raytrace_multi, Grid3D.h:810-853) returns, source by source, exactly what
+    a solve of that source alone returns, iterations included"""
+    from ttcr_b200 import Grid3d
+    x, s = _model(40, 9)
+    rng = np.random.default_rng(11)
+    src = rng.uniform(0.5, 19.5, (5, 3))
+    rcv = rng.uniform(0.5, 19.5, (9, 3))
+    t0 = np.array([0.0, 0.5, 0.0, 1.25, 0.0])
+    g = Grid3d(x, x, x, n_threads=n_threads, cell_slowness=0, tt_from_rp=False, weno=1, dtype=np.float32)
+    g.set_slowness(s)
+    tt, its = g.raytrace_sources(src, rcv, t0)
+    assert tt.shape == (5, 9) and its.shape == (5, 2)
+    g1 = Grid3d(x, x, x, cell_slowness=0, tt_from_rp=False, weno=1, dtype=np.float32)
+    g1.set_slowness(s)
+    for i in range(5):
+        ref = g1.raytrace(np.column_stack([t0[i:i + 1], src[i:i + 1]]), rcv)
+        assert np.array_equal(tt[i], ref)
+        assert tuple(its[i]) == g1.get_niter()
+    tt0, its0 = g.raytrace_sources(np.zeros((0, 3)), rcv)
+    assert tt0.shape == (0, 9) and its0.shape == (0, 2)

@@ -18,7 +18,7 @@ s = ((1 + 0.3 * np.sin(0.7 * X) * np.cos(0.9 * Y)) / (1 + 0.1 * Z)).astype(np.fl
 rng = np.random.default_rng(7)
 src = rng.uniform(0.5, 19.5, (5, 3))
 rcv = rng.uniform(0.5, 19.5, (33, 3))
-g = Grid3d(x, x, x, cell_slowness=0, tt_from_rp=False, weno=0, dtype=np.float32, device=local)
+g = Grid3d(x, x, x, n_threads=2, cell_slowness=0, tt_from_rp=False, weno=0, dtype=np.float32, device=local)
 tt, its = raytrace_sharded(g, src, rcv, s if rank == 0 else None)
 g1 = Grid3d(x, x, x, cell_slowness=0, tt_from_rp=False, weno=0, dtype=np.float32, device=local)
 g1.set_slowness(s)

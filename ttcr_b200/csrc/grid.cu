@@ -548,9 +548,12 @@ class Grid final : public GridBase {
                 else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sweep_planes_coop<T, false>, 256, 0));
                 if (occ < 1) throw Err(TTCR_B200_ERR_CUDA, "k_sweep_planes_coop does not fit on an SM");
             }
-            // enough CTAs for about half of the widest plane, at most coop_ctas_ (4) per SM: the barrier costs one atomic per CTA
-            const int per_sm = std::max(1, std::min(std::min(occ, coop_ctas_), (max_blocks + 2 * sm_count_ - 1) / (2 * sm_count_)));
-            const int grid = std::max(1, std::min(max_blocks, per_sm * sm_count_));
+            // About one CTA per block of the widest plane (half of a plane's blocks hold no node: the sheared rows), at most
+            // coop_ctas_ per SM: the barrier costs one atomic per CTA.  CTA c takes blocks c, c + G, ...: G is made odd so
+            // that a CTA does not always land on the same lane chunk (chunks near the row ends are mostly empty).
+            const int per_sm = std::max(1, std::min(std::min(occ, coop_ctas_), (max_blocks + sm_count_ - 1) / sm_count_));
+            int grid = std::max(1, std::min(max_blocks, per_sm * sm_count_));
+            if (grid > 1 && grid < max_blocks && grid % 2 == 0) --grid;
             CK(cudaMemsetAsync(s.d_bar, 0, sizeof(unsigned), s.stream));
             SweepView wv = w;
             Dims dv = d_;

@@ -346,6 +346,11 @@ __device__ __forceinline__ double plane_node(const SweepView& w, const Dims& d, 
     if (valid) {
         const long long e = w.base + (long long)u * w.su + (long long)m * w.sm + (long long)v * w.sv;
         const int it = w.ri ? d.ni - 1 - u : u, jt = w.rj ? d.nj - 1 - jo : jo, kt = w.rk ? d.nk - 1 - ko : ko;
+        // The next plane updates (u, m+1, v): everything it reads has been touched by this plane or the ones before,
+        // except its farthest downwind row and its slowness.  Pull those into L2 now (guard rows keep the addresses
+        // inside the arrays), so that the next plane waits for L2, not for DRAM.
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(tt + e + (WENO ? 3 : 2) * w.sm));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(slo + e + w.sm));
         bool frz = false;
         if (it >= fb.ilo && it <= fb.ihi && jt >= fb.jlo && jt <= fb.jhi && kt >= fb.klo && kt <= fb.khi)
             frz = (frozen[e >> 5] >> (e & 31)) & 1u;

@@ -859,7 +859,11 @@ inline int tile5_launch(TileState& s, Tile5State& s5, const TileOptions& o, int 
     if (s5.order_key != key || s5.ntiles != p.ntiles) {
         // ticket order: a linear extension of (U-1,V) < (U,V), (U,V-1) < (U,V), sorted by estimated start time
         std::vector<std::pair<long long, int>> k(p.ntiles);
-        const long long lag_u = PU + 4;
+        // start-time estimate of a tile: one hop along U costs PU steps plus hand-off; a larger value (TTCR_B200_LAG_U)
+        // spreads the tiles in flight further apart along m, trading start-up time for slack between a tile and its
+        // predecessor
+        static const int lag_env = getenv("TTCR_B200_LAG_U") ? atoi(getenv("TTCR_B200_LAG_U")) : 0;
+        const long long lag_u = lag_env > 0 ? lag_env : PU + 4;
         for (int U = 0; U < p.nU; ++U)
             for (int V = 0; V < p.nV; ++V) {
                 const int va = std::max(V * 128, w.vlo);

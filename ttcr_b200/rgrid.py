@@ -372,6 +372,31 @@ class _Grid3d:
                 tt[iRx[n]] = out[int(rx_off[n]):int(rx_off[n + 1])]
         return tt
 
+    def raytrace_sources(self, sources, rcv, t0=None):
+        """Extension for source-parallel work: solve the ``n`` independent sources (n x 3) against the same receivers
+        (m x 3).  The sources are dealt to the ``n_threads`` slots of the grid, each on its own CUDA stream
+        (``ttcr_b200_raytrace_multi``; the reference's one-source-per-thread fan-out, ttcr/Grid3D.h:810-853), so with
+        ``n_threads >= 2`` consecutive solves overlap on the device.  Returns ``(tt (n, m), iterations (n, 2))``."""
+        sources = np.ascontiguousarray(np.asarray(sources, dtype=self.dtype).reshape(-1, 3))
+        rcv = np.ascontiguousarray(np.asarray(rcv, dtype=self.dtype).reshape(-1, 3))
+        n, m = sources.shape[0], rcv.shape[0]
+        t0a = np.zeros(n, dtype=self.dtype) if t0 is None else np.ascontiguousarray(np.asarray(t0, dtype=self.dtype).reshape(n))
+        if n and self.is_outside(sources):
+            raise ValueError("Source point outside grid")
+        if m and self.is_outside(rcv):
+            raise ValueError("Receiver outside grid")
+        tx_off = np.arange(n + 1, dtype=np.uintp)
+        rx_off = np.arange(n + 1, dtype=np.uintp) * np.uintp(m)
+        rxa = np.ascontiguousarray(np.tile(rcv, (n, 1)))
+        out = np.empty(n * m, dtype=self.dtype)
+        ni = np.zeros(n, dtype=np.int32)
+        nw = np.zeros(n, dtype=np.int32)
+        if n:
+            self._chk(self._lib.ttcr_b200_raytrace_multi(self._h, n, tx_off.ctypes.data, sources.ctypes.data, t0a.ctypes.data,
+                                                         rx_off.ctypes.data, rxa.ctypes.data, out.ctypes.data, ni.ctypes.data,
+                                                         nw.ctypes.data))
+        return out.reshape(n, m), np.column_stack([ni, nw]).astype(np.int64)
+
     def _raytrace_one(self, tx, t0, rx, slot, rays=False):
         tx = np.ascontiguousarray(tx, dtype=self.dtype)
         t0 = np.ascontiguousarray(t0, dtype=self.dtype)
