@@ -50,6 +50,22 @@ static inline unsigned nblocks(size_t n, unsigned threads = 256, unsigned cap = 
     return (unsigned)std::min<size_t>(std::max<size_t>(b, 1), cap);
 }
 
+// stream-ordered scratch allocation that is released on every exit path
+struct ScratchBuf {
+    void* p = nullptr;
+    cudaStream_t st = nullptr;
+    ScratchBuf() = default;
+    ScratchBuf(const ScratchBuf&) = delete;
+    ScratchBuf& operator=(const ScratchBuf&) = delete;
+    ~ScratchBuf() { if (p) cudaFreeAsync(p, st); }
+    void alloc(size_t bytes, cudaStream_t s) {
+        st = s;
+        const cudaError_t e = cudaMallocAsync(&p, bytes ? bytes : 1, s);
+        if (e != cudaSuccess) { p = nullptr; throw Err(TTCR_B200_ERR_CUDA, std::string("cudaMallocAsync: ") + cudaGetErrorString(e)); }
+    }
+    template <typename U> U* as() const { return static_cast<U*>(p); }
+};
+
 struct GridBase {
     virtual ~GridBase() {}
     virtual void set_slowness(const void* s, size_t n, int order) = 0;
@@ -293,12 +309,13 @@ class Grid final : public GridBase {
             CK(cudaMemcpyAsync(d_rx, h_rx, 3 * nrx * sizeof(T), cudaMemcpyHostToDevice, s.stream));
             T* d_out = d_rx + 3 * nrx;
             const unsigned rp_blocks = (unsigned)((nrx + 63) / 64);
-            int* d_rn = nullptr;
-            unsigned long long* d_off = nullptr;
+            ScratchBuf b_rn, b_off, b_xyz;
             if (want_rays) {   // counts and offsets of the ray points
-                CK(cudaMallocAsync(&d_rn, nrx * sizeof(int), s.stream));
-                CK(cudaMallocAsync(&d_off, nrx * sizeof(unsigned long long), s.stream));
+                b_rn.alloc(nrx * sizeof(int), s.stream);
+                b_off.alloc(nrx * sizeof(unsigned long long), s.stream);
             }
+            int* const d_rn = b_rn.as<int>();
+            unsigned long long* const d_off = b_off.as<unsigned long long>();
             if (walk) {
                 // Grid3D.h:493-501 with tt_from_rp: traveltimes integrated along the raypaths (raypath.cuh)
                 k_tt_from_rp<T><<<rp_blocks, 64, 0, s.stream>>>(g_, d_, s.tt[0], slo_[0], s.d_pts, s.d_pts + 3 * ntx, (int)ntx, d_rx, (int)nrx,
@@ -316,7 +333,6 @@ class Grid final : public GridBase {
                 const T* st = h_rx + 4 * nrx;
                 for (size_t n = 0; n < nrx; ++n) {
                     if (st[n] == T(0)) continue;
-                    if (want_rays) { cudaFreeAsync(d_rn, s.stream); cudaFreeAsync(d_off, s.stream); }
                     std::ostringstream msg;
                     if (st[n] == T(1))
                         msg << "Error while computing raypaths: going outside grid \n                Rx: " << vrx[3 * n] << " " << vrx[3 * n + 1] << " "
@@ -332,17 +348,14 @@ class Grid final : public GridBase {
                 std::vector<unsigned long long> off(nrx);
                 unsigned long long total = 0;
                 for (size_t n = 0; n < nrx; ++n) { off[n] = total; total += (unsigned long long)rn[n]; npts[n] = (size_t)rn[n]; }
-                T* d_xyz = nullptr;
-                CK(cudaMallocAsync(&d_xyz, std::max<size_t>(1, 3 * total) * sizeof(T), s.stream));
+                b_xyz.alloc(3 * total * sizeof(T), s.stream);
+                T* const d_xyz = b_xyz.as<T>();
                 CK(cudaMemcpyAsync(d_off, off.data(), nrx * sizeof(unsigned long long), cudaMemcpyHostToDevice, s.stream));
                 k_tt_from_rp<T><<<rp_blocks, 64, 0, s.stream>>>(g_, d_, s.tt[0], slo_[0], s.d_pts, s.d_pts + 3 * ntx, (int)ntx, d_rx, (int)nrx,
                                                                 d_out, d_out + nrx, d_rn, d_off, d_xyz);
                 CK(cudaGetLastError());
                 s.rays.resize(3 * total);
                 CK(cudaMemcpyAsync(s.rays.data(), d_xyz, 3 * total * sizeof(T), cudaMemcpyDeviceToHost, s.stream));
-                CK(cudaFreeAsync(d_xyz, s.stream));
-                CK(cudaFreeAsync(d_rn, s.stream));
-                CK(cudaFreeAsync(d_off, s.stream));
                 CK(cudaStreamSynchronize(s.stream));
                 if (translate_)   // Grid3D.h:578-584: r_data += origin
                     for (size_t n = 0; n < s.rays.size(); n += 3) { s.rays[n] += origin_[0]; s.rays[n + 1] += origin_[1]; s.rays[n + 2] += origin_[2]; }
