@@ -964,6 +964,8 @@ inline int tile5_sweep<float>(TileState& s, Tile5State& s5, const TileOptions& o
     // <compute warps, planes per thread, steps per TMA chunk, ring slots, rows per U ring, ring groups>
     if (o.rows >= 2) return tile5_launch<4, 2, 2, 3, 8, 4>(s, s5, o, sm_count, w, d, tt, slo, frozen, fb, dx, d_change, st);
     if (o.warps <= 4) return tile5_launch<4, 1, 4, 4, 8, 1>(s, s5, o, sm_count, w, d, tt, slo, frozen, fb, dx, d_change, st);
+    // 6 compute warps + importer + loader = 8 warps: two per scheduler, the helpers paired with one compute warp each
+    if (o.warps == 6) return tile5_launch<6, 1, 4, 5, 4, 2>(s, s5, o, sm_count, w, d, tt, slo, frozen, fb, dx, d_change, st);
     if (o.depth >= 16) return tile5_launch<8, 1, 4, 4, 8, 2>(s, s5, o, sm_count, w, d, tt, slo, frozen, fb, dx, d_change, st);
     return tile5_launch<8, 1, 4, 5, 4, 2>(s, s5, o, sm_count, w, d, tt, slo, frozen, fb, dx, d_change, st);
 }
