@@ -6,7 +6,8 @@ Run in the container where /root/reference is mounted:
 
 Every file holds the inputs (grid, slowness, sources, receivers) and what the reference's own
 Grid3Drnfs / Grid3Drcfs (through oracle/_ref/libttcr_ref.so) produced for them: the full
-traveltime field, receiver traveltimes, niter / niterw.  The two `ref_*` cases use the
+traveltime field, receiver traveltimes, niter / niterw; tests/golden/rays/ holds the reference's raypaths and the
+traveltimes integrated along them for some of the cases (`--rays-only` regenerates just those).  The two `ref_*` cases use the
 reference's own test fixtures (tests/files/gradient_medium.vtr, layers_medium.vtr, src.dat,
 rcv.dat) and also store the analytic solution at the receivers
 (sol_analytique_*_tt.vtr), so the reference's acceptance criterion (mean relative error
@@ -110,8 +111,53 @@ def synthetic():
                      cell_slowness=cell, src=src, rcv=rcv, weno=weno, eps=1e-5, maxit=50, translate=(org != 0.0), **r)
 
 
+RAY_CASES = ("syn_het21_offnode_w_float64", "syn_het21_offnode_f_float32", "syn_het_ragged_f_float64", "syn_het_ragged_w_float32",
+             "syn_cells_ragged_w_float64", "syn_cells_ragged_f_float32", "syn_translate_w_float64")
+
+
+def raypath_case(base):
+    g = dict(np.load(os.path.join(OUT, base + ".npz")))
+    x, y, z = g["x"], g["y"], g["z"]
+    dtype = g["tt_grid"].dtype
+    rcv = g["rcv"]
+    # receivers on the faces of the grid are left out, and so are cases with a source point on a face (the reference's own
+    # gradient_medium / src.dat fixture: source on the corner; syn_het_multitx: one Tx on z max): the reference's walk reads
+    # out of bounds there and dies with SIGSEGV (the CUDA path and the restatement clamp their indices instead)
+    inside = np.all((rcv > [x[0], y[0], z[0]]) & (rcv < [x[-1], y[-1], z[-1]]), axis=1)
+    rcv = rcv[inside]
+    dx = float(np.asarray(x, dtype=dtype)[1] - np.asarray(x, dtype=dtype)[0])
+    ref = O.RefGrid(x.size - 1, y.size - 1, z.size - 1, dx, float(x[0]), float(y[0]), float(z[0]), eps=float(g["eps"]),
+                    maxit=int(g["maxit"]), weno=bool(g["weno"]), cell_slowness=bool(g["cell_slowness"]), dtype=dtype,
+                    translate_grid=bool(g.get("translate", False)))
+    ref.set_slowness(O.to_cxx(g["slowness"]))
+    tt, rays = ref.raytrace_rays(g["src"][:, 1:4], g["src"][:, 0], rcv)
+    ref.close()
+    npts = np.array([len(r) for r in rays], dtype=np.int64)
+    out = os.path.join(OUT, "rays")
+    os.makedirs(out, exist_ok=True)
+    path = os.path.join(out, base + ".npz")
+    np.savez_compressed(path, base=base, rcv=rcv, rp_tt=tt.astype(dtype), rp_npts=npts, rp_xyz=np.vstack(rays))
+    print(f"rays/{base}: {len(rays)} rays, {int(npts.sum())} points, {os.path.getsize(path) / 1024:.0f} KiB", flush=True)
+
+
+def raypaths():
+    """tests/golden/rays/<case>.npz: what the reference's rays overload (Grid3D::raytrace(Tx,t0,Rx,tt,r_data,threadNo),
+    i.e. Grid3Drn::getRaypath per receiver) returns for some of the cases above: traveltimes along the rays, points per
+    ray and the points.  One subprocess per case: a case the reference cannot walk kills only its own process."""
+    import subprocess
+    for base in RAY_CASES:
+        rc = subprocess.run([sys.executable, os.path.abspath(__file__), "--ray-case", base]).returncode
+        if rc:
+            print(f"rays/{base}: the reference died (rc {rc}); no fixture written", flush=True)
+
+
 if __name__ == "__main__":
     if not O.have_ref():
         sys.exit("oracle/_ref/libttcr_ref.so missing: run `make -C oracle` where /root/reference exists")
-    reference_fixtures()
-    synthetic()
+    if "--ray-case" in sys.argv:
+        raypath_case(sys.argv[sys.argv.index("--ray-case") + 1])
+        sys.exit(0)
+    if "--rays-only" not in sys.argv:
+        reference_fixtures()
+        synthetic()
+    raypaths()

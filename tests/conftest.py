@@ -32,6 +32,20 @@ def load_golden(name):
     return d
 
 
+def golden_ray_names():
+    return sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "rays", "*.npz")))
+
+
+def load_golden_rays(name):
+    """the reference's raypaths for golden case `name` (oracle/make_golden.py::raypath_case): receivers, traveltimes along
+    the rays, and the rays as a list of (npts, 3) arrays"""
+    with np.load(os.path.join(GOLDEN_DIR, "rays", name + ".npz")) as f:
+        d = {k: f[k] for k in f.files}
+    ends = np.cumsum(d["rp_npts"])
+    d["rays"] = [d["rp_xyz"][e - n:e] for n, e in zip(d["rp_npts"], ends)]
+    return d
+
+
 def has_cuda():
     try:
         import torch

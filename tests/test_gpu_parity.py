@@ -6,7 +6,7 @@
 import numpy as np
 import pytest
 
-from conftest import golden_names, load_golden
+from conftest import golden_names, load_golden, golden_ray_names, load_golden_rays
 
 pytestmark = pytest.mark.gpu
 
@@ -288,3 +288,26 @@ def test_raytrace_sources_matches_single_solves(n_threads):
         assert tuple(its[i]) == g1.get_niter()
     tt0, its0 = g.raytrace_sources(np.zeros((0, 3)), rcv)
     assert tt0.shape == (0, 9) and its0.shape == (0, 2)
+
+
+@pytest.mark.parametrize("name", golden_ray_names())
+def test_golden_raypaths(name):
+    """return_rays against the raypaths the UNMODIFIED reference produced (tests/golden/rays, oracle/make_golden.py): fp64
+    fields are bit-identical to the reference's, so traveltimes along the rays and every ray point are too (translated grid
+    included); fp32 fields differ in the last bits, so the walk may cross a plane elsewhere: traveltimes within 2e-3."""
+    g = load_golden(name)
+    r = load_golden_rays(name)
+    grid = make_grid(g, None)
+    tt, rays = grid.raytrace(g["src"], r["rcv"], g["slowness"], aggregate_src=True, return_rays=True)
+    assert len(rays) == len(r["rays"])
+    if g["dtype"] == np.float64:
+        assert np.array_equal(tt, r["rp_tt"])
+        for a, b in zip(rays, r["rays"]):
+            assert a.shape == b.shape and np.array_equal(a, b)
+    else:
+        assert np.max(np.abs(tt - r["rp_tt"]) / r["rp_tt"]) < 2e-3
+        for a, b in zip(rays, r["rays"]):
+            assert np.array_equal(a[0], b[0]) and np.array_equal(a[-1], b[-1])   # receiver first, source point last
+    # tt_from_rp = 1 without rays (Grid3D.h:493-501) integrates along the same paths
+    grid.set_traveltime_from_raypath(True)
+    assert np.array_equal(grid.raytrace(g["src"], r["rcv"], aggregate_src=True), tt)

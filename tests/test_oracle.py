@@ -7,7 +7,7 @@ oracle/_ref) -- and the live reference when oracle/_ref is present.
 import numpy as np
 import pytest
 
-from conftest import golden_names, load_golden
+from conftest import golden_names, load_golden, golden_ray_names, load_golden_rays
 
 
 def _run_oracle(O, g, order=0):
@@ -146,3 +146,23 @@ def test_raypath_restatement_is_bit_identical_to_reference(oracle, dtype):
             assert a.shape == b.shape and np.array_equal(a, b)
         assert r[-1].shape == (1, 3)      # a receiver on the source: the ray is that point alone
         assert min(len(a) for a in r[:-1]) >= 2
+
+
+@pytest.mark.parametrize("name", golden_ray_names())
+def test_raypath_restatement_matches_golden_rays(oracle, name):
+    """the committed raypaths of the reference (tests/golden/rays, Grid3D::raytrace with r_data): the restatement walks the
+    reference's golden field and returns the same traveltimes and the same points, bit for bit, in double and in float"""
+    g = load_golden(name)
+    r = load_golden_rays(name)
+    if g["translate"]:
+        pytest.skip("origin translation is the library's business (GPU test), not the restatement's")
+    dtype = g["dtype"]
+    x, y, z = g["x"], g["y"], g["z"]
+    dx = float(np.asarray(x, dtype=dtype)[1] - np.asarray(x, dtype=dtype)[0])
+    s_node = g["node_slowness"] if g["cell_slowness"] else g["slowness"]
+    tt, rays = oracle.raypaths(x.size - 1, y.size - 1, z.size - 1, dx, oracle.to_cxx(g["tt_grid"]), oracle.to_cxx(s_node),
+                               g["src"][:, 1:4], g["src"][:, 0], r["rcv"], float(x[0]), float(y[0]), float(z[0]), dtype=dtype)
+    assert np.array_equal(tt, r["rp_tt"])
+    assert [len(a) for a in rays] == r["rp_npts"].tolist()
+    for a, b in zip(rays, r["rays"]):
+        assert np.array_equal(a, b)
