@@ -962,6 +962,9 @@ inline int tile5_sweep<float>(TileState& s, Tile5State& s5, const TileOptions& o
                               const Dims& d, float* tt, const float* slo, const uint32_t* frozen, const FrozenBox& fb, float dx,
                               double* d_change, cudaStream_t st) {
     // <compute warps, planes per thread, steps per TMA chunk, ring slots, rows per U ring, ring groups>
+    // 16-plane tiles (8 warps x 2 planes): half as many hops along u, 8 independent updates per thread and step
+    if (o.rows >= 2 && o.warps >= 8 && o.depth >= 16) return tile5_launch<8, 2, 4, 2, 4, 4>(s, s5, o, sm_count, w, d, tt, slo, frozen, fb, dx, d_change, st);
+    if (o.rows >= 2 && o.warps >= 8) return tile5_launch<8, 2, 2, 3, 8, 4>(s, s5, o, sm_count, w, d, tt, slo, frozen, fb, dx, d_change, st);
     if (o.rows >= 2) return tile5_launch<4, 2, 2, 3, 8, 4>(s, s5, o, sm_count, w, d, tt, slo, frozen, fb, dx, d_change, st);
     if (o.warps <= 4) return tile5_launch<4, 1, 4, 4, 8, 1>(s, s5, o, sm_count, w, d, tt, slo, frozen, fb, dx, d_change, st);
     // 6 compute warps + importer + loader = 8 warps: two per scheduler, the helpers paired with one compute warp each

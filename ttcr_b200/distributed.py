@@ -70,7 +70,15 @@ def raytrace_sharded(grid, sources, rcv, slowness=None, t0=None):
     distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
     world = dist.get_world_size() if distributed else 1
     rank = dist.get_rank() if distributed else 0
-    if slowness is not None or distributed:
+    if distributed:
+        # rank 0 decides whether a model travels (None there = the model of an earlier call is still resident everywhere)
+        use_cuda = dist.get_backend() == "nccl"
+        flag = torch.tensor([0 if slowness is None else 1], dtype=torch.int32,
+                            device=torch.device("cuda", torch.cuda.current_device()) if use_cuda else torch.device("cpu"))
+        dist.broadcast(flag, src=0)
+        if int(flag.item()):
+            broadcast_slowness(grid, slowness)
+    elif slowness is not None:
         broadcast_slowness(grid, slowness)
     mine = shard_sources(n, world, rank)
     tt_local = np.zeros((len(mine), m))
