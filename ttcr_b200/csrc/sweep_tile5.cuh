@@ -691,15 +691,10 @@ __global__ void __launch_bounds__((NU + 2) * 32, (NU <= 4 ? 2 : 1)) k_sweep_patc
 #if TTCR_T5_STEP_TRACE
                 if (tr) tr[1] = TTCR_T5_CLOCK();
 #endif
-                // ---- (4) old values of the NEXT step (they do not depend on anybody: the loads overlap the arithmetic)
-                float4 jn[R], sn[R], un;
-                float hn[R];
-                {
-                    const bool first = ((sb + 1) & (C - 1)) == 0;   // the next step opens a chunk
-                    oT = first ? oTc : oT + (unsigned)DRT;
-                    oS = first ? oSc : oS + (unsigned)DRS;
-                    load_old(oT, oS, jn, hn, sn, un);
-                }
+                // What sits between the arrival of the neighbours' words and the hand-off of this step's last plane is the
+                // sweep's critical path (the hop from warp to warp, 1535 times per sweep): only the update itself is left
+                // there.  The loads of the NEXT step's old values, the stores of this step's results and the change sum
+                // come after the hand-off, in the shadow of the next wait.
                 float4 um = make_float4(__uint_as_float(xa.x), __uint_as_float(xa.z), __uint_as_float(xb.x), __uint_as_float(xb.z));
                 if (!need_u) um = make_float4(MAXV, MAXV, MAXV, MAXV);
 #pragma unroll
@@ -710,8 +705,9 @@ __global__ void __launch_bounds__((NU + 2) * 32, (NU <= 4 ? 2 : 1)) k_sweep_patc
 #if TTCR_T5_STEP_TRACE
                 if (tr) tr[2] = TTCR_T5_CLOCK();
 #endif
-                // ---- (5) update, last plane first (plane r reads the previous-step result of plane r-1); branch free
-                float4 nlast;
+                // ---- (4) update, last plane first (plane r reads the previous-step result of plane r-1); branch free
+                float4 nn[R], oo[R];
+                int chg[R];
 #pragma unroll
                 for (int r = R - 1; r >= 0; --r) {
                     float4 upv = (r == R - 1) ? up : jp[r + 1 < R ? r + 1 : r];
@@ -723,36 +719,45 @@ __global__ void __launch_bounds__((NU + 2) * 32, (NU <= 4 ? 2 : 1)) k_sweep_patc
                     const float t2 = godunov(tmin(tp.y, j.w), tmin(tp.z, j.z), tmin(umv.z, upv.z), s.z * dx);
                     const float t3 = godunov(tmin(tp.z, h[r]), tmin(tp.w, j.w), tmin(umv.w, upv.w), s.w * dx);
                     const bool c0 = t0 < o.x, c1 = t1 < o.y, c2 = t2 < o.z, c3 = t3 < o.w;
-                    float* const dst = tt + (e0[r] + (long long)(a - r) * w.sm);
                     float4 n;
                     n.x = c0 ? t0 : o.x; n.y = c1 ? t1 : o.y; n.z = c2 ? t2 : o.z; n.w = c3 ? t3 : o.w;
-                    const int ch = (c0 || c1 || c2 || c3) ? 1 : 0;
-                    if (RK) stg_f4_stream_if(dst, n.w, n.z, n.y, n.x, ch); else stg_f4_stream_if(dst, n.x, n.y, n.z, n.w, ch);
-                    acc += ((o.x - n.x) + (o.y - n.y)) + ((o.z - n.z) + (o.w - n.w));
+                    chg[r] = (c0 || c1 || c2 || c3) ? 1 : 0;
+                    nn[r] = n; oo[r] = o;
+                    if (r == R - 1) {
+                        // ---- (5) last plane of the patch -> warp wu+1 (shared ring) / tile U+1 (global mailbox); predicated
+                        const int row = a - (R - 1);
+                        const bool inr = (unsigned)row < (unsigned)ulim;
+                        const unsigned ao = a_uout + (unsigned)(row & (DU - 1)) * 1024;
+                        const unsigned tg = (unsigned)(row + 1);
+                        sts_u4_if(ao, __float_as_uint(n.x), tg, __float_as_uint(n.y), tg, inr && !last_w);
+                        sts_u4_if(ao + 512, __float_as_uint(n.z), tg, __float_as_uint(n.w), tg, inr && !last_w);
+                        const int og = (inr && last_w && has_down) ? 1 : 0;
+                        st_mail2_if(mu_out + (long long)row * 128, tag_g, n.x, n.y, og);
+                        st_mail2_if(mu_out + (long long)row * 128 + 64, tag_g, n.z, n.w, og);
+                    }
                     // lane v0+127 of this plane -> tile V+1
                     st_mail_if(mv_out + (long long)(a - r) * PU + r, tag_g, n.w, mail_v_out);
-                    if (r == R - 1) nlast = n;
                     tprev[r] = n;
                     told[r] = j;
-                }
-                // ---- (6) last plane of the patch -> warp wu+1 (shared ring) / tile U+1 (global mailbox); predicated, no branch
-                {
-                    const int row = a - (R - 1);
-                    const bool inr = (unsigned)row < (unsigned)ulim;
-                    const unsigned ao = a_uout + (unsigned)(row & (DU - 1)) * 1024;
-                    const unsigned tg = (unsigned)(row + 1);
-                    sts_u4_if(ao, __float_as_uint(nlast.x), tg, __float_as_uint(nlast.y), tg, inr && !last_w);
-                    sts_u4_if(ao + 512, __float_as_uint(nlast.z), tg, __float_as_uint(nlast.w), tg, inr && !last_w);
-                    const int og = (inr && last_w && has_down) ? 1 : 0;
-                    st_mail2_if(mu_out + (long long)row * 128, tag_g, nlast.x, nlast.y, og);
-                    st_mail2_if(mu_out + (long long)row * 128 + 64, tag_g, nlast.z, nlast.w, og);
                 }
 #if TTCR_T5_STEP_TRACE
                 if (tr) tr[3] = TTCR_T5_CLOCK();
 #endif
+                // ---- (6) old values of the NEXT step (they do not depend on anybody)
+                {
+                    const bool first = ((sb + 1) & (C - 1)) == 0;   // the next step opens a chunk
+                    oT = first ? oTc : oT + (unsigned)DRT;
+                    oS = first ? oSc : oS + (unsigned)DRS;
+                    load_old(oT, oS, jp, h, sl, up);
+                }
+                // ---- (7) results to the field, change sum
 #pragma unroll
-                for (int r = 0; r < R; ++r) { jp[r] = jn[r]; h[r] = hn[r]; sl[r] = sn[r]; }
-                up = un;
+                for (int r = 0; r < R; ++r) {
+                    float* const dst = tt + (e0[r] + (long long)(a - r) * w.sm);
+                    const float4 n = nn[r], o = oo[r];
+                    if (RK) stg_f4_stream_if(dst, n.w, n.z, n.y, n.x, chg[r]); else stg_f4_stream_if(dst, n.x, n.y, n.z, n.w, chg[r]);
+                    acc += ((o.x - n.x) + (o.y - n.y)) + ((o.z - n.z) + (o.w - n.w));
+                }
             };
             for (int a = 0; a < nsteps_w && !dead_u; a += 2) {   // nsteps_w is a multiple of C, hence even
                 step(a);
