@@ -67,6 +67,7 @@ struct Tile5Params {
     int trace_a0, trace_tile;   // per-step clocks: first step and tile of the window (debug)
     int* dbg;                   // [tile][NU + 2][16]: what every warp was waiting for when a march was given up
     int pf_chunks;              // L2 prefetch distance of the loader, in chunks (0 = off)
+    int perm;                   // 1: the warps that share a scheduler with a helper warp come first in the chain
 };
 
 constexpr int t5_round128(int x) { return (x + 127) / 128 * 128; }
@@ -450,7 +451,11 @@ __global__ void __launch_bounds__((NU + 2) * 32, (NU <= 4 ? 2 : 1)) k_sweep_patc
             __syncwarp();
         } else {
             // ================= compute warps ==============================================================
-            const int wu = warp;
+            // Position in the tile's chain of warps.  Warps 0,4 and 1,5 share their schedulers with the importer and the
+            // loader (warp id mod 4) and are the slower ones; a slow warp makes every warp ABOVE it run ahead to the end
+            // of its ring (latency through the tile), while warps below a slow one simply follow one step behind.  With
+            // `perm` the four slower warps take the first four positions.
+            const int wu = (NU == 8 && p.perm) ? ((warp & 1) | ((warp & 2) << 1) | ((warp & 4) >> 1)) : warp;
             const int u0w = u0 + wu * R;                       // first plane of this warp
             const int ulast = w.nu - 1;
             const bool edge = u0w + R > ulast;                 // some (u+1) plane of the patch does not exist
@@ -860,6 +865,8 @@ inline int tile5_launch(TileState& s, Tile5State& s5, const TileOptions& o, int 
     }
     p.order = s5.d_order; p.partial = s5.d_partial; p.dbg = s5.d_dbg;
     p.pf_chunks = getenv("TTCR_B200_PF") ? atoi(getenv("TTCR_B200_PF")) : 0;
+    static const int perm_env = getenv("TTCR_B200_PERM") ? atoi(getenv("TTCR_B200_PERM")) : 0;
+    p.perm = perm_env;
     const int key = 5000000 + PU * 100000 + w.vlo;   // the order depends on the tile height and on where the lanes start
     if (s5.order_key != key || s5.ntiles != p.ntiles) {
         // ticket order: a linear extension of (U-1,V) < (U,V), (U,V-1) < (U,V), sorted by estimated start time
@@ -975,6 +982,10 @@ inline int tile5_sweep<float>(TileState& s, Tile5State& s5, const TileOptions& o
     // 6 compute warps + importer + loader = 8 warps: two per scheduler, the helpers paired with one compute warp each
     if (o.warps == 6) return tile5_launch<6, 1, 4, 5, 4, 2>(s, s5, o, sm_count, w, d, tt, slo, frozen, fb, dx, d_change, st);
     if (o.depth >= 16) return tile5_launch<8, 1, 4, 4, 8, 2>(s, s5, o, sm_count, w, d, tt, slo, frozen, fb, dx, d_change, st);
+    // shallower U rings: a fast warp can run at most DU steps ahead of the slower warp below it, and every step of that
+    // slack is latency on the way through the tile
+    if (o.depth == 2) return tile5_launch<8, 1, 4, 5, 2, 2>(s, s5, o, sm_count, w, d, tt, slo, frozen, fb, dx, d_change, st);
+    if (o.depth == 1) return tile5_launch<8, 1, 4, 5, 1, 2>(s, s5, o, sm_count, w, d, tt, slo, frozen, fb, dx, d_change, st);
     return tile5_launch<8, 1, 4, 5, 4, 2>(s, s5, o, sm_count, w, d, tt, slo, frozen, fb, dx, d_change, st);
 }
 
