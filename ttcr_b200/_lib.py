@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libttcr_b200.so")
+# development only: TTCR_B200_LIB points at another build of the same library (e.g. one compiled with step tracing)
+LIB_PATH = os.environ.get("TTCR_B200_LIB") or os.path.join(_HERE, "libttcr_b200.so")
 
 OK, ERR_RUNTIME, ERR_LENGTH, ERR_LOGIC, ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED = range(7)
 F64, F32 = 0, 1
