@@ -117,7 +117,7 @@ def test_plane_and_tile_kernels_agree_bitwise():
                          (5, {}), (5, {"tile_warps": 4}), (5, {"tile_urows": 2, "ctas_per_sm": 1}),
                          (1, {"plane_graph": 0, "plane_pdl": 0}), (1, {"plane_graph": 1, "plane_pdl": 0}),
                          (1, {"plane_graph": 0, "plane_pdl": 1}), (6, {}), (6, {"coop_ctas": 1}), (6, {"coop_ctas": 8}),
-                         (5, {"weno_kernel": 1}), (5, {"tile_depth": 2}), (5, {"tile_depth": 1}), (5, {"tile_warps": 6}),
+                         (5, {"weno_kernel": 1}), (5, {"tile_depth": 2}), (5, {"tile_depth": 1}), (5, {"tile_depth": 3}), (5, {"tile_warps": 6}),
                          (5, {"tile_urows": 2, "tile_depth": 16})):
         grid = Grid3d(x, y, z, cell_slowness=0, tt_from_rp=False, weno=1, dtype=np.float32)
         grid.set_option("kernel", kernel)

@@ -191,7 +191,7 @@ __device__ __noinline__ int t5_wait_words(unsigned ar, unsigned av, unsigned a_n
 
 // RJ: the sweep runs the row axis downwards, RK: the lane axis (boxes arrive in memory order).
 template <int NU, int R, int C, int NCH, int DU_, int NG, bool RJ, bool RK>
-__global__ void __launch_bounds__((NU + 2) * 32, (NU <= 4 ? 2 : 1)) k_sweep_patch(const __grid_constant__ CUtensorMap tmT,
+__global__ void __launch_bounds__((NU + 2) * 32, ((NU <= 4 || (C == 2 && R == 1)) ? 2 : 1)) k_sweep_patch(const __grid_constant__ CUtensorMap tmT,
                                                                   const __grid_constant__ CUtensorMap tmS, Tile5Params p,
                                                                   Tile5Mail mail, float* __restrict__ tt,
                                                                   const uint32_t* __restrict__ frozen, float dx) {
@@ -984,6 +984,8 @@ inline int tile5_sweep<float>(TileState& s, Tile5State& s5, const TileOptions& o
     if (o.depth >= 16) return tile5_launch<8, 1, 4, 4, 8, 2>(s, s5, o, sm_count, w, d, tt, slo, frozen, fb, dx, d_change, st);
     // shallower U rings: a fast warp can run at most DU steps ahead of the slower warp below it, and every step of that
     // slack is latency on the way through the tile
+    // two CTAs per SM with 8-plane tiles: 2-row chunks (93 KB of rings) and a register cap of 102 (launch bounds)
+    if (o.depth == 3) return tile5_launch<8, 1, 2, 3, 4, 2>(s, s5, o, sm_count, w, d, tt, slo, frozen, fb, dx, d_change, st);
     if (o.depth == 2) return tile5_launch<8, 1, 4, 5, 2, 2>(s, s5, o, sm_count, w, d, tt, slo, frozen, fb, dx, d_change, st);
     if (o.depth == 1) return tile5_launch<8, 1, 4, 5, 1, 2>(s, s5, o, sm_count, w, d, tt, slo, frozen, fb, dx, d_change, st);
     return tile5_launch<8, 1, 4, 5, 4, 2>(s, s5, o, sm_count, w, d, tt, slo, frozen, fb, dx, d_change, st);
