@@ -97,14 +97,14 @@ class RefGrid:
     """The reference's own Grid3Drnfs / Grid3Drcfs (double or float)."""
 
     def __init__(self, ncx, ncy, ncz, dx, xmin=0.0, ymin=0.0, zmin=0.0, eps=1e-5, maxit=50, weno=True,
-                 cell_slowness=False, dtype=np.float64, tt_from_rp=False, n_threads=1, translate_grid=False):
+                 cell_slowness=False, dtype=np.float64, tt_from_rp=False, n_threads=1, translate_grid=False, interp_vel=False):
         lib = _load_ref()
         self._lib = lib
         self.dtype = np.dtype(dtype)
         self.shape = (ncx + 1, ncy + 1, ncz + 1)
         self._h = lib.ttcr_ref_create(0 if self.dtype == np.float64 else 1, int(bool(cell_slowness)), ncx, ncy,
                                       ncz, dx, xmin, ymin, zmin, eps, maxit, int(bool(weno)),
-                                      int(bool(tt_from_rp)), n_threads, int(bool(translate_grid)))
+                                      int(bool(tt_from_rp)) | (2 if interp_vel else 0), n_threads, int(bool(translate_grid)))
         if not self._h:
             raise RuntimeError(lib.ttcr_ref_last_error().decode())
 
@@ -263,7 +263,8 @@ def tt_from_rp(ncx, ncy, ncz, dx, tt_flat, s_node_flat, tx, t0, rx, xmin=0.0, ym
     return out
 
 
-def raypaths(ncx, ncy, ncz, dx, tt_flat, s_node_flat, tx, t0, rx, xmin=0.0, ymin=0.0, zmin=0.0, dtype=np.float64, cap=4096):
+def raypaths(ncx, ncy, ncz, dx, tt_flat, s_node_flat, tx, t0, rx, xmin=0.0, ymin=0.0, zmin=0.0, dtype=np.float64, cap=4096,
+             interp_vel=False):
     """Grid3Drn::getRaypath (Grid3Drn.h:1339-1500) from a solved field: (traveltimes, list of (npts, 3) float64 arrays)."""
     sfx, ct = _sfx(dtype)
     lib = _load()
@@ -278,9 +279,9 @@ def raypaths(ncx, ncy, ncz, dx, tt_flat, s_node_flat, tx, t0, rx, xmin=0.0, ymin
     f = getattr(lib, "fsmo_raypaths" + sfx)
     f.restype = C.c_int
     f.argtypes = [C.c_size_t] * 3 + [ct] * 4 + [C.c_void_p] * 4 + [C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p,
-                                                                  C.c_void_p, C.c_size_t]
+                                                                  C.c_void_p, C.c_size_t, C.c_int]
     rc = f(ncx, ncy, ncz, dx, xmin, ymin, zmin, tt.ctypes.data, sl.ctypes.data, tx.ctypes.data, t0.ctypes.data, tx.shape[0],
-           rx.ctypes.data, rx.shape[0], out.ctypes.data, xyz.ctypes.data, npts.ctypes.data, cap)
+           rx.ctypes.data, rx.shape[0], out.ctypes.data, xyz.ctypes.data, npts.ctypes.data, cap, int(bool(interp_vel)))
     if rc == 1:
         raise RuntimeError("Error while computing raypaths: going outside grid")
     if rc:

@@ -407,7 +407,7 @@ static REAL FN(tt_at_)(size_t ncx, size_t ncy, size_t ncz, REAL dx, REAL xmin, R
 }
 
 static REAL FN(slow_at_)(size_t ncx, size_t ncy, size_t ncz, REAL dx, REAL xmin, REAL ymin, REAL zmin, const REAL *sl,
-                         REAL px, REAL py, REAL pz) {
+                         REAL px, REAL py, REAL pz, int pv) {
     const size_t nnx = ncx + 1, nny = ncy + 1, nnz = ncz + 1;
     const double small = 1.e-4, small2 = small * small;
     ptrdiff_t onX = -1, onY = -1, onZ = -1;
@@ -427,8 +427,11 @@ static REAL FN(slow_at_)(size_t ncx, size_t ncy, size_t ncz, REAL dx, REAL xmin,
         for (ptrdiff_t n = c - 1 < 0 ? 0 : c - 1; n <= c + 2 && n < (ptrdiff_t)nnz; ++n)
             if (FABS(pz - (zmin + n * dx)) < small2) { onZ = n; break; }
     }
-#define SN(ii, jj, kk) sl[((size_t)(kk) * nny + (size_t)(jj)) * nnx + (size_t)(ii)]
-    if (onX != -1 && onY != -1 && onZ != -1) return SN(onX, onY, onZ);
+#define SN0(ii, jj, kk) sl[((size_t)(kk) * nny + (size_t)(jj)) * nnx + (size_t)(ii)]
+/* processVel (interp_vel): the VELOCITIES of the nodes are interpolated and the result is inverted, Grid3Drn.h:2489-2669 */
+#define SN(ii, jj, kk) (pv ? (REAL)(1.0 / SN0(ii, jj, kk)) : SN0(ii, jj, kk))
+#define RET(e) do { const REAL r_ = (e); return pv ? (REAL)(1.0 / r_) : r_; } while (0)
+    if (onX != -1 && onY != -1 && onZ != -1) return SN0(onX, onY, onZ);
     const unsigned i = (unsigned)(small + (px - xmin) / dx);
     const unsigned j = (unsigned)(small + (py - ymin) / dx);
     const unsigned k = (unsigned)(small + (pz - zmin) / dx);
@@ -436,15 +439,15 @@ static REAL FN(slow_at_)(size_t ncx, size_t ncy, size_t ncz, REAL dx, REAL xmin,
     if (onX != -1 && onY != -1) {
         s[0] = SN(onX, onY, k); s[1] = SN(onX, onY, k + 1);
         x[0] = pz; x[1] = zmin + k * dx; x[2] = zmin + (k + 1) * dx;
-        return (s[0] * (x[2] - x[0]) + s[1] * (x[0] - x[1])) / (x[2] - x[1]);
+        RET((s[0] * (x[2] - x[0]) + s[1] * (x[0] - x[1])) / (x[2] - x[1]));
     } else if (onX != -1 && onZ != -1) {
         s[0] = SN(onX, j, onZ); s[1] = SN(onX, j + 1, onZ);
         x[0] = py; x[1] = ymin + j * dx; x[2] = ymin + (j + 1) * dx;
-        return (s[0] * (x[2] - x[0]) + s[1] * (x[0] - x[1])) / (x[2] - x[1]);
+        RET((s[0] * (x[2] - x[0]) + s[1] * (x[0] - x[1])) / (x[2] - x[1]));
     } else if (onY != -1 && onZ != -1) {
         s[0] = SN(i, onY, onZ); s[1] = SN(i + 1, onY, onZ);
         x[0] = px; x[1] = xmin + i * dx; x[2] = xmin + (i + 1) * dx;
-        return (s[0] * (x[2] - x[0]) + s[1] * (x[0] - x[1])) / (x[2] - x[1]);
+        RET((s[0] * (x[2] - x[0]) + s[1] * (x[0] - x[1])) / (x[2] - x[1]));
     } else if (onX != -1 || onY != -1 || onZ != -1) {
         if (onX != -1) {
             s[0] = SN(onX, j, k); s[1] = SN(onX, j, k + 1); s[2] = SN(onX, j + 1, k); s[3] = SN(onX, j + 1, k + 1);
@@ -456,9 +459,9 @@ static REAL FN(slow_at_)(size_t ncx, size_t ncy, size_t ncz, REAL dx, REAL xmin,
             s[0] = SN(i, j, onZ); s[1] = SN(i, j + 1, onZ); s[2] = SN(i + 1, j, onZ); s[3] = SN(i + 1, j + 1, onZ);
             x[0] = px; y[0] = py; x[1] = xmin + i * dx; y[1] = ymin + j * dx; x[2] = xmin + (i + 1) * dx; y[2] = ymin + (j + 1) * dx;
         }
-        return (s[0] * (x[2] - x[0]) * (y[2] - y[0]) + s[1] * (x[2] - x[0]) * (y[0] - y[1]) + s[2] * (x[0] - x[1]) * (y[2] - y[0]) +
-                s[3] * (x[0] - x[1]) * (y[0] - y[1])) /
-               ((x[2] - x[1]) * (y[2] - y[1]));
+        RET((s[0] * (x[2] - x[0]) * (y[2] - y[0]) + s[1] * (x[2] - x[0]) * (y[0] - y[1]) + s[2] * (x[0] - x[1]) * (y[2] - y[0]) +
+             s[3] * (x[0] - x[1]) * (y[0] - y[1])) /
+            ((x[2] - x[1]) * (y[2] - y[1])));
     }
     s[0] = SN(i, j, k); s[1] = SN(i, j, k + 1); s[2] = SN(i, j + 1, k); s[3] = SN(i, j + 1, k + 1);
     s[4] = SN(i + 1, j, k); s[5] = SN(i + 1, j, k + 1); s[6] = SN(i + 1, j + 1, k); s[7] = SN(i + 1, j + 1, k + 1);
@@ -466,11 +469,13 @@ static REAL FN(slow_at_)(size_t ncx, size_t ncy, size_t ncz, REAL dx, REAL xmin,
     x[1] = xmin + i * dx; y[1] = ymin + j * dx; z[1] = zmin + k * dx;
     x[2] = xmin + (i + 1) * dx; y[2] = ymin + (j + 1) * dx; z[2] = zmin + (k + 1) * dx;
 #undef SN
-    return (s[0] * (x[2] - x[0]) * (y[2] - y[0]) * (z[2] - z[0]) + s[1] * (x[2] - x[0]) * (y[2] - y[0]) * (z[0] - z[1]) +
-            s[2] * (x[2] - x[0]) * (y[0] - y[1]) * (z[2] - z[0]) + s[3] * (x[2] - x[0]) * (y[0] - y[1]) * (z[0] - z[1]) +
-            s[4] * (x[0] - x[1]) * (y[2] - y[0]) * (z[2] - z[0]) + s[5] * (x[0] - x[1]) * (y[2] - y[0]) * (z[0] - z[1]) +
-            s[6] * (x[0] - x[1]) * (y[0] - y[1]) * (z[2] - z[0]) + s[7] * (x[0] - x[1]) * (y[0] - y[1]) * (z[0] - z[1])) /
-           ((x[2] - x[1]) * (y[2] - y[1]) * (z[2] - z[1]));
+#undef SN0
+    RET((s[0] * (x[2] - x[0]) * (y[2] - y[0]) * (z[2] - z[0]) + s[1] * (x[2] - x[0]) * (y[2] - y[0]) * (z[0] - z[1]) +
+         s[2] * (x[2] - x[0]) * (y[0] - y[1]) * (z[2] - z[0]) + s[3] * (x[2] - x[0]) * (y[0] - y[1]) * (z[0] - z[1]) +
+         s[4] * (x[0] - x[1]) * (y[2] - y[0]) * (z[2] - z[0]) + s[5] * (x[0] - x[1]) * (y[2] - y[0]) * (z[0] - z[1]) +
+         s[6] * (x[0] - x[1]) * (y[0] - y[1]) * (z[2] - z[0]) + s[7] * (x[0] - x[1]) * (y[0] - y[1]) * (z[0] - z[1])) /
+        ((x[2] - x[1]) * (y[2] - y[1]) * (z[2] - z[1])));
+#undef RET
 }
 
 /* one axis of grad(): stencil points p1..p4 (first = p - off), shifted inwards at the grid faces */
@@ -492,13 +497,13 @@ static int FN(sgn_)(REAL v) { return v > 0 ? 1 : (v < 0 ? -1 : 0); }   /* boost:
  * r_data.push_back): ray r gets npts[r] points, the first `cap` of which are stored at rays + 3 * cap * r. */
 int FN(fsmo_raypaths)(size_t ncx, size_t ncy, size_t ncz, REAL dx, REAL xmin, REAL ymin, REAL zmin, const REAL *tt,
                       const REAL *sl, const REAL *tx, const REAL *t0, size_t ntx, const REAL *rx, size_t nrx, REAL *out,
-                      REAL *rays, size_t *npts, size_t cap) {
+                      REAL *rays, size_t *npts, size_t cap, int interp_vel) {
     const double small2 = 1.e-8;
     const REAL xmax = xmin + ncx * dx, ymax = ymin + ncy * dx, zmax = zmin + ncz * dx;   /* Grid3Drn ctor, :63-65 */
     const REAL k1 = 1. / 24., k2 = 9. / 8.;
     const REAL maxDist = SQRT(dx * dx + dx * dx + dx * dx);
 #define TTAT(a, b, c) FN(tt_at_)(ncx, ncy, ncz, dx, xmin, ymin, zmin, tt, a, b, c)
-#define SLAT(a, b, c) FN(slow_at_)(ncx, ncy, ncz, dx, xmin, ymin, zmin, sl, a, b, c)
+#define SLAT(a, b, c) FN(slow_at_)(ncx, ncy, ncz, dx, xmin, ymin, zmin, sl, a, b, c, interp_vel)
 #define DIST(ax, ay, az, bx, by, bz) SQRT(((ax) - (bx)) * ((ax) - (bx)) + ((ay) - (by)) * ((ay) - (by)) + ((az) - (bz)) * ((az) - (bz)))
     for (size_t r = 0; r < nrx; ++r) {
         const REAL Rx = rx[3 * r], Ry = rx[3 * r + 1], Rz = rx[3 * r + 2];
@@ -609,7 +614,7 @@ int FN(fsmo_raypaths)(size_t ncx, size_t ncy, size_t ncz, REAL dx, REAL xmin, RE
 
 int FN(fsmo_tt_from_rp)(size_t ncx, size_t ncy, size_t ncz, REAL dx, REAL xmin, REAL ymin, REAL zmin, const REAL *tt,
                         const REAL *sl, const REAL *tx, const REAL *t0, size_t ntx, const REAL *rx, size_t nrx, REAL *out) {
-    return FN(fsmo_raypaths)(ncx, ncy, ncz, dx, xmin, ymin, zmin, tt, sl, tx, t0, ntx, rx, nrx, out, NULL, NULL, 0);
+    return FN(fsmo_raypaths)(ncx, ncy, ncz, dx, xmin, ymin, zmin, tt, sl, tx, t0, ntx, rx, nrx, out, NULL, NULL, 0, 0);
 }
 
 #undef NIDX

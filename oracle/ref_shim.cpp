@@ -53,7 +53,7 @@ struct Impl : Base {
     Impl(uint32_t nx, uint32_t ny, uint32_t nz, double dx, double x0, double y0, double z0,
          double eps, int maxit, int weno, int ttrp, int nt, int translate)
         : g(new G(nx, ny, nz, T(dx), T(x0), T(y0), T(z0), T(eps), maxit, weno != 0,
-                  ttrp != 0, false, size_t(nt), translate != 0)) {}
+                  (ttrp & 1) != 0, (ttrp & 2) != 0, size_t(nt), translate != 0)) {}   // ttrp bit 1: intVel (processVel)
     ttcr::Grid3D<T, uint32_t>& base() { return *g; }
     void set_slowness(const double* s, size_t n) override {
         std::vector<T> v(n);

@@ -176,10 +176,8 @@ def test_errors_match_reference_behaviour():
         g.raytrace(np.array([[9.5, 0, 0]]), np.array([[1.0, 1, 1]]))
     with pytest.raises(ValueError, match="Thread number"):
         g.get_grid_traveltimes(3)
-    g2 = Grid3d(x, x, x, cell_slowness=0, tt_from_rp=True, interp_vel=1)
-    g2.set_slowness(np.ones((9, 9, 9)))
     with pytest.raises(NotImplementedError):
-        g2.raytrace(np.array([[1.0, 1, 1]]), np.array([[2.0, 2, 2]]))
+        g.raytrace(np.array([[1.0, 1, 1]]), np.array([[2.0, 2, 2]]), compute_M=True)
     g3 = Grid3d(x, x, x, cell_slowness=0, tt_from_rp=False)
     with pytest.raises(RuntimeError, match="slowness"):
         g3.raytrace(np.array([[1.0, 1, 1]]), np.array([[2.0, 2, 2]]))
@@ -312,3 +310,30 @@ def test_golden_raypaths(name):
     # tt_from_rp = 1 without rays (Grid3D.h:493-501) integrates along the same paths
     grid.set_traveltime_from_raypath(True)
     assert np.array_equal(grid.raytrace(g["src"], r["rcv"], aggregate_src=True), tt)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_raypaths_interp_vel_vs_oracle(oracle, dtype):
+    """interp_vel = 1 (processVel, Grid3Drn.h:2489-2669): velocities interpolated along the raypath; bit-identical to the
+    restatement (itself bit-identical to the reference, tests/test_oracle.py) on the device's own field"""
+    from ttcr_b200 import Grid3d
+    n = 29
+    x = np.linspace(0.0, 14.0, n)
+    X, Y, Z = np.meshgrid(x, x, x, indexing="ij")
+    s = ((1 + 0.3 * np.sin(0.7 * X) * np.cos(0.9 * Y)) / (1 + 0.1 * Z)).astype(dtype)
+    dx = float(x.astype(dtype)[1] - x.astype(dtype)[0])
+    rng = np.random.default_rng(4)
+    src = np.array([[3.3, 7.1, 9.9]])
+    rcv = np.vstack([rng.uniform(1.5, 12.5, (40, 3)), [[x[5], x[7], 3.3], [x[10], x[11], x[12]], [x[3], 5.5, x[9]]]])
+    res = {}
+    for iv in (0, 1):
+        g = Grid3d(x, x, x, cell_slowness=0, tt_from_rp=True, interp_vel=iv, weno=1, dtype=dtype)
+        tt = g.raytrace(src, rcv, s)
+        tt2, rays = g.raytrace(src, rcv, return_rays=True)
+        gf = oracle.to_cxx(g.get_grid_traveltimes())
+        tref, rref = oracle.raypaths(n - 1, n - 1, n - 1, dx, gf, oracle.to_cxx(s), src, 0.0, rcv, dtype=dtype, interp_vel=bool(iv))
+        assert np.array_equal(tt, tref) and np.array_equal(tt2, tref)
+        for a, b in zip(rays, rref):
+            assert np.array_equal(a, b)
+        res[iv] = tt
+    assert not np.array_equal(res[0], res[1])

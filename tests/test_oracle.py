@@ -166,3 +166,31 @@ def test_raypath_restatement_matches_golden_rays(oracle, name):
     assert [len(a) for a in rays] == r["rp_npts"].tolist()
     for a, b in zip(rays, r["rays"]):
         assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_raypath_restatement_interp_vel_bit_identical_to_reference(oracle, dtype):
+    """interp_vel = 1 (processVel, Grid3Drn.h:2489-2669): node VELOCITIES are interpolated along the raypath and inverted"""
+    O = oracle
+    if not O.have_ref():
+        pytest.skip("needs oracle/_ref (built from /root/reference)")
+    n = 29
+    x = np.linspace(0.0, 14.0, n)
+    X, Y, Z = np.meshgrid(x, x, x, indexing="ij")
+    s = ((1 + 0.3 * np.sin(0.7 * X) * np.cos(0.9 * Y)) / (1 + 0.1 * Z)).astype(dtype)
+    dx = float(x.astype(dtype)[1] - x.astype(dtype)[0])
+    rng = np.random.default_rng(4)
+    src = np.array([[3.3, 7.1, 9.9]])
+    rcv = np.vstack([rng.uniform(1.5, 12.5, (40, 3)), [[x[5], x[7], 3.3], [x[10], x[11], x[12]], [x[3], 5.5, x[9]]]])
+    out = {}
+    for iv in (False, True):
+        g = O.RefGrid(n - 1, n - 1, n - 1, dx, weno=True, dtype=dtype, tt_from_rp=True, interp_vel=iv)
+        g.set_slowness(O.to_cxx(s))
+        tref, rref = g.raytrace_rays(src, 0.0, rcv)
+        t, r = O.raypaths(n - 1, n - 1, n - 1, dx, g.get_tt(), O.to_cxx(s), src, 0.0, rcv, dtype=dtype, interp_vel=iv)
+        g.close()
+        assert np.array_equal(t.astype(np.float64), tref)
+        for a, b in zip(r, rref):
+            assert np.array_equal(a, b)
+        out[iv] = t
+    assert not np.array_equal(out[False], out[True])     # the option does change the traveltimes

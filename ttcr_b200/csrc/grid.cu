@@ -295,10 +295,6 @@ class Grid final : public GridBase {
         vrx.assign((const T*)rx, (const T*)rx + 3 * nrx);
         translate_pts(vrx);
         check_pts(vrx);
-        if (nrx && walk && intvel_)
-            throw Err(TTCR_B200_ERR_UNSUPPORTED,
-                      "raypaths with interp_vel=1 (slowness along the raypath from interpolated velocity, Grid3Drn.h:2489-2669) "
-                      "are not part of the B200 path; use interp_vel=0");
         ensure_pts(s, 4 * ntx + 5 * nrx);   // Tx, t0 | Rx, traveltimes, status (before the solve: it uploads Tx into this buffer)
         solve_device(s, vtx, vt0);
         s.rays.clear();
@@ -319,7 +315,7 @@ class Grid final : public GridBase {
             if (walk) {
                 // Grid3D.h:493-501 with tt_from_rp: traveltimes integrated along the raypaths (raypath.cuh)
                 k_tt_from_rp<T><<<rp_blocks, 64, 0, s.stream>>>(g_, d_, s.tt[0], slo_[0], s.d_pts, s.d_pts + 3 * ntx, (int)ntx, d_rx, (int)nrx,
-                                                                d_out, d_out + nrx, d_rn, nullptr, nullptr);
+                                                                d_out, d_out + nrx, d_rn, nullptr, nullptr, intvel_);
             } else {
                 k_interp<T><<<(unsigned)((nrx + 127) / 128), 128, 0, s.stream>>>(g_, d_, s.tt[0], d_rx, (int)nrx, d_out);
             }
@@ -352,7 +348,7 @@ class Grid final : public GridBase {
                 T* const d_xyz = b_xyz.as<T>();
                 CK(cudaMemcpyAsync(d_off, off.data(), nrx * sizeof(unsigned long long), cudaMemcpyHostToDevice, s.stream));
                 k_tt_from_rp<T><<<rp_blocks, 64, 0, s.stream>>>(g_, d_, s.tt[0], slo_[0], s.d_pts, s.d_pts + 3 * ntx, (int)ntx, d_rx, (int)nrx,
-                                                                d_out, d_out + nrx, d_rn, d_off, d_xyz);
+                                                                d_out, d_out + nrx, d_rn, d_off, d_xyz, intvel_);
                 CK(cudaGetLastError());
                 s.rays.resize(3 * total);
                 CK(cudaMemcpyAsync(s.rays.data(), d_xyz, 3 * total * sizeof(T), cudaMemcpyDeviceToHost, s.stream));

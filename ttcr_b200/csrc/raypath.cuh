@@ -75,14 +75,17 @@ __device__ __forceinline__ int rp_on_node(T p, T pmin, T dx, int nn) {
     return -1;
 }
 
-// Grid3Drn::computeSlowness(pt, true) with processVel == false
+// Grid3Drn::computeSlowness(pt, true); pv = processVel (interp_vel): the node VELOCITIES are interpolated and the result
+// inverted (Grid3Drn.h:2489-2669; 1.0 is a double literal there, so the divisions are done in double)
 template <typename T>
-__device__ T rp_slow_at(const Geom<T>& g, const Dims& d, const T* __restrict__ s_l1, T px, T py, T pz) {
+__device__ T rp_slow_at(const Geom<T>& g, const Dims& d, const T* __restrict__ s_l1, T px, T py, T pz, bool pv) {
     const double small = 1.e-4;
     const T dx = g.dx;
     const int onX = rp_on_node(px, g.xmin, dx, d.ni), onY = rp_on_node(py, g.ymin, dx, d.nj), onZ = rp_on_node(pz, g.zmin, dx, d.nk);
-    auto SN = [&](int a, int b, int c) -> T { return s_l1[d.l1(min(a, d.ni - 1), min(b, d.nj - 1), min(c, d.nk - 1))]; };
-    if (onX != -1 && onY != -1 && onZ != -1) return SN(onX, onY, onZ);
+    auto SN0 = [&](int a, int b, int c) -> T { return s_l1[d.l1(min(a, d.ni - 1), min(b, d.nj - 1), min(c, d.nk - 1))]; };
+    auto SN = [&](int a, int b, int c) -> T { const T v = SN0(a, b, c); return pv ? T(1.0 / (double)v) : v; };
+    auto RET = [&](T r) -> T { return pv ? T(1.0 / (double)r) : r; };
+    if (onX != -1 && onY != -1 && onZ != -1) return SN0(onX, onY, onZ);
     const int i = (int)(unsigned)(small + (double)((px - g.xmin) / dx));
     const int j = (int)(unsigned)(small + (double)((py - g.ymin) / dx));
     const int k = (int)(unsigned)(small + (double)((pz - g.zmin) / dx));
@@ -90,17 +93,17 @@ __device__ T rp_slow_at(const Geom<T>& g, const Dims& d, const T* __restrict__ s
     if (onX != -1 && onY != -1) {
         s[0] = SN(onX, onY, k); s[1] = SN(onX, onY, k + 1);
         x[0] = pz; x[1] = g.zmin + T(k) * dx; x[2] = g.zmin + T(k + 1) * dx;
-        return (s[0] * (x[2] - x[0]) + s[1] * (x[0] - x[1])) / (x[2] - x[1]);
+        return RET((s[0] * (x[2] - x[0]) + s[1] * (x[0] - x[1])) / (x[2] - x[1]));
     }
     if (onX != -1 && onZ != -1) {
         s[0] = SN(onX, j, onZ); s[1] = SN(onX, j + 1, onZ);
         x[0] = py; x[1] = g.ymin + T(j) * dx; x[2] = g.ymin + T(j + 1) * dx;
-        return (s[0] * (x[2] - x[0]) + s[1] * (x[0] - x[1])) / (x[2] - x[1]);
+        return RET((s[0] * (x[2] - x[0]) + s[1] * (x[0] - x[1])) / (x[2] - x[1]));
     }
     if (onY != -1 && onZ != -1) {
         s[0] = SN(i, onY, onZ); s[1] = SN(i + 1, onY, onZ);
         x[0] = px; x[1] = g.xmin + T(i) * dx; x[2] = g.xmin + T(i + 1) * dx;
-        return (s[0] * (x[2] - x[0]) + s[1] * (x[0] - x[1])) / (x[2] - x[1]);
+        return RET((s[0] * (x[2] - x[0]) + s[1] * (x[0] - x[1])) / (x[2] - x[1]));
     }
     if (onX != -1 || onY != -1 || onZ != -1) {
         if (onX != -1) {
@@ -113,20 +116,20 @@ __device__ T rp_slow_at(const Geom<T>& g, const Dims& d, const T* __restrict__ s
             s[0] = SN(i, j, onZ); s[1] = SN(i, j + 1, onZ); s[2] = SN(i + 1, j, onZ); s[3] = SN(i + 1, j + 1, onZ);
             x[0] = px; y[0] = py; x[1] = g.xmin + T(i) * dx; y[1] = g.ymin + T(j) * dx; x[2] = g.xmin + T(i + 1) * dx; y[2] = g.ymin + T(j + 1) * dx;
         }
-        return (s[0] * (x[2] - x[0]) * (y[2] - y[0]) + s[1] * (x[2] - x[0]) * (y[0] - y[1]) + s[2] * (x[0] - x[1]) * (y[2] - y[0]) +
-                s[3] * (x[0] - x[1]) * (y[0] - y[1])) /
-               ((x[2] - x[1]) * (y[2] - y[1]));
+        return RET((s[0] * (x[2] - x[0]) * (y[2] - y[0]) + s[1] * (x[2] - x[0]) * (y[0] - y[1]) + s[2] * (x[0] - x[1]) * (y[2] - y[0]) +
+                    s[3] * (x[0] - x[1]) * (y[0] - y[1])) /
+                   ((x[2] - x[1]) * (y[2] - y[1])));
     }
     s[0] = SN(i, j, k); s[1] = SN(i, j, k + 1); s[2] = SN(i, j + 1, k); s[3] = SN(i, j + 1, k + 1);
     s[4] = SN(i + 1, j, k); s[5] = SN(i + 1, j, k + 1); s[6] = SN(i + 1, j + 1, k); s[7] = SN(i + 1, j + 1, k + 1);
     x[0] = px; y[0] = py; z[0] = pz;
     x[1] = g.xmin + T(i) * dx; y[1] = g.ymin + T(j) * dx; z[1] = g.zmin + T(k) * dx;
     x[2] = g.xmin + T(i + 1) * dx; y[2] = g.ymin + T(j + 1) * dx; z[2] = g.zmin + T(k + 1) * dx;
-    return (s[0] * (x[2] - x[0]) * (y[2] - y[0]) * (z[2] - z[0]) + s[1] * (x[2] - x[0]) * (y[2] - y[0]) * (z[0] - z[1]) +
-            s[2] * (x[2] - x[0]) * (y[0] - y[1]) * (z[2] - z[0]) + s[3] * (x[2] - x[0]) * (y[0] - y[1]) * (z[0] - z[1]) +
-            s[4] * (x[0] - x[1]) * (y[2] - y[0]) * (z[2] - z[0]) + s[5] * (x[0] - x[1]) * (y[2] - y[0]) * (z[0] - z[1]) +
-            s[6] * (x[0] - x[1]) * (y[0] - y[1]) * (z[2] - z[0]) + s[7] * (x[0] - x[1]) * (y[0] - y[1]) * (z[0] - z[1])) /
-           ((x[2] - x[1]) * (y[2] - y[1]) * (z[2] - z[1]));
+    return RET((s[0] * (x[2] - x[0]) * (y[2] - y[0]) * (z[2] - z[0]) + s[1] * (x[2] - x[0]) * (y[2] - y[0]) * (z[0] - z[1]) +
+                s[2] * (x[2] - x[0]) * (y[0] - y[1]) * (z[2] - z[0]) + s[3] * (x[2] - x[0]) * (y[0] - y[1]) * (z[0] - z[1]) +
+                s[4] * (x[0] - x[1]) * (y[2] - y[0]) * (z[2] - z[0]) + s[5] * (x[0] - x[1]) * (y[2] - y[0]) * (z[0] - z[1]) +
+                s[6] * (x[0] - x[1]) * (y[0] - y[1]) * (z[2] - z[0]) + s[7] * (x[0] - x[1]) * (y[0] - y[1]) * (z[0] - z[1])) /
+               ((x[2] - x[1]) * (y[2] - y[1]) * (z[2] - z[1])));
 }
 
 // one axis of grad(): stencil points p1..p4 (first = p - off), shifted inwards at the grid faces
@@ -178,7 +181,7 @@ template <typename T>
 __global__ void k_tt_from_rp(Geom<T> g, Dims d, const T* __restrict__ tt_l1, const T* __restrict__ s_l1, const T* __restrict__ tx,
                              const T* __restrict__ t0, int ntx, const T* __restrict__ rx, int nrx, T* __restrict__ out,
                              T* __restrict__ status, int* __restrict__ ray_n, const unsigned long long* __restrict__ ray_off,
-                             T* __restrict__ ray_xyz) {
+                             T* __restrict__ ray_xyz, bool interp_vel) {
     // ray_n != nullptr: the points of the raypath are wanted too (Grid3Drn::getRaypath, Grid3Drn.h:1339-1500: the same walk
     // with r_data.push_back).  First launch with ray_xyz == nullptr counts them, the second one (ray_off = exclusive prefix
     // sum of the counts) stores them.
@@ -205,7 +208,7 @@ __global__ void k_tt_from_rp(Geom<T> g, Dims d, const T* __restrict__ tt_l1, con
     T ttr = 0.0;
     T px = Rx, py = Ry, pz = Rz;   // prev_pt
     T cx = Rx, cy = Ry, cz = Rz;   // curr_pt
-    T s1 = rp_slow_at(g, d, s_l1, cx, cy, cz), s2;
+    T s1 = rp_slow_at(g, d, s_l1, cx, cy, cz, interp_vel), s2;
     bool reached = false;
     const long long guard_max = 16ll * (g.ncx + g.ncy + g.ncz) + 1024;
     for (long long it = 0; !reached; ++it) {
@@ -228,7 +231,7 @@ __global__ void k_tt_from_rp(Geom<T> g, Dims d, const T* __restrict__ tt_l1, con
             if (ray_n) ray_n[r] = npt;
             return;
         }
-        s2 = rp_slow_at(g, d, s_l1, cx, cy, cz);
+        s2 = rp_slow_at(g, d, s_l1, cx, cy, cz, interp_vel);
         ttr += 0.5 * (s1 + s2) * rp_dist(px, py, pz, cx, cy, cz);
         s1 = s2;
         px = cx; py = cy; pz = cz;
@@ -240,15 +243,15 @@ __global__ void k_tt_from_rp(Geom<T> g, Dims d, const T* __restrict__ tt_l1, con
             if (dist < maxDist) {
                 rp_advance(g, T(Tx - cx), T(Ty - cy), T(Tz - cz), cx, cy, cz);
                 if (rp_dist(cx, cy, cz, px, py, pz) > dist || (cx == Tx && cy == Ty && cz == Tz)) {
-                    s2 = rp_slow_at(g, d, s_l1, Tx, Ty, Tz);
+                    s2 = rp_slow_at(g, d, s_l1, Tx, Ty, Tz, interp_vel);
                     ttr += t0[ns] + 0.5 * (s1 + s2) * rp_dist(px, py, pz, Tx, Ty, Tz);
                     push(Tx, Ty, Tz);
                 } else {
-                    s2 = rp_slow_at(g, d, s_l1, cx, cy, cz);
+                    s2 = rp_slow_at(g, d, s_l1, cx, cy, cz, interp_vel);
                     ttr += 0.5 * (s1 + s2) * rp_dist(px, py, pz, cx, cy, cz);
                     push(cx, cy, cz);
                     s1 = s2;
-                    s2 = rp_slow_at(g, d, s_l1, Tx, Ty, Tz);
+                    s2 = rp_slow_at(g, d, s_l1, Tx, Ty, Tz, interp_vel);
                     ttr += t0[ns] + 0.5 * (s1 + s2) * rp_dist(cx, cy, cz, Tx, Ty, Tz);
                     push(Tx, Ty, Tz);
                 }
