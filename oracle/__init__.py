@@ -288,3 +288,47 @@ def raypaths(ncx, ncy, ncz, dx, tt_flat, s_node_flat, tx, t0, rx, xmin=0.0, ymin
         raise RuntimeError("raypath did not reach a source")
     assert npts.max(initial=0) <= cap
     return out, [xyz[i, :int(n)].astype(np.float64) for i, n in enumerate(npts)]
+
+
+# ---- 2-D twin (Grid2Drnfs): oracle for SURVEY section 8 row f4, not yet built in the product ------------------------
+def solve2d(ncx, ncz, dx, dz, s_node, tx, t0=0.0, xmin=0.0, zmin=0.0, eps=1e-5, maxit=20, weno=False, rotated=False,
+            dtype=np.float64):
+    """Grid2Drnfs::raytrace restated (oracle/fsm2d_oracle.c): s_node (ncx+1, ncz+1) C order (z fastest), tx (n, 2) = (x, z).
+    Returns (traveltime field (ncx+1, ncz+1), niter, niterw)."""
+    sfx, ct = _sfx(dtype)
+    lib = _load()
+    s = np.ascontiguousarray(s_node, dtype=dtype).ravel()
+    if s.size != (ncx + 1) * (ncz + 1):
+        raise ValueError("Error: slowness vectors of incompatible size.")
+    tx = np.ascontiguousarray(np.asarray(tx, dtype=dtype).reshape(-1, 2))
+    t0 = np.ascontiguousarray(np.broadcast_to(np.asarray(t0, dtype=dtype), (tx.shape[0],)))
+    tt = np.empty(s.size, dtype=dtype)
+    ni, nw = C.c_int(), C.c_int()
+    f = getattr(lib, "fsmo2d_solve" + sfx)
+    f.restype = C.c_int
+    f.argtypes = [C.c_size_t, C.c_size_t] + [ct] * 5 + [C.c_int] * 3 + [C.c_void_p] * 3 + [C.c_size_t, C.c_void_p,
+                                                                                            C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    rc = f(ncx, ncz, dx, dz, xmin, zmin, eps, maxit, int(bool(weno)), int(bool(rotated)), s.ctypes.data, tx.ctypes.data,
+           t0.ctypes.data, tx.shape[0], tt.ctypes.data, C.byref(ni), C.byref(nw))
+    if rc:
+        raise RuntimeError("Error: Point outside grid.")
+    return tt.reshape(ncx + 1, ncz + 1), ni.value, nw.value
+
+
+def ref_solve2d(ncx, ncz, dx, dz, s_node, tx, t0=0.0, xmin=0.0, zmin=0.0, eps=1e-5, maxit=20, weno=False, rotated=False,
+                dtype=np.float64):
+    """the same solve through the UNMODIFIED reference (Grid2Drnfs<T, uint32_t, sxz<T>>, oracle/ref_shim.cpp)"""
+    lib = _load_ref()
+    dp = C.POINTER(C.c_double)
+    lib.ttcr_ref2d_solve.argtypes = [C.c_int, C.c_uint32, C.c_uint32] + [C.c_double] * 5 + [C.c_int] * 3 + [dp, dp, dp, C.c_size_t, dp,
+                                                                                                    C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    s = np.ascontiguousarray(np.asarray(s_node, dtype=dtype), dtype=np.float64).ravel()
+    tx = np.ascontiguousarray(np.asarray(tx, dtype=np.float64).reshape(-1, 2))
+    t0 = np.ascontiguousarray(np.broadcast_to(np.asarray(t0, dtype=np.float64), (tx.shape[0],)))
+    tt = np.empty(s.size)
+    ni, nw = C.c_int(), C.c_int()
+    rc = lib.ttcr_ref2d_solve(0 if np.dtype(dtype) == np.float64 else 1, ncx, ncz, dx, dz, xmin, zmin, eps, maxit, int(bool(weno)),
+                              int(bool(rotated)), _dp(s), _dp(tx), _dp(t0), tx.shape[0], _dp(tt), C.byref(ni), C.byref(nw))
+    if rc:
+        raise RuntimeError(lib.ttcr_ref_last_error().decode())
+    return tt.astype(dtype).reshape(ncx + 1, ncz + 1), ni.value, nw.value

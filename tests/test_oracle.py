@@ -194,3 +194,44 @@ def test_raypath_restatement_interp_vel_bit_identical_to_reference(oracle, dtype
             assert np.array_equal(a, b)
         out[iv] = t
     assert not np.array_equal(out[False], out[True])     # the option does change the traveltimes
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("case", ["square", "square_rotated", "xz", "weno", "weno_xz"])
+def test_2d_restatement_is_bit_identical_to_reference(oracle, dtype, case):
+    """Grid2Drnfs (oracle only so far): all five node updates, on- and off-node and multi-point
+    sources, first-order and WENO, dx == dz and dx != dz: field and iteration counts equal to the unmodified reference's"""
+    O = oracle
+    if not O.have_ref():
+        pytest.skip("needs oracle/_ref (built from /root/reference)")
+    ncx, ncz = 47, 61
+    dx = 0.5
+    dz = 0.5 if "xz" not in case else 0.3
+    rng = np.random.default_rng(21)
+    X, Z = np.meshgrid(np.arange(ncx + 1) * dx, np.arange(ncz + 1) * dz, indexing="ij")
+    s = ((1 + 0.3 * np.sin(0.5 * X) * np.cos(0.4 * Z)) / (1 + 0.05 * Z) * np.exp(0.03 * rng.standard_normal(X.shape))).astype(dtype)
+    weno = case.startswith("weno")
+    rot = case == "square_rotated"
+    for tx, t0 in (([[0.0, 0.0]], 0.0), ([[7.3, 4.9]], 0.25), ([[3 * dx, 5 * dz], [20.1, 11.7]], [0.0, 0.4]),
+                   ([[ncx * dx, ncz * dz]], 0.0)):
+        a, ni, nw = O.solve2d(ncx, ncz, dx, dz, s, tx, t0, weno=weno, rotated=rot, dtype=dtype)
+        b, ri, rw = O.ref_solve2d(ncx, ncz, dx, dz, s, tx, t0, weno=weno, rotated=rot, dtype=dtype)
+        assert (ni, nw) == (ri, rw)
+        assert np.array_equal(a, b)
+        assert np.all(np.isfinite(a)) and a.max() < 1e3
+
+
+def test_2d_restatement_homogeneous_analytic(oracle):
+    """constant slowness: the 2-D solution is s * distance; first-order FSM error a few percent of a cell, WENO smaller"""
+    n, h, sl = 101, 0.2, 0.5
+    s = np.full((n, n), sl)
+    src = [[10.0, 10.0]]
+    X, Z = np.meshgrid(np.arange(n) * h, np.arange(n) * h, indexing="ij")
+    exact = sl * np.hypot(X - 10.0, Z - 10.0)
+    m = exact > 3 * h * sl
+    errs = {}
+    for weno in (False, True):
+        t, ni, nw = oracle.solve2d(n - 1, n - 1, h, h, s, src, weno=weno)
+        errs[weno] = float(np.mean(np.abs(t[m] - exact[m]) / exact[m]))
+        assert ni >= 2 and (nw >= 2) == weno
+    assert errs[False] < 2e-2 and errs[True] < errs[False]

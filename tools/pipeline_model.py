@@ -31,6 +31,9 @@ T_MAIL = arg("--mail", 2.0)       # tile to tile through the global mailbox and 
 CTAS = arg("--ctas", 148, int)
 NU = arg("--nu", 8, int)
 LANES = 128
+LAG_U = arg("--lagu", NU + 4)      # ticket key = U * LAG_U + V * LAG_V (the kernel: NU + 4 and 128)
+LAG_V = arg("--lagv", LANES)
+T_STEP_DEP = arg("--stepdep", T_STEP)   # step of a tile that imports words (has a U or V predecessor)
 GATE = arg("--gate", 24, int)     # rows the first sweep must be ahead of the second one's loader (TMA look-ahead + publish period)
 OVERLAP = "--overlap" in sys.argv
 
@@ -39,7 +42,7 @@ nV = (N + LANES - 1) // LANES
 rows = N + LANES - 1              # march steps of a tile (sheared rows that hold a node of the tile)
 
 
-def tile_schedule(start, up_last, left_last, gate=None):
+def tile_schedule(start, up_last, left_last, gate=None, t_step=None):
     """finish times of warp 0 and of the last warp of a tile for all rows, given when the CTA is free (`start`), the last
     warp's times of tile U-1 (`up_last`), of tile V-1 (`left_last`, already shifted to this tile's rows) and an optional
     gate (earliest time per row)."""
@@ -51,6 +54,7 @@ def tile_schedule(start, up_last, left_last, gate=None):
     if gate is not None:
         t_prev = np.maximum(t_prev, gate)
     first = None
+    T_STEP = t_step if t_step is not None else globals()["T_STEP"]
     k = np.arange(rows)
     for w in range(NU):
         # t[a] = max(t[a-1], t_prev[a]) + T_STEP  ==  (a+1) T + max(start, max_{k<=a} (t_prev[k] - k T))
@@ -68,9 +72,9 @@ def run(n_sweeps):
     for s in range(n_sweeps):
         for U in range(nU):
             for V in range(nV):
-                key = U * (NU + 4) + V * LANES
+                key = U * LAG_U + V * LAG_V
                 if s == 1:
-                    key += (nU - 1 - U) * (NU + 4) + GATE + NU + 8   # after first-sweep tile (nU-1-U, V) has got that far
+                    key += (nU - 1 - U) * LAG_U + GATE + NU + 8   # after first-sweep tile (nU-1-U, V) has got that far
                 tickets.append((key, s, U, V))
     tickets.sort()
     free = [0.0] * min(CTAS, len(tickets))
@@ -97,7 +101,7 @@ def run(n_sweeps):
                 ok = idx >= 0
                 sh[ok] = b[np.minimum(idx[ok], rows - 1)]
                 gate = np.maximum(gate, sh)
-        first, t_last = tile_schedule(start, up, left, gate)
+        first, t_last = tile_schedule(start, up, left, gate, T_STEP if (up is None and left is None) else T_STEP_DEP)
         last[(s, U, V)] = t_last
         heapq.heappush(free, t_last[-1])
         busy += t_last[-1] - start
