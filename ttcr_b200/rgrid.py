@@ -415,6 +415,18 @@ class _Grid3d:
                                                rx.shape[0], out.ctypes.data, slot))
         return out
 
+    # ---- operators for inversion codes (rgrid.pyx:610-756), host side ----------------------------------
+    def compute_D(self, coord):
+        """Matrix of interpolation weights for velocity data points (csr, npts x nparams); rgrid.pyx:610-677"""
+        from .matrices import compute_D
+        return compute_D(self._x, self._y, self._z, coord, self.cell_slowness)
+
+    def compute_K(self):
+        """Smoothing matrices (second derivatives along x, y, z) on the parameter grid; rgrid.pyx:679-756"""
+        from .matrices import compute_K
+        nx, ny, nz = self.shape
+        return compute_K((nx, ny, nz), self.dx, self.dy, self.dz)
+
     # ---- files (rgrid.pyx:1314-1378; Grid3Drn.h:2696-2746) -----------------------------------------
     def to_vtk(self, fields, filename):
         """Save grid variables to ``filename + '.vtr'``: ``fields`` maps names to (nx,ny,nz) node or cell arrays."""
