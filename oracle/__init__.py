@@ -290,6 +290,20 @@ def raypaths(ncx, ncy, ncz, dx, tt_flat, s_node_flat, tx, t0, rx, xmin=0.0, ymin
     return out, [xyz[i, :int(n)].astype(np.float64) for i, n in enumerate(npts)]
 
 
+def slowness_at(ncx, ncy, ncz, dx, s_node_flat, pts, xmin=0.0, ymin=0.0, zmin=0.0, dtype=np.float64, interp_vel=False):
+    """Grid3Drn::computeSlowness (Grid3Drn.h:2451-2676) at points (n, 3); s_node_flat in the reference's x-fastest order"""
+    sfx, ct = _sfx(dtype)
+    lib = _load()
+    sl = np.ascontiguousarray(s_node_flat, dtype=dtype).ravel()
+    pts = np.ascontiguousarray(np.asarray(pts, dtype=dtype).reshape(-1, 3))
+    out = np.empty(pts.shape[0], dtype=dtype)
+    f = getattr(lib, "fsmo_slowness_at" + sfx)
+    f.restype = None
+    f.argtypes = [C.c_size_t] * 3 + [ct] * 4 + [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]
+    f(ncx, ncy, ncz, dx, xmin, ymin, zmin, sl.ctypes.data, pts.ctypes.data, pts.shape[0], int(bool(interp_vel)), out.ctypes.data)
+    return out
+
+
 # ---- 2-D twin (Grid2Drnfs): oracle for SURVEY section 8 row f4, not yet built in the product ------------------------
 def solve2d(ncx, ncz, dx, dz, s_node, tx, t0=0.0, xmin=0.0, zmin=0.0, eps=1e-5, maxit=20, weno=False, rotated=False,
             dtype=np.float64):

@@ -478,6 +478,13 @@ static REAL FN(slow_at_)(size_t ncx, size_t ncy, size_t ncz, REAL dx, REAL xmin,
 #undef RET
 }
 
+/* Grid3Drn::computeSlowness at n points (x, y, z rows); used by the tests of Grid3d.get_s0 */
+void FN(fsmo_slowness_at)(size_t ncx, size_t ncy, size_t ncz, REAL dx, REAL xmin, REAL ymin, REAL zmin, const REAL *sl,
+                          const REAL *pts, size_t n, int interp_vel, REAL *out) {
+    for (size_t r = 0; r < n; ++r)
+        out[r] = FN(slow_at_)(ncx, ncy, ncz, dx, xmin, ymin, zmin, sl, pts[3 * r], pts[3 * r + 1], pts[3 * r + 2], interp_vel);
+}
+
 /* one axis of grad(): stencil points p1..p4 (first = p - off), shifted inwards at the grid faces */
 static void FN(stencil_)(REAL p, REAL off, REAL d, REAL lo, REAL hi, REAL q[4]) {
     REAL p1 = p - off;

@@ -4,7 +4,7 @@ description of the operators, and through exactness properties of the interpolat
 import numpy as np
 import pytest
 
-from ttcr_b200.matrices import compute_D, compute_K
+from ttcr_b200.matrices import compute_D, compute_K, slowness_at
 
 
 def _grid():
@@ -69,3 +69,18 @@ def test_compute_K_matches_per_parameter_loop_and_is_exact_for_quadratics():
     assert np.allclose(K[0] @ f, 3.0) and np.allclose(K[1] @ f, -1.0) and np.allclose(K[2] @ f, 0.5)
     with pytest.raises(ValueError):
         compute_K((2, 4, 4), 1.0, 1.0, 1.0)
+
+
+@pytest.mark.parametrize("interp_vel", [False, True])
+def test_slowness_at_agrees_with_the_restatement_of_computeSlowness(oracle, interp_vel):
+    """Grid3d.get_s0's interpolation against the oracle's Grid3Drn::computeSlowness (bit-identical to the reference inside
+    the raypath tests): inside cells, on faces, edges and nodes"""
+    n = 17
+    x = np.linspace(0.0, 8.0, n)
+    rng = np.random.default_rng(3)
+    s = rng.uniform(0.3, 1.2, (n, n, n))
+    pts = np.vstack([rng.uniform(0.0, 7.99, (200, 3)), [[x[3], x[5], x[7]], [x[3], 2.2, x[7]], [x[3], 2.2, 6.1], [1.1, x[5], 6.1],
+                                                         [x[0], x[0], x[0]], [x[-1], x[-1], x[-1]], [x[-1], 3.3, 4.4]]])
+    ref = oracle.slowness_at(n - 1, n - 1, n - 1, float(x[1] - x[0]), oracle.to_cxx(s), pts, interp_vel=interp_vel)
+    got = slowness_at(x, x, x, s, pts, interp_vel=interp_vel)
+    assert np.allclose(got, ref, rtol=1e-12, atol=0)

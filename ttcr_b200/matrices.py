@@ -74,3 +74,25 @@ def compute_K(shape, dx, dy, dz):
         vals = np.tile(np.array([1., -2., 1.]), n) / (h * h)
         out.append(sp.csr_matrix((vals, (rows, cols)), shape=(n, n)))
     return tuple(out)
+
+
+def slowness_at(x, y, z, s_node, pts, interp_vel=False):
+    """Node slowness interpolated at ``pts`` (n, 3) as ``Grid3Drn::computeSlowness`` does it (ttcr/Grid3Drn.h:2451-2676):
+    trilinear between the 8 nodes of the cell int(1e-4 + (p - min) / d), of the slowness or -- ``interp_vel`` -- of the
+    velocity (then inverted).  The reference returns the node / edge / face values through separate branches; their
+    results agree with the trilinear formula to rounding, which is what ``Grid3d.get_s0`` needs."""
+    x, y, z = (np.asarray(a, dtype=np.float64) for a in (x, y, z))
+    s = np.asarray(s_node, dtype=np.float64).reshape(x.size, y.size, z.size)
+    pts = np.asarray(pts, dtype=np.float64).reshape(-1, 3)
+    f = 1.0 / s if interp_vel else s
+    dx, dy, dz = x[1] - x[0], y[1] - y[0], z[1] - z[0]
+    i = np.minimum((1.e-4 + (pts[:, 0] - x[0]) / dx).astype(np.int64), x.size - 2)
+    j = np.minimum((1.e-4 + (pts[:, 1] - y[0]) / dy).astype(np.int64), y.size - 2)
+    k = np.minimum((1.e-4 + (pts[:, 2] - z[0]) / dz).astype(np.int64), z.size - 2)
+    wx, wy, wz = (pts[:, 0] - x[i]) / dx, (pts[:, 1] - y[j]) / dy, (pts[:, 2] - z[k]) / dz
+    v = 0.0
+    for di, ax in ((0, 1 - wx), (1, wx)):
+        for dj, ay in ((0, 1 - wy), (1, wy)):
+            for dk, az in ((0, 1 - wz), (1, wz)):
+                v = v + f[i + di, j + dj, k + dk] * ax * ay * az
+    return 1.0 / v if interp_vel else v

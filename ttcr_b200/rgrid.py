@@ -427,6 +427,20 @@ class _Grid3d:
         nx, ny, nz = self.shape
         return compute_K((nx, ny, nz), self.dx, self.dy, self.dz)
 
+    def get_s0(self, hypo, slowness=None):
+        """Slowness at the source points of ``hypo`` (npts x 5: event ID, origin time, x, y, z): every row gets the
+        slowness interpolated at the FIRST point of its event (rgrid.pyx:758-826, Grid3Drn::computeSlowness)."""
+        from .matrices import slowness_at
+        hypo = np.asarray(hypo, dtype=np.float64)
+        if hypo.ndim != 2 or hypo.shape[1] != 5:
+            raise ValueError("hypo should be npts x 5")
+        if slowness is not None:
+            self.set_slowness(slowness)
+        ev = hypo[:, 0]
+        _, first, inverse = np.unique(ev, return_index=True, return_inverse=True)
+        s_first = slowness_at(self._x, self._y, self._z, self.get_slowness(), hypo[first, 2:5], bool(self.interp_vel))
+        return np.asarray(s_first)[inverse]
+
     # ---- files (rgrid.pyx:1314-1378; Grid3Drn.h:2696-2746) -----------------------------------------
     def to_vtk(self, fields, filename):
         """Save grid variables to ``filename + '.vtr'``: ``fields`` maps names to (nx,ny,nz) node or cell arrays."""
