@@ -9,7 +9,8 @@ and a tile starts when a CTA is free (tickets in the kernel's order, `ctas` pers
 Every quantity is in microseconds.  The model has no jitter and no back-pressure (ring depth); it is the optimistic
 schedule for given constants, to be compared with the measured sweep (1.16 ms at 512^3, 6.4 ms at 1024^3).
 
-usage: pipeline_model.py [N] [--step us] [--hand us] [--mail us] [--ctas n] [--nu planes] [--overlap]
+usage: pipeline_model.py [N] [--step us] [--stepdep us] [--hand us] [--mail us] [--ctas n] [--nu planes] [--lanes n]
+                         [--lagu k] [--lagv k] [--overlap]
   --overlap: the same network for two consecutive sweeps that differ in the i direction only, the second one following
              the first with the dependency of DESIGN.md section 8 item 1 (its tile (U,V) at row a needs the first sweep's
              tiles (nU-1-U, V) and (nU-1-U, V+1) to be `gate` rows further), one ticket list, same CTAs.
@@ -30,7 +31,7 @@ T_HAND = arg("--hand", 0.06)      # ring hand-off between two warps (visibility 
 T_MAIL = arg("--mail", 2.0)       # tile to tile through the global mailbox and the importer
 CTAS = arg("--ctas", 148, int)
 NU = arg("--nu", 8, int)
-LANES = 128
+LANES = arg("--lanes", 128, int)   # lanes of v per tile (128 = 4 per thread; 64 = the 2-lanes-per-thread patch of DESIGN section 8)
 LAG_U = arg("--lagu", NU + 4)      # ticket key = U * LAG_U + V * LAG_V (the kernel: NU + 4 and 128)
 LAG_V = arg("--lagv", LANES)
 T_STEP_DEP = arg("--stepdep", T_STEP)   # step of a tile that imports words (has a U or V predecessor)
