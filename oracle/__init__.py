@@ -329,20 +329,56 @@ def solve2d(ncx, ncz, dx, dz, s_node, tx, t0=0.0, xmin=0.0, zmin=0.0, eps=1e-5, 
     return tt.reshape(ncx + 1, ncz + 1), ni.value, nw.value
 
 
-def ref_solve2d(ncx, ncz, dx, dz, s_node, tx, t0=0.0, xmin=0.0, zmin=0.0, eps=1e-5, maxit=20, weno=False, rotated=False,
-                dtype=np.float64):
-    """the same solve through the UNMODIFIED reference (Grid2Drnfs<T, uint32_t, sxz<T>>, oracle/ref_shim.cpp)"""
+def cell_to_node2d(s_cell, ncx, ncz, dtype=np.float64):
+    """Grid2Drcfs::setSlowness (Grid2Drcfs.h:99-138): (ncx, ncz) cell slowness -> (ncx+1, ncz+1) node slowness"""
+    sfx, _ = _sfx(dtype)
+    lib = _load()
+    s = np.ascontiguousarray(s_cell, dtype=dtype).ravel()
+    if s.size != ncx * ncz:
+        raise ValueError("Error: slowness vectors of incompatible size.")
+    out = np.empty((ncx + 1) * (ncz + 1), dtype=dtype)
+    f = getattr(lib, "fsmo2d_cell_to_node" + sfx)
+    f.restype = None
+    f.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p]
+    f(s.ctypes.data, ncx, ncz, out.ctypes.data)
+    return out.reshape(ncx + 1, ncz + 1)
+
+
+def interp2d(ncx, ncz, dx, dz, tt, rx, xmin=0.0, zmin=0.0, dtype=np.float64):
+    """Grid2Drn::getTraveltime (Grid2Drn.h:359-415) at receivers rx (n, 2)"""
+    sfx, ct = _sfx(dtype)
+    lib = _load()
+    t = np.ascontiguousarray(tt, dtype=dtype).ravel()
+    rx = np.ascontiguousarray(np.asarray(rx, dtype=dtype).reshape(-1, 2))
+    out = np.empty(rx.shape[0], dtype=dtype)
+    f = getattr(lib, "fsmo2d_interp" + sfx)
+    f.restype = None
+    f.argtypes = [C.c_size_t, C.c_size_t] + [ct] * 4 + [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+    f(ncx, ncz, dx, dz, xmin, zmin, t.ctypes.data, rx.ctypes.data, rx.shape[0], out.ctypes.data)
+    return out
+
+
+def ref_solve2d(ncx, ncz, dx, dz, slowness, tx, t0=0.0, xmin=0.0, zmin=0.0, eps=1e-5, maxit=20, weno=False, rotated=False,
+                dtype=np.float64, cell_slowness=False, rx=None):
+    """the same solve through the UNMODIFIED reference (Grid2Drnfs / Grid2Drcfs <T, uint32_t, sxz<T>>, oracle/ref_shim.cpp);
+    returns (field, niter, niterw) or, with receivers, (field, niter, niterw, receiver times)"""
     lib = _load_ref()
     dp = C.POINTER(C.c_double)
-    lib.ttcr_ref2d_solve.argtypes = [C.c_int, C.c_uint32, C.c_uint32] + [C.c_double] * 5 + [C.c_int] * 3 + [dp, dp, dp, C.c_size_t, dp,
-                                                                                                    C.POINTER(C.c_int), C.POINTER(C.c_int)]
-    s = np.ascontiguousarray(np.asarray(s_node, dtype=dtype), dtype=np.float64).ravel()
+    lib.ttcr_ref2d_solve.argtypes = ([C.c_int, C.c_int, C.c_uint32, C.c_uint32] + [C.c_double] * 5 + [C.c_int] * 3 +
+                                     [dp, C.c_size_t, dp, dp, C.c_size_t, dp, C.c_size_t, dp, dp, C.POINTER(C.c_int), C.POINTER(C.c_int)])
+    s = np.ascontiguousarray(np.asarray(slowness, dtype=dtype), dtype=np.float64).ravel()
     tx = np.ascontiguousarray(np.asarray(tx, dtype=np.float64).reshape(-1, 2))
     t0 = np.ascontiguousarray(np.broadcast_to(np.asarray(t0, dtype=np.float64), (tx.shape[0],)))
-    tt = np.empty(s.size)
+    r = np.zeros((0, 2)) if rx is None else np.ascontiguousarray(np.asarray(rx, dtype=np.float64).reshape(-1, 2))
+    tt = np.empty((ncx + 1) * (ncz + 1))
+    ttr = np.empty(max(1, r.shape[0]))
     ni, nw = C.c_int(), C.c_int()
-    rc = lib.ttcr_ref2d_solve(0 if np.dtype(dtype) == np.float64 else 1, ncx, ncz, dx, dz, xmin, zmin, eps, maxit, int(bool(weno)),
-                              int(bool(rotated)), _dp(s), _dp(tx), _dp(t0), tx.shape[0], _dp(tt), C.byref(ni), C.byref(nw))
+    rc = lib.ttcr_ref2d_solve(0 if np.dtype(dtype) == np.float64 else 1, int(bool(cell_slowness)), ncx, ncz, dx, dz, xmin, zmin, eps,
+                              maxit, int(bool(weno)), int(bool(rotated)), _dp(s), s.size, _dp(tx), _dp(t0), tx.shape[0], _dp(r),
+                              r.shape[0], _dp(tt), _dp(ttr), C.byref(ni), C.byref(nw))
     if rc:
         raise RuntimeError(lib.ttcr_ref_last_error().decode())
-    return tt.astype(dtype).reshape(ncx + 1, ncz + 1), ni.value, nw.value
+    field = tt.astype(dtype).reshape(ncx + 1, ncz + 1)
+    if rx is None:
+        return field, ni.value, nw.value
+    return field, ni.value, nw.value, ttr[:r.shape[0]].astype(dtype)

@@ -260,6 +260,63 @@ int FN(fsmo2d_solve)(size_t ncx, size_t ncz, REAL dx, REAL dz, REAL xmin, REAL z
     return 0;
 }
 
+/* Grid2Drcfs::setSlowness, Grid2Drcfs.h:99-138: node slowness = mean of the 1 / 2 / 4 adjacent cells (cell index
+ * i * ncz + j); the order of the additions is the source's */
+void FN(fsmo2d_cell_to_node)(const REAL *s, size_t nx, size_t nz, REAL *sn) {
+    const size_t st = nz + 1;
+    sn[0] = s[0];
+    sn[nz] = s[nz - 1];
+    sn[nx * st] = s[nz * (nx - 1)];
+    sn[(nx + 1) * st - 1] = s[nx * nz - 1];
+    for (size_t j = 1; j < nz; ++j) {
+        sn[j] = 0.5 * (s[j] + s[j - 1]);
+        sn[nx * st + j] = 0.5 * (s[nz * (nx - 1) + j] + s[nz * (nx - 1) + j - 1]);
+    }
+    for (size_t i = 1; i < nx; ++i) {
+        sn[i * st] = 0.5 * (s[i * nz] + s[(i - 1) * nz]);
+        sn[i * st + nz] = 0.5 * (s[(i + 1) * nz - 1] + s[i * nz - 1]);
+    }
+    for (size_t i = 1; i < nx; ++i)
+        for (size_t j = 1; j < nz; ++j)
+            sn[i * st + j] = 0.25 * (s[i * nz + j] + s[i * nz + j - 1] + s[(i - 1) * nz + j] + s[(i - 1) * nz + j - 1]);
+}
+
+/* Grid2Drn::getTraveltime, Grid2Drn.h:359-415: bilinear, x first then z, with the on-node and on-edge cases at
+ * tolerance small = 1e-4 (getIJ, :186-189) */
+void FN(fsmo2d_interp)(size_t ncx, size_t ncz, REAL dx, REAL dz, REAL xmin, REAL zmin, const REAL *tt, const REAL *rx, size_t nrx,
+                       REAL *out) {
+    const double small = 1.e-4;
+    const size_t nnz = ncz + 1;
+    (void)ncx;
+    for (size_t r = 0; r < nrx; ++r) {
+        const REAL px = rx[2 * r], pz = rx[2 * r + 1];
+        const size_t i = (unsigned)(small + (px - xmin) / dx), j = (unsigned)(small + (pz - zmin) / dz);
+        const int onx = fabs(px - (xmin + i * dx)) < small, onz = fabs(pz - (zmin + j * dz)) < small;
+        REAL t;
+        if (onx && onz) {
+            t = tt[i * nnz + j];
+        } else if (onx) {
+            const REAL t1 = tt[i * nnz + j], t2 = tt[i * nnz + j + 1];
+            const REAL w1 = (zmin + (j + 1) * dz - pz) / dz, w2 = (pz - (zmin + j * dz)) / dz;
+            t = t1 * w1 + t2 * w2;
+        } else if (onz) {
+            const REAL t1 = tt[i * nnz + j], t2 = tt[(i + 1) * nnz + j];
+            const REAL w1 = (xmin + (i + 1) * dx - px) / dx, w2 = (px - (xmin + i * dx)) / dx;
+            t = t1 * w1 + t2 * w2;
+        } else {
+            REAL t1 = tt[i * nnz + j], t2 = tt[(i + 1) * nnz + j];
+            const REAL t3 = tt[i * nnz + j + 1], t4 = tt[(i + 1) * nnz + j + 1];
+            REAL w1 = (xmin + (i + 1) * dx - px) / dx, w2 = (px - (xmin + i * dx)) / dx;
+            t1 = t1 * w1 + t2 * w2;
+            t2 = t3 * w1 + t4 * w2;
+            w1 = (zmin + (j + 1) * dz - pz) / dz;
+            w2 = (pz - (zmin + j * dz)) / dz;
+            t = t1 * w1 + t2 * w2;
+        }
+        out[r] = t;
+    }
+}
+
 #undef N2
 #undef FN
 #undef CAT

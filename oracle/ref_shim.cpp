@@ -22,7 +22,8 @@
 
 #include "Grid3Drnfs.h"
 #include "Grid3Drcfs.h"
-#include "Grid2Drnfs.h"   // the 2-D twin: pins oracle/fsm2d_oracle.c
+#include "Grid2Drcfs.h"
+#include "Grid2Drnfs.h"   // the 2-D twins: pins oracle/fsm2d_oracle.c
 
 namespace ttcr {
 int verbose = 0;       // ttcr/ttcr_t.h:35 (extern)
@@ -151,25 +152,28 @@ int guard(F&& f) {
 
 }  // namespace
 
-// One solve of the reference's 2-D Grid2Drnfs<T, uint32_t, sxz<T>> (Grid2Drnfs.h:83-95): node slowness s ((ncx+1)(ncz+1)
-// values, z fastest), Tx points tx (ntx x 2: x, z) with origin times t0; returns the traveltime field and the iteration
-// counts.  dtype: 0 = double, 1 = float.
-template <typename T>
+// One solve of the reference's 2-D Grid2Drnfs / Grid2Drcfs <T, uint32_t, sxz<T>> (Grid2Drnfs.h:83-95, Grid2Drcfs.h:36-50):
+// slowness s at the nodes ((ncx+1)(ncz+1) values) or in the cells (ncx ncz values), z fastest; Tx points tx (ntx x 2:
+// x, z) with origin times t0; receivers rx (nrx x 2) get Grid2Drn::getTraveltime (tt_from_rp = false).  Returns the
+// traveltime field, the receiver times and the iteration counts.
+template <typename T, typename G>
 static void solve2d(uint32_t ncx, uint32_t ncz, double dx, double dz, double xmin, double zmin, double eps, int maxit, int weno,
-                    int rotated, const double* s, const double* tx, const double* t0, size_t ntx, double* tt, int* niter, int* niterw) {
+                    int rotated, const double* s, size_t ns, const double* tx, const double* t0, size_t ntx, const double* rx, size_t nrx,
+                    double* tt, double* tt_rx, int* niter, int* niterw) {
     typedef ttcr::sxz<T> S;
-    ttcr::Grid2Drnfs<T, uint32_t, S> g(ncx, ncz, T(dx), T(dz), T(xmin), T(zmin), T(eps), maxit, weno != 0, rotated != 0, false, 1);
-    const size_t N = size_t(ncx + 1) * (ncz + 1);
-    std::vector<T> v(N);
-    for (size_t i = 0; i < N; ++i) v[i] = T(s[i]);
+    G g(ncx, ncz, T(dx), T(dz), T(xmin), T(zmin), T(eps), maxit, weno != 0, rotated != 0, false, 1);
+    std::vector<T> v(ns);
+    for (size_t i = 0; i < ns; ++i) v[i] = T(s[i]);
     g.setSlowness(v);
-    std::vector<S> Tx(ntx), Rx;
+    std::vector<S> Tx(ntx), Rx(nrx);
     std::vector<T> vt0(ntx), tr;
     for (size_t i = 0; i < ntx; ++i) { Tx[i].x = T(tx[2 * i]); Tx[i].z = T(tx[2 * i + 1]); vt0[i] = T(t0[i]); }
+    for (size_t i = 0; i < nrx; ++i) { Rx[i].x = T(rx[2 * i]); Rx[i].z = T(rx[2 * i + 1]); }
     static_cast<ttcr::Grid2D<T, uint32_t, S>&>(g).raytrace(Tx, vt0, Rx, tr, 0);
+    for (size_t i = 0; i < nrx; ++i) tt_rx[i] = double(tr[i]);
     std::vector<T> f;
     g.getTT(f, 0);
-    for (size_t i = 0; i < N; ++i) tt[i] = double(f[i]);
+    for (size_t i = 0; i < f.size(); ++i) tt[i] = double(f[i]);
     *niter = g.get_niter();
     *niterw = g.get_niterw();
 }
@@ -229,12 +233,17 @@ int ttcr_ref_get_niter(void* h, int* niter, int* niterw) {
     return guard([&] { static_cast<Base*>(h)->niter(niter, niterw); });
 }
 
-int ttcr_ref2d_solve(int dtype, uint32_t ncx, uint32_t ncz, double dx, double dz, double xmin, double zmin, double eps, int maxit,
-                     int weno, int rotated, const double* s, const double* tx, const double* t0, size_t ntx, double* tt, int* niter,
-                     int* niterw) {
+int ttcr_ref2d_solve(int dtype, int cell, uint32_t ncx, uint32_t ncz, double dx, double dz, double xmin, double zmin, double eps,
+                     int maxit, int weno, int rotated, const double* s, size_t ns, const double* tx, const double* t0, size_t ntx,
+                     const double* rx, size_t nrx, double* tt, double* tt_rx, int* niter, int* niterw) {
     return guard([&] {
-        if (dtype == 0) solve2d<double>(ncx, ncz, dx, dz, xmin, zmin, eps, maxit, weno, rotated, s, tx, t0, ntx, tt, niter, niterw);
-        else solve2d<float>(ncx, ncz, dx, dz, xmin, zmin, eps, maxit, weno, rotated, s, tx, t0, ntx, tt, niter, niterw);
+#define TTCR_SOLVE2D(T, G) solve2d<T, ttcr::G<T, uint32_t, ttcr::sxz<T>>>(ncx, ncz, dx, dz, xmin, zmin, eps, maxit, weno, rotated, s, ns, \
+                                                                         tx, t0, ntx, rx, nrx, tt, tt_rx, niter, niterw)
+        if (dtype == 0 && !cell) TTCR_SOLVE2D(double, Grid2Drnfs);
+        else if (dtype == 0) TTCR_SOLVE2D(double, Grid2Drcfs);
+        else if (!cell) TTCR_SOLVE2D(float, Grid2Drnfs);
+        else TTCR_SOLVE2D(float, Grid2Drcfs);
+#undef TTCR_SOLVE2D
     });
 }
 

@@ -235,3 +235,24 @@ def test_2d_restatement_homogeneous_analytic(oracle):
         errs[weno] = float(np.mean(np.abs(t[m] - exact[m]) / exact[m]))
         assert ni >= 2 and (nw >= 2) == weno
     assert errs[False] < 2e-2 and errs[True] < errs[False]
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("weno", [False, True])
+def test_2d_cell_slowness_and_receivers_bit_identical_to_reference(oracle, dtype, weno):
+    """Grid2Drcfs: cell -> node averaging (checked through the solve: the reference does not hand the node values out) and
+    Grid2Drn::getTraveltime at receivers inside cells, on edges and on nodes"""
+    O = oracle
+    if not O.have_ref():
+        pytest.skip("needs oracle/_ref (built from /root/reference)")
+    ncx, ncz, h = 40, 33, 0.5
+    rng = np.random.default_rng(8)
+    sc = rng.uniform(0.3, 1.0, (ncx, ncz)).astype(dtype)
+    tx, t0 = [[6.2, 9.9]], 0.1
+    rx = np.vstack([np.column_stack([rng.uniform(0, ncx * h, 30), rng.uniform(0, ncz * h, 30)]),
+                    [[3 * h, 7.77], [4.44, 5 * h], [8 * h, 9 * h], [0.0, 0.0], [ncx * h - 0.2, ncz * h - 0.3]]])
+    sn = O.cell_to_node2d(sc, ncx, ncz, dtype=dtype)
+    a, ni, nw = O.solve2d(ncx, ncz, h, h, sn, tx, t0, weno=weno, dtype=dtype)
+    b, ri, rw, tr = O.ref_solve2d(ncx, ncz, h, h, sc, tx, t0, weno=weno, dtype=dtype, cell_slowness=True, rx=rx)
+    assert (ni, nw) == (ri, rw) and np.array_equal(a, b)
+    assert np.array_equal(O.interp2d(ncx, ncz, h, h, a, rx, dtype=dtype), tr)
