@@ -111,6 +111,68 @@ def synthetic():
                      cell_slowness=cell, src=src, rcv=rcv, weno=weno, eps=1e-5, maxit=50, translate=(org != 0.0), **r)
 
 
+def mt19937_64_uniform(seed, n, lo, hi):
+    """std::mt19937_64(seed) driving std::uniform_real_distribution<double>(lo, hi) as libstdc++ implements it (one
+    64-bit draw per number: generate_canonical = draw * 2^-64 in double, clamped below 1): the source positions of the
+    reference's accuracy study (tests/accuracy_grid3d.cpp:352-360)."""
+    NN, MM, MASK = 312, 156, (1 << 64) - 1
+    mt = [0] * NN
+    mt[0] = seed & MASK
+    for i in range(1, NN):
+        mt[i] = (6364136223846793005 * (mt[i - 1] ^ (mt[i - 1] >> 62)) + i) & MASK
+    idx = NN
+    out = np.empty(n)
+    for k in range(n):
+        if idx >= NN:
+            for i in range(NN):
+                x = (mt[i] & 0xFFFFFFFF80000000) | (mt[(i + 1) % NN] & 0x7FFFFFFF)
+                xa = x >> 1
+                if x & 1:
+                    xa ^= 0xB5026F5AA96619E9
+                mt[i] = mt[(i + MM) % NN] ^ xa
+            idx = 0
+        y = mt[idx]
+        idx += 1
+        y ^= (y >> 29) & 0x5555555555555555
+        y ^= (y << 17) & 0x71D67FFFEDA60000
+        y ^= (y << 37) & 0xFFF7EEE000000000
+        y ^= y >> 43
+        u = float(y) * (1.0 / 18446744073709551616.0)
+        if u >= 1.0:
+            u = np.nextafter(1.0, 0.0)
+        out[k] = u * (hi - lo) + lo
+    return out
+
+
+def accuracy_kat():
+    """tests/golden/kat/kat_constant_medium.npz: study 2 of the reference's tests/accuracy_grid3d.cpp (constant_medium.vtr,
+    100 random sources from mt19937_64(12345), receivers rcv.dat, FSM with weno3 = 1, double, eps 1e-5, nitermax 50,
+    receiver times by interpolation), run through the UNMODIFIED reference; its published result for this case is a mean
+    relative error of 0.00152022 (tests/accuracy_grid3d.csv, line "double,constant,FAST_SWEEPING,Grid3Drnfs,medium")."""
+    m = read_vtr(os.path.join(REF, "constant_medium.vtr"))
+    x, y, z = m["x"], m["y"], m["z"]
+    slowness = np.ascontiguousarray(m["point_data"]["Slowness"].reshape((x.size, y.size, z.size), order="F"))
+    rcv = np.loadtxt(os.path.join(REF, "rcv.dat"), skiprows=1)
+    src = mt19937_64_uniform(12345, 300, 0.5, 19.5).reshape(100, 3)
+    dx = float(x[1] - x[0])
+    g = O.RefGrid(x.size - 1, y.size - 1, z.size - 1, dx, float(x[0]), float(y[0]), float(z[0]), eps=1e-5, maxit=50, weno=True,
+                  cell_slowness=False, dtype=np.float64)
+    g.set_slowness(O.to_cxx(slowness))
+    tt = np.empty((100, rcv.shape[0]))
+    it = np.empty((100, 2), dtype=np.int64)
+    for n in range(100):
+        tt[n], _ = g.raytrace(src[n:n + 1], 0.0, rcv)
+        it[n] = g.niter()
+    g.close()
+    s0 = float(slowness.ravel()[0])
+    ref = s0 * np.sqrt(((rcv[None, :, :] - src[:, None, :]) ** 2).sum(axis=2))
+    err = float(np.mean(np.abs((ref - tt) / ref)[ref != 0.0]))
+    os.makedirs(os.path.join(OUT, "kat"), exist_ok=True)
+    save(os.path.join("kat", "kat_constant_medium"), x=x, y=y, z=z, slowness=np.float64(s0), src=src, rcv=rcv, tt_rcv=tt, iters=it, error=err,
+         published_error=0.00152022)
+    print(f"kat_constant_medium: mean relative error {err:.8f} (published 0.00152022), niterw {it[:, 1].min()}..{it[:, 1].max()}")
+
+
 RAY_CASES = ("syn_het21_offnode_w_float64", "syn_het21_offnode_f_float32", "syn_het_ragged_f_float64", "syn_het_ragged_w_float32",
              "syn_cells_ragged_w_float64", "syn_cells_ragged_f_float32", "syn_translate_w_float64")
 
@@ -157,7 +219,11 @@ if __name__ == "__main__":
     if "--ray-case" in sys.argv:
         raypath_case(sys.argv[sys.argv.index("--ray-case") + 1])
         sys.exit(0)
+    if "--kat-only" in sys.argv:
+        accuracy_kat()
+        sys.exit(0)
     if "--rays-only" not in sys.argv:
         reference_fixtures()
         synthetic()
+        accuracy_kat()
     raypaths()

@@ -337,3 +337,22 @@ def test_raypaths_interp_vel_vs_oracle(oracle, dtype):
             assert np.array_equal(a, b)
         res[iv] = tt
     assert not np.array_equal(res[0], res[1])
+
+
+def test_accuracy_study_constant_model_random_sources():
+    """study 2 of the reference's tests/accuracy_grid3d.cpp (constant_medium.vtr, 100 sources from mt19937_64(12345), the
+    441 receivers of rcv.dat, weno, double; tests/golden/kat/kat_constant_medium.npz holds what the unmodified reference
+    computes): receiver times and iteration counts of all 100 sources bit for bit, hence the same mean relative error"""
+    import os
+    from conftest import ROOT
+    from ttcr_b200 import Grid3d
+    with np.load(os.path.join(ROOT, "tests", "golden", "kat", "kat_constant_medium.npz")) as f:
+        k = {n: f[n] for n in f.files}
+    x = k["x"]
+    g = Grid3d(x, k["y"], k["z"], n_threads=2, cell_slowness=0, tt_from_rp=False, eps=1e-5, maxit=50, weno=1, dtype=np.float64)
+    g.set_slowness(np.full((x.size, x.size, x.size), float(k["slowness"])))
+    tt, its = g.raytrace_sources(k["src"], k["rcv"])
+    assert np.array_equal(its, k["iters"])
+    assert np.array_equal(tt, k["tt_rcv"])
+    ref = float(k["slowness"]) * np.sqrt(((k["rcv"][None, :, :] - k["src"][:, None, :]) ** 2).sum(axis=2))
+    assert abs(float(np.mean(np.abs((ref - tt) / ref)[ref != 0.0])) - float(k["error"])) < 1e-15

@@ -4,10 +4,12 @@ The plain-C restatement (oracle/fsm_oracle.c) must reproduce, bit for bit, the f
 UNMODIFIED reference produced (tests/golden/*.npz, written by oracle/make_golden.py through
 oracle/_ref) -- and the live reference when oracle/_ref is present.
 """
+import os
+
 import numpy as np
 import pytest
 
-from conftest import golden_names, load_golden, golden_ray_names, load_golden_rays
+from conftest import ROOT, golden_names, load_golden, golden_ray_names, load_golden_rays
 
 
 def _run_oracle(O, g, order=0):
@@ -256,3 +258,51 @@ def test_2d_cell_slowness_and_receivers_bit_identical_to_reference(oracle, dtype
     b, ri, rw, tr = O.ref_solve2d(ncx, ncz, h, h, sc, tx, t0, weno=weno, dtype=dtype, cell_slowness=True, rx=rx)
     assert (ni, nw) == (ri, rw) and np.array_equal(a, b)
     assert np.array_equal(O.interp2d(ncx, ncz, h, h, a, rx, dtype=dtype), tr)
+
+
+# the reference's own accuracy table (tests/accuracy_grid3d.csv, study 1: FAST_SWEEPING on the medium models, mean relative
+# error of the receiver times against the analytic solution); make_golden.py stored what the unmodified reference gives here
+PUBLISHED = {("gradient", "float64"): 0.00228619, ("gradient", "float32"): 0.00228538,
+             ("layers", "float64"): 0.00669965, ("layers", "float32"): 0.00670199}
+
+
+@pytest.mark.parametrize("model,dt", sorted(PUBLISHED))
+def test_published_accuracy_numbers_are_reproduced(oracle, model, dt):
+    """the reference run here, and the restatement, reproduce the reference's published accuracy figures to all six digits"""
+    g = load_golden(f"ref_{model}_medium_w_{dt}")
+    assert float(f"{float(g['ref_mean_rel_err']):.6g}") == PUBLISHED[(model, dt)]
+    dtype = g["dtype"]
+    x, y, z = g["x"], g["y"], g["z"]
+    dx = float(np.asarray(x, dtype=dtype)[1] - np.asarray(x, dtype=dtype)[0])
+    s = g["slowness"]
+    if g["cell_slowness"]:
+        s_node = oracle.cell_to_node(oracle.to_cxx(s.astype(dtype)), x.size - 1, y.size - 1, z.size - 1, dtype=dtype)
+    else:
+        s_node = oracle.to_cxx(s.astype(dtype))
+    tt, _, _ = oracle.solve(x.size - 1, y.size - 1, z.size - 1, dx, s_node, g["src"][:, 1:4].astype(dtype), g["src"][:, 0], weno=True,
+                            dtype=dtype)
+    t = oracle.interp(x.size - 1, y.size - 1, z.size - 1, dx, tt, g["rcv"], dtype=dtype).astype(np.float64)
+    a = g["analytic_rcv"]
+    err = np.mean(np.abs(t[1:] - a[1:]) / a[1:])
+    assert float(f"{err:.6g}") == PUBLISHED[(model, dt)]
+
+
+def test_accuracy_study_constant_model_random_sources(oracle):
+    """study 2 of tests/accuracy_grid3d.cpp (constant_medium.vtr, sources from mt19937_64(12345), receivers rcv.dat, weno,
+    double) as the unmodified reference computes it here (tests/golden/kat/kat_constant_medium.npz): the restatement gives the
+    same receiver times bit for bit (every fourth source), and the fixture's mean relative error is the one of its times.
+    (The reference's csv lists 0.00152022 for this case; the reference built here from the same sources gives 0.00118933,
+    with the very source positions libstdc++ generates -- the csv predates the tree or comes from another build.)"""
+    with np.load(os.path.join(ROOT, "tests", "golden", "kat", "kat_constant_medium.npz")) as f:
+        k = {n: f[n] for n in f.files}
+    x = k["x"]
+    n = x.size
+    s0 = float(k["slowness"])
+    s_node = np.full(n ** 3, s0)
+    ref = s0 * np.sqrt(((k["rcv"][None, :, :] - k["src"][:, None, :]) ** 2).sum(axis=2))
+    assert abs(float(np.mean(np.abs((ref - k["tt_rcv"]) / ref)[ref != 0.0])) - float(k["error"])) < 1e-15
+    assert abs(float(k["error"]) - 0.00118933) < 5e-9
+    for i in range(0, 100, 4):
+        tt, ni, nw = oracle.solve(n - 1, n - 1, n - 1, float(x[1] - x[0]), s_node, k["src"][i:i + 1], 0.0, weno=True)
+        assert (ni, nw) == tuple(k["iters"][i])
+        assert np.array_equal(oracle.interp(n - 1, n - 1, n - 1, float(x[1] - x[0]), tt, k["rcv"]), k["tt_rcv"][i])
