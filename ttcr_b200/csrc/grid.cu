@@ -24,6 +24,7 @@
 #include "sweep_tile3.cuh"
 #include "raypath.cuh"
 #include "sweep_tile5.cuh"
+#include "sweep_march.cuh"
 
 namespace ttcrb200 {
 
@@ -162,6 +163,7 @@ class Grid final : public GridBase {
             cudaFree(s.d_pts); cudaFreeHost(s.h_pts);
             tile_free(s.tile);
             tile5_free(s.tile5);
+            march_free(s.march);
             cudaEventDestroy(s.e0); cudaEventDestroy(s.e1);
             cudaStreamDestroy(s.stream);
         }
@@ -398,7 +400,7 @@ class Grid final : public GridBase {
         if (key == "tt_from_rp") ttrp_ = v != 0;
         else if (key == "kernel") {
             if (v != TTCR_B200_KERNEL_AUTO && v != TTCR_B200_KERNEL_PLANE && v != TTCR_B200_KERNEL_TILE &&
-                v != TTCR_B200_KERNEL_TILE3 && v != TTCR_B200_KERNEL_TILE4 && v != TTCR_B200_KERNEL_TILE5 && v != TTCR_B200_KERNEL_COOP)
+                v != TTCR_B200_KERNEL_TILE3 && v != TTCR_B200_KERNEL_TILE4 && v != TTCR_B200_KERNEL_TILE5 && v != TTCR_B200_KERNEL_COOP && v != TTCR_B200_KERNEL_MARCH)
                 throw Err(TTCR_B200_ERR_INVALID, "unknown kernel id");
             kernel_ = (int)v;
         } else if (key == "tile_rows") tile_opt_.chunk = std::max(1, (int)v);
@@ -433,6 +435,7 @@ class Grid final : public GridBase {
         size_t pts_cap = 0;
         TileState tile;
         Tile5State tile5;
+        MarchState march;
         ttcr_b200_stats st{};
         unsigned* d_bar = nullptr;           // arrival counter of k_sweep_planes_coop's grid barrier
         FrozenBox* d_fb = nullptr;           // the source's frozen box, for k_sweep_plane (launch arguments stay source independent)
@@ -523,6 +526,12 @@ class Grid final : public GridBase {
     void launch_sweep(Slot& s, int dir, bool weno_stage, const FrozenBox& fb, int kernel) {
         const SweepView w = make_view(d_, dir);
         T* tt = s.tt[w.layout];
+        if (kernel == TTCR_B200_KERNEL_MARCH) {
+            const int nl = march_sweep<T>(s.tile, s.march, tile_opt_, sm_count_, w, d_, tt, slo_[w.layout], s.mask[w.layout], fb,
+                                         g_.dx, s.d_change, s.stream);
+            s.st.launches += nl; s.st.sweep_launches += nl;
+            return;
+        }
         if (kernel == TTCR_B200_KERNEL_TILE5) {
             const int nl = tile5_sweep<T>(s.tile, s.tile5, tile_opt_, sm_count_, w, d_, tt, slo_[w.layout], s.mask[w.layout], fb,
                                          g_.dx, s.d_change, s.stream);
@@ -643,7 +652,8 @@ class Grid final : public GridBase {
     int pick_kernel(bool weno_stage) const {
         const int weno_kernel_ = plane_kernel();
         if (kernel_ != TTCR_B200_KERNEL_AUTO) {
-            if ((kernel_ == TTCR_B200_KERNEL_TILE3 || kernel_ == TTCR_B200_KERNEL_TILE4 || kernel_ == TTCR_B200_KERNEL_TILE5) &&
+            if ((kernel_ == TTCR_B200_KERNEL_TILE3 || kernel_ == TTCR_B200_KERNEL_TILE4 || kernel_ == TTCR_B200_KERNEL_TILE5 ||
+                 kernel_ == TTCR_B200_KERNEL_MARCH) &&
                 !tile3_supported<T>(weno_stage))
                 return tile_supported<T>(weno_stage) ? TTCR_B200_KERNEL_TILE : weno_kernel_;
             if (kernel_ == TTCR_B200_KERNEL_TILE && !tile_supported<T>(weno_stage)) return weno_kernel_;
