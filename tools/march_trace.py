@@ -10,13 +10,14 @@ pos, k = 0, 0
 while pos < len(raw):
     ntiles, nU, nV, PUT = np.frombuffer(raw, dtype=np.int32, count=4, offset=pos)
     pos += 16
-    t = np.frombuffer(raw, dtype=np.int64, count=ntiles * 8, offset=pos).reshape(ntiles, 8).astype(np.float64)
-    pos += ntiles * 64
+    RL, PUT = max(8, PUT // 1000), PUT % 1000
+    t = np.frombuffer(raw, dtype=np.int64, count=ntiles * RL, offset=pos).reshape(ntiles, RL).astype(np.float64)
+    pos += ntiles * RL * 8
     k += 1
     if len(sys.argv) > 2 and k != int(sys.argv[2]):
         continue
     t0 = t[:, 0].min()
-    T = (t.reshape(nU, nV, 8) - t0) / 1e3
+    T = (t.reshape(nU, nV, RL) - t0) / 1e3
     tk, st, en = T[:, :, 0], T[:, :, 1], T[:, :, 5]
     print(f"sweep {k}: tiles {ntiles} (nU {nU} x nV {nV}, PUT {PUT}); span {en.max():.1f} us; SMs used {len(np.unique(t[:, 7]))}")
     run = en - st

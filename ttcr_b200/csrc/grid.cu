@@ -409,6 +409,7 @@ class Grid final : public GridBase {
         else if (key == "tile_urows") tile_opt_.rows = std::max(1, std::min(4, (int)v));
         else if (key == "tile_depth") tile_opt_.depth = (int)v;
         else if (key == "spin_limit") tile_opt_.spin_limit = (long long)v;
+        else if (key == "max_ctas") tile_opt_.max_ctas = std::max(0, (int)v);
         else if (key == "plane_graph") plane_graph_ = v != 0;
         else if (key == "coop_ctas") coop_ctas_ = std::max(1, std::min(8, (int)v));
         else if (key == "weno_kernel") {

@@ -1,44 +1,49 @@
-// Sweep kernel "MARCH" (k_sweep_march): one node per thread and step.
+// Sweep kernel "MARCH" (k_sweep_march): two nodes per thread and step, warp patches of 4 planes x 16 lanes.
 //
-// A directional sweep is a chain of ni + nj + nk dependent steps, and what k_sweep_patch (sweep_tile5.cuh) pays per step
-// is the time one thread needs for its FOUR nodes (775 cycles alone on a scheduler) -- 1535 x 0.49 us is 0.75 ms before
-// any hand-off, three times the HBM time of the sweep.  This kernel keeps the decomposition of the earlier ones
-// (sheared layouts, tiles marching along the row axis m, tickets in dependency order, tagged words between tiles,
-// TMA boxes skewed by the tensor map) and changes the thread geometry so that a step is ONE Godunov update deep:
+// A directional sweep is a chain of ni + nj + nk dependent steps and ~50 issued instructions per node; both, not HBM,
+// bound k_sweep_patch (sweep_tile5.cuh: a step is FOUR Godunov updates deep, 775 cycles, and a third of the issued
+// instructions poll).  This kernel keeps the decomposition of the earlier ones (sheared layouts, tiles marching along
+// the row axis m, tickets in dependency order, tagged words between tiles, TMA boxes skewed by the tensor map) and
+// changes the thread geometry so that a step is ONE update deep (two independent ones per thread, ILP 2):
 //
-//   * a WARP owns a patch of 4 planes (u) x 8 lanes (v): thread (lu, lv) = lane (lu*8 + lv).  Plane lu runs lu rows
-//     behind plane 0, so at step a the thread updates node (u0w + lu, m_first - 1 + a - pl, v0w + lv) and
-//         (u-1, m, v)    = result of lane - 8 at the previous step      one SHFL   (lu == 0: ring word)
-//         (u, m-1, v-1)  = result of lane - 1 at the previous step      one SHFL   (lv == 0: ring word)
-//         (u, m-1, v)    = own previous result                          register
-//         (u, m+1, v), (u, m+1, v+1), (u+1, m, v), slowness             four LDS.32 from the TMA boxes
-//     Both upwind neighbours across the patch edges arrive as tagged 8-byte words {value, step tag} in a per-warp
-//     shared-memory ring (8 U words + 4 V words per step), written by the warp above / to the left, or by the importer
-//     warp from the global mailboxes of the neighbouring tiles.  No CTA barrier, no mbarrier in a compute warp.
-//   * a CTA stacks WU x WV warps (default 4 x 4: a tile of 16 planes x 32 lanes, 16 compute warps + importer + loader),
-//     two CTAs per SM.  All warps of a tile run the same step index; v-adjacent warps are NOT lagged (a lag would have
-//     to be paid in ring depth of the TMA boxes).
-//   * the loader warp issues one 3-D box of traveltimes {TW+4 lanes, 2 rows, PUT+1 planes} and one of slowness per chunk
-//     of 2 steps into a ring of NCH slots and publishes "rows landed" as a plain shared word; compute warps publish
-//     their progress every other step (ring reuse, back-pressure of the word rings).  The box is stored
-//     [plane][row][lane] with 2*(TW+4) words per plane = 8 (mod 32): the 4 x 8 threads of a warp hit 32 different banks.
-//   * slots that are no node hold +MAX (traveltime) and NaN (slowness), as for k_sweep_patch: no validity test.  Frozen
-//     nodes and the grid's last plane / last lane take a warp-uniform slow branch.
+//   * a WARP owns a patch of 4 planes (u) x 16 lanes (v): thread (lu, lv) = lane lu*8 + lv owns lanes 2 lv, 2 lv + 1
+//     (nodes A and B) of plane lu.  Plane lu runs lu rows behind plane 0, so at step t the thread updates the nodes
+//     (u, m, v) = (u0w + lu, m_first + t - 2 - pl, v0w + 2 lv + {0, 1}) and
+//         (u-1, m, v)      = results of lane - 8 at the previous step      two SHFL     (lu == 0: ring words)
+//         (u, m-1, v-1)    = A: result B of lane - 1 at the previous step  one SHFL     (lv == 0: ring word)
+//                            B: own previous result A                      register
+//         (u, m-1, v)      = own previous results                          registers
+//         (u, m+1, v)      = next old row                                  one LDS.64 (becomes `old` of the next step)
+//         (u, m+1, v+1)    = A: the B half of that load; B: lane + 2       one LDS.32
+//         (u+1, m, v), slowness                                            two LDS.64
+//     all from the TMA boxes, loaded one step ahead.  Upwind neighbours across the patch edges arrive as tagged
+//     8-byte words {value, step tag} in per-warp shared-memory rings (8 x 2 U words + 4 V words per step) written by
+//     the warp above / to the left, or by the importer warp from the global mailboxes of the neighbouring tiles.  An
+//     aligned 8-byte shared access is single-copy atomic: who sees the tag has the value; no fence, no barrier.
+//   * a CTA stacks WU x WV warps (default 4 x 2: a tile of 16 planes x 32 lanes, 8 compute warps + importer + loader),
+//     one CTA per SM: two compute warps per scheduler keep a step near the latency of one update, which is what the
+//     chain of ~1500 steps pays for; more warps per SM only lengthen the step.
+//   * the loader thread issues one 3-D box of traveltimes {TW+4 lanes, 4 rows, PUT+1 planes} and one of slowness per
+//     chunk of 4 steps into a ring of NCH slots (mbarrier "full" per slot, completed by the TMA bytes; mbarrier
+//     "empty", one arrival per compute warp).  The plane skew lives in the TENSOR MAP (plane stride = rows per plane
+//     -+ 1), so a box arrives skewed and every shared-memory address of a step is slot base + immediate.  A plane of a
+//     box is 4 rows x 36 words = 64 (mod 128) bytes: the 64-bit loads of a half-warp hit 32 different banks.
+//   * no warp can be more than NCH*4 steps ahead of another one of its tile (the chunk ring), so the word rings
+//     (depth 32 > NCH*4) need no back-pressure between compute warps; the importer looks at the consumer's progress.
+//   * slots that are no node hold +MAX (traveltime) and NaN (slowness), as for k_sweep_patch, and the TMA unit fills what
+//     lies beyond the arrays with NaN: no validity test, no edge case.  Frozen nodes take a warp-uniform slow variant of
+//     the step (a few groups of a few tiles).
 //
 // fp32, first-order stage.  Same DAG and same arithmetic (update.cuh) as every other sweep kernel: bit-identical field.
 #pragma once
 #include "sweep_tile5.cuh"
 
-#ifndef TTCR_MARCH_STEP_TRACE
-#define TTCR_MARCH_STEP_TRACE 0   // 1: per-step clocks of tile 0 (TTCR_B200_TRACE_STEPS), development builds only
-#endif
-
 namespace ttcrb200 {
 
 struct MarchMail {
-    unsigned long long* u = nullptr;   // [tile][rows][TW]:  last plane of the tile, one word per lane and row
-    unsigned long long* v = nullptr;   // [tile][rows][PUT]: last lane of the tile, one word per plane and row
-    int rows = 0;                      // row stride per tile (MARGIN rows before local row 0)
+    unsigned long long* u = nullptr;   // [tile][step][TW]:  last plane of the tile, one word per lane and step
+    unsigned long long* v = nullptr;   // [tile][step][PUT]: last lane of the tile, one word per plane and step
+    int rows = 0;                      // steps per tile (row stride)
     unsigned serial = 0;               // tag of the current sweep (never cleared)
 };
 
@@ -51,45 +56,41 @@ struct MarchParams {
     const int* order;
     int* ctrl;
     double* partial;   // [tile][NW]
-    long long* trace;  // [tile][8] or nullptr
-    unsigned pause_ns; // sleep between two polls of a waiting compute warp (0 = spin)
-    unsigned lpause_ns; // sleep of the loader when it can neither issue nor land a chunk
+    long long* trace;  // [tile][16] or nullptr
     int pf_chunks;     // L2 prefetch distance of the loader, in chunks beyond the box ring (0 = off)
-    int trace_tile;    // tile whose steps a step-trace build records
 };
 
-template <int WU, int WV, int NCH, int D>
+template <int WU, int WV, int NCH>
 struct MarchLayout {
-    static constexpr int NW = WU * WV, PUT = 4 * WU, TW = 8 * WV, BW = TW + 4, C = 2;
-    static constexpr int NT = (NW + 2) * 32;
+    static constexpr int NW = WU * WV, PUT = 4 * WU, TW = 16 * WV, BW = TW + 4, C = 4, D = 32;
+    static constexpr int NT = (NW + 3) * 32;
     static constexpr int ROWB = BW * 4, PSB = C * ROWB;                               // bytes per box row / per plane of a box
     static constexpr int TBYTES = (PUT + 1) * PSB, SBYTES = PUT * PSB;                // bytes a box delivers
-    static constexpr int CHB_T = t5_round128(TBYTES), CHB_S = t5_round128(SBYTES), CHB = CHB_T + CHB_S;
-    static constexpr int SLOTB = 128, RINGB = D * SLOTB;                              // ring slot: 8 U words | 4 V words | pad
-    static constexpr int MARGIN = PUT + 4;                                            // mailbox rows before local row 0
+    // the two mbarriers of a chunk slot live in the padding behind its T box
+    static constexpr int OFF_EMPTY = TBYTES, OFF_FULL = TBYTES + 8;
+    static constexpr int CHB_T = t5_round128(TBYTES + 16), CHB_S = t5_round128(SBYTES), CHB = CHB_T + CHB_S;
+    static constexpr int USLOT = 128, VSLOT = 32;                                     // 8 x {A, tag, B, tag} | 4 x {B, tag}
+    static constexpr int URING = D * USLOT, VRING = D * VSLOT;
+    static constexpr int OFF_UR = NCH * CHB;
+    static constexpr int OFF_VR = OFF_UR + NW * URING;
+    static constexpr int OFF_PROG = OFF_VR + NW * VRING;                              // steps completed, per compute warp
+    static constexpr int OFF_CTL = OFF_PROG + (NW * 4 + 15) / 16 * 16;                // dead, tile
+    static constexpr int BYTES = OFF_CTL + 16;
     static constexpr int BIG = 1 << 29;
-    static constexpr int OFF_BOX = 0;
-    static constexpr int OFF_BAR = NCH * CHB;                                         // NCH mbarriers
-    static constexpr int OFF_PROG = OFF_BAR + (NCH * 8 + 15) / 16 * 16;               // progress of the NW compute warps
-    static constexpr int OFF_CTL = OFF_PROG + (NW * 4 + 15) / 16 * 16;                // landed, dead, tile, chunks issued
-    static constexpr int OFF_RING = OFF_CTL + 16;                                     // word rings: aligned at run time to RINGB in the
-    static constexpr int BYTES = OFF_RING + RINGB + NW * RINGB;                       // shared ADDRESS space (slot wrap by masking)
-    static_assert((2 * BW) % 32 == 8 || (2 * BW) % 32 == 24, "plane stride of a box must spread the 4 planes of a warp over the banks");
-    static_assert((D & (D - 1)) == 0 && D >= 8, "ring depth: a power of two, at least 8");
-    // A warp at step a has seen chunk (a+2)/2 landed, which the loader issued only after EVERY warp had published step
-    // a + 2 - 2 NCH: no warp can be more than 2 NCH steps ahead of another, so the word rings need no back-pressure of their own.
-    static_assert(D >= 2 * NCH + 1, "word rings must outlast the box ring");
-    static_assert(PUT + C + 6 <= GUARD, "guard rows too few");
-    static_assert(PUT <= 32 && TW <= 32 && NW % 4 == 0, "one importer lane per plane and per lane of the tile");
+    static_assert(PSB % 128 == 64, "plane stride of a box must put the two planes of a half-warp on different banks");
+    static_assert(NCH * C < D, "word rings must outlast the box ring");
+    static_assert(PUT + 2 * C + 6 <= GUARD, "guard rows too few");
+    static_assert(TW % 32 == 0, "tiles are cut on kpad's granularity: no tile without a valid lane");
+    static_assert(BYTES <= 227 * 1024, "shared memory");
 };
 
-// ---- geometry (host + device: tests/ emulate the TMA boxes with these) ---------------------------------------------
+// ---- geometry (host + device) ------------------------------------------------------------------------------------------
 struct MarchTile {
     int U, V, u0, v0, va, vb, m_first, nrows, nA, nch;
-    int has_u, has_v, has_down, has_right, nrows_p, dmf;
+    int has_u, has_v, has_down, has_right, nA_left, dmf;
 };
 
-template <int PUT, int TW>
+template <int PUT, int TW, int C>
 __host__ __device__ inline MarchTile march_tile(const SweepView& w, int nU, int nV, int tile) {
     MarchTile t;
     t.U = tile / nV; t.V = tile - t.U * nV;
@@ -98,89 +99,95 @@ __host__ __device__ inline MarchTile march_tile(const SweepView& w, int nU, int 
     t.vb = t.v0 + TW < w.vhi ? t.v0 + TW : w.vhi;
     t.m_first = t.va - w.joff;                      // first row that holds a node of the tile (j = 0 on lane va)
     t.nrows = (t.vb - t.va) + w.nj - 1;             // local rows 0 .. nrows-1 hold all its nodes
-    const int nsteps = t.nrows + PUT;               // at step a plane pl runs local row a - 1 - pl
-    t.nA = (nsteps + 1) & ~1;                       // steps executed (pairs)
-    t.nch = t.nA / 2 + 1;                           // chunks of 2 box rows: rows 0 .. nA (the last step still prefetches)
+    // step t = 1 .. nA: plane pl updates local row t - 2 - pl and reads box row t - 1
+    t.nA = (t.nrows + PUT + 1 + C - 1) / C * C;
+    t.nch = t.nA / C + 1;                           // (the last step still prefetches)
     t.has_u = t.U > 0; t.has_v = t.V > 0;
     t.has_down = t.U + 1 < nU; t.has_right = t.v0 + TW < w.vhi;
     const int va_p = (t.v0 - TW) > w.vlo ? (t.v0 - TW) : w.vlo;
-    t.nrows_p = (t.v0 - va_p) + w.nj - 1;           // rows of tile V-1
+    const int nrows_p = (t.v0 - va_p) + w.nj - 1;   // rows of tile V-1
+    t.nA_left = (nrows_p + PUT + 1 + C - 1) / C * C;
     t.dmf = t.m_first - (va_p - w.joff);            // its local row index of my local row 0
     return t;
 }
 
-template <int WU, int WV, int NCH, int D, bool RI, bool RJ, bool RK>
+template <int WU, int WV, int NCH, bool RI, bool RJ, bool RK>
 struct MarchGeom {
-    using L = MarchLayout<WU, WV, NCH, D>;
-    // byte offsets inside a chunk slot, relative to the traveltime word (u, m+1, v) of the EVEN step of the chunk
-    static constexpr int DR = RJ ? -L::ROWB : L::ROWB;                 // ... of the odd step
-    static constexpr int DH = RK ? -4 : 4;                             // (u, m+1, v+1)
+    using L = MarchLayout<WU, WV, NCH>;
+    // byte offsets inside a chunk slot, relative to the pair of traveltime words (u, m+1, {vA, vB}) of box row 0
+    static constexpr int DR = RJ ? -L::ROWB : L::ROWB;                 // next box row
+    static constexpr int DH = RK ? -4 : 8;                             // (u, m+1, vB+1)
     static constexpr int DUP = RI ? -L::PSB : L::PSB;                  // (u+1, m, v)
     static constexpr int DS = L::CHB_T + (RI ? -L::PSB : 0);           // slowness (u, m, v)
+    // vl: first (even) lane of the thread inside the tile.  With RK the pair sits mirrored in memory: vB below vA.
     __host__ __device__ static int thread_off(int pl, int vl) {
-        return (RI ? L::PUT - pl : pl) * L::PSB + (RK ? L::BW - 1 - vl : vl) * 4 + (RJ ? L::ROWB : 0);
+        return (RI ? L::PUT - pl : pl) * L::PSB + (RK ? L::BW - 2 - vl : vl) * 4 + (RJ ? (L::C - 1) * L::ROWB : 0);
     }
     // box origins in tensor-map coordinates (x lane, y skewed row, z plane) of chunk c; `s` = 1 for the slowness box.
-    // Box row b (= step b) holds, for plane pl, row m_first + b - pl of the traveltimes and m_first - 1 + b - pl of slowness.
+    // Box row b holds, for plane pl, row m_first + b - pl of the traveltimes and m_first - 1 + b - pl of slowness.
     __host__ __device__ static int box_x(const Dims& d, const MarchTile& t) { return RK ? d.kpad - L::BW - t.v0 : t.v0; }
     __host__ __device__ static int box_z(const Dims& d, const MarchTile& t, int s) {
         return RI ? d.ni - 1 - (t.u0 + L::PUT - s) : t.u0;
     }
     __host__ __device__ static int box_y(const SweepView& w, const Dims& d, const MarchTile& t, int c, int s) {
         const int mf = t.m_first - s;
-        if (!RJ) return GUARD + mf + 2 * c + t.u0 + (RI ? 1 : 0);
-        return GUARD + (w.nm - 1) - mf - (2 * c + 1) - t.u0 + d.ni - (RI ? 1 : 0);
+        if (!RJ) return GUARD + mf + L::C * c + t.u0 + (RI ? 1 : 0);
+        return GUARD + (w.nm - 1) - mf - (L::C * c + L::C - 1) - t.u0 + d.ni - (RI ? 1 : 0);
     }
 };
 
-// ---- small PTX helpers ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void sts_u2_if(unsigned a, unsigned x, unsigned y, int on) {
-    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %3, 0;\n\t@q st.volatile.shared.v2.u32 [%0], {%1, %2};\n\t}" ::"r"(a), "r"(x), "r"(y), "r"(on) : "memory");
+// ---- small PTX helpers -------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float2 lds_f2(unsigned a) {
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a) : "memory");
+    return v;
 }
-__device__ __forceinline__ void stg_f_stream_if(float* p, float x, int on) {
-    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %2, 0;\n\t@q st.global.L1::no_allocate.f32 [%0], %1;\n\t}" ::"l"(p), "f"(x), "r"(on) : "memory");
+__device__ __forceinline__ void sts_u2_ifu(unsigned a, unsigned x, unsigned y, unsigned on) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %3, 0;\n\t@q st.volatile.shared.v2.u32 [%0], {%1, %2};\n\t}" ::"r"(a), "r"(x), "r"(y), "r"(on) : "memory");
 }
-__device__ __forceinline__ void sts_i_if(unsigned a, int v, unsigned on) {
+__device__ __forceinline__ void sts_u4_ifu(unsigned a, unsigned x, unsigned y, unsigned z, unsigned w, unsigned on) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %5, 0;\n\t@q st.volatile.shared.v4.u32 [%0], {%1, %2, %3, %4};\n\t}" ::"r"(a), "r"(x), "r"(y), "r"(z),
+                 "r"(w), "r"(on)
+                 : "memory");
+}
+__device__ __forceinline__ void stg_f2_stream_if(float* p, float x, float y, int on) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %3, 0;\n\t@q st.global.L1::no_allocate.v2.f32 [%0], {%1, %2};\n\t}" ::"l"(p), "f"(x), "f"(y), "r"(on) : "memory");
+}
+__device__ __forceinline__ void sts_i_ifu(unsigned a, int v, unsigned on) {
     asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q st.volatile.shared.s32 [%0], %1;\n\t}" ::"r"(a), "r"(v), "r"(on) : "memory");
 }
-// next slot of a ring that is aligned to its size: (a & ~(SIZE-1)) | ((a + STEP) & (SIZE-1)), one add and one LOP3
-template <unsigned SIZE, unsigned STEP>
-__device__ __forceinline__ unsigned ring_next(unsigned a) {
-    unsigned r;
-    asm("{\n\t.reg .b32 t;\n\tadd.u32 t, %1, %2;\n\tlop3.b32 %0, %1, t, %3, 0xD8;\n\t}" : "=r"(r) : "r"(a), "n"(STEP), "n"(SIZE - 1));
-    return r;
+__device__ __forceinline__ void mbar_arrive_ifu(unsigned a, unsigned on) {
+    asm volatile("{\n\t.reg .pred q;\n\t.reg .b64 t;\n\tsetp.ne.u32 q, %1, 0;\n\t@q mbarrier.arrive.shared::cta.b64 t, [%0];\n\t}" ::"r"(a), "r"(on) : "memory");
 }
-__device__ __forceinline__ int mbar_test_nb(unsigned a, unsigned parity) {
-    int ok;
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.s32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(a), "r"(parity) : "memory");
-    return ok;
-}
-__device__ __forceinline__ void sts_release_i(unsigned a, int v) { asm volatile("st.release.cta.shared.s32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 
-template <int WU, int WV, int NCH, int D, bool RI, bool RJ, bool RK>
-__global__ void __launch_bounds__((WU * WV + 2) * 32, 2)
+template <int WU, int WV, int NCH, bool RI, bool RJ, bool RK>
+__global__ void __launch_bounds__((WU * WV + 3) * 32, 1)
 k_sweep_march(const __grid_constant__ CUtensorMap tmT, const __grid_constant__ CUtensorMap tmS, MarchParams p, MarchMail mail,
               float* __restrict__ tt, const uint32_t* __restrict__ frozen, float dx) {
-    using L = MarchLayout<WU, WV, NCH, D>;
-    using G = MarchGeom<WU, WV, NCH, D, RI, RJ, RK>;
-    constexpr int NW = L::NW, PUT = L::PUT, TW = L::TW, SLOTB = L::SLOTB, RINGB = L::RINGB, MG = L::MARGIN, BIG = L::BIG;
-    constexpr int IG = 4;   // mailbox rows the importer keeps in flight
+    using L = MarchLayout<WU, WV, NCH>;
+    using G = MarchGeom<WU, WV, NCH, RI, RJ, RK>;
+    constexpr int NW = L::NW, PUT = L::PUT, TW = L::TW, C = L::C, D = L::D, BIG = L::BIG;
+    constexpr int USLOT = L::USLOT, VSLOT = L::VSLOT, URING = L::URING, VRING = L::VRING;
     extern __shared__ __align__(128) unsigned char smem_raw[];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const SweepView& w = p.w;
     const float MAXV = FLT_MAX;
     const unsigned sbase = (unsigned)pin((int)__cvta_generic_to_shared(smem_raw));
-    const unsigned a_ctl = sbase + L::OFF_CTL, a_dead = a_ctl + 4, a_tile = a_ctl + 8;
+    const unsigned a_ctl = sbase + L::OFF_CTL, a_dead = a_ctl, a_tile = a_ctl + 4;
     const unsigned a_prog = sbase + L::OFF_PROG;
-    const unsigned a_ring = (sbase + L::OFF_RING + RINGB - 1) & ~(unsigned)(RINGB - 1);   // (the shared window does not start at 0)
+    const unsigned a_ur = sbase + L::OFF_UR, a_vr = sbase + L::OFF_VR;
     const unsigned serial = mail.serial;
     const long long spin_cycles = p.spin_cycles;
-    const unsigned pause_ns = p.pause_ns;
-    unsigned par = 0;   // loader: per chunk slot, parity of the mbarrier phase its next chunk completes
+    // Every warp sees the same sequence of chunks (nch per tile); fill k of the CTA goes to slot k % NCH.  Compute warps keep
+    // the parity of the "full" phase of the fill they wait for (cpar), the loader the round of the ring it is in (cpar).
+    unsigned cslot = 0, cpar = 0;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < NCH; ++i) mbar_init(sbase + L::OFF_BAR + 8 * i, 1);
+        for (int i = 0; i < NCH; ++i) {
+            mbar_init(sbase + i * L::CHB + L::OFF_FULL, 1);
+            mbar_init(sbase + i * L::CHB + L::OFF_EMPTY, NW);
+        }
         fence_mbar_init();
     }
 
@@ -191,205 +198,186 @@ k_sweep_march(const __grid_constant__ CUtensorMap tmT, const __grid_constant__ C
             const int ab = *((volatile int*)&p.ctrl[1]);
             sts_i(a_tile, (ab || t >= p.ntiles) ? -1 : t);
             sts_i(a_dead, 0);
-            sts_i(a_ctl, -3);
-            sts_i(a_ctl + 12, 0);
         }
-        if (threadIdx.x < NW) sts_i(a_prog + 4 * threadIdx.x, -1);   // progress a = even step a has issued its reads of box row a + 1
+        if (threadIdx.x < NW) sts_i(a_prog + 4 * threadIdx.x, 0);
         __syncthreads();
         const int ticket = lds_i(a_tile);
         if (ticket < 0) break;
         const int tile = p.order[ticket];
-        const MarchTile T = march_tile<PUT, TW>(w, p.nU, p.nV, tile);
+        const MarchTile T = march_tile<PUT, TW, C>(w, p.nU, p.nV, tile);
         const int nA = T.nA;
-        // Word rings.  A word is valid for step a when its tag is >= a + 1 (a slot only ever holds the tag of its step or an
-        // older one).  Slot 0 holds the words of step 0 (+MAX: row -1 of a tile holds no node).  Words nobody will send --
-        // U words of the first warp row of a tile without a tile above, V words of the first warp column of a tile without
-        // a tile to the left -- are +MAX with tag BIG in every slot: those warps never wait.
-        for (unsigned o = threadIdx.x * 16; o < (unsigned)(NW * RINGB); o += L::NT * 16) {
-            const unsigned wr = o / RINGB, in = o & (SLOTB - 1);   // ring (= warp), byte inside the slot: U words 0..63, V words 64..95
-            const bool open_end = in < 64 ? (wr < (unsigned)WV && !T.has_u) : (wr % WV == 0 && !T.has_v);
-            const unsigned tag = open_end ? (unsigned)BIG : (((o & (RINGB - 1)) < (unsigned)SLOTB) ? 1u : 0u);
-            sts_u4(a_ring + o, __float_as_uint(MAXV), tag, __float_as_uint(MAXV), tag);
+        // Word rings.  The words of step t live in slot (t - 1) % D and are valid when their tag is >= t (a slot only ever
+        // holds the tag of its step or of an older one).  Step 1 reads +MAX (the row before the tile's first row holds
+        // no node).  Words nobody will send -- U words of the first warp row of a tile without a tile above, V words of the
+        // first warp column of a tile without a tile to the left -- are +MAX with tag BIG in every slot.
+        for (unsigned o = threadIdx.x * 16; o < (unsigned)(NW * URING); o += L::NT * 16) {
+            const unsigned wr = o / URING, slot = (o % URING) / USLOT;
+            const unsigned tag = (wr < (unsigned)WV && !T.has_u) ? (unsigned)BIG : (slot == 0 ? 1u : 0u);
+            sts_u4(a_ur + o, __float_as_uint(MAXV), tag, __float_as_uint(MAXV), tag);
+        }
+        for (unsigned o = threadIdx.x * 16; o < (unsigned)(NW * VRING); o += L::NT * 16) {
+            const unsigned wr = o / VRING, slot = (o % VRING) / VSLOT;
+            const unsigned tag = (wr % WV == 0 && !T.has_v) ? (unsigned)BIG : (slot == 0 ? 1u : 0u);
+            sts_u4(a_vr + o, __float_as_uint(MAXV), tag, __float_as_uint(MAXV), tag);
         }
         __syncthreads();
         if (p.trace && threadIdx.x == 0) {
-            p.trace[tile * 8 + 0] = gtime();
+            p.trace[tile * 16 + 0] = gtime();
             unsigned smid;
             asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-            p.trace[tile * 8 + 7] = smid;
+            p.trace[tile * 16 + 7] = smid;
         }
 
-        if (warp == NW) {
-            // ================= importer ==================================================================================
-            // step a (>= 1): ring of warp (0, l/8), slot a, U word l%8   <- row a-1 of the last plane of tile U-1, lane l
-            //                ring of warp (pl/4, 0), slot a, V word pl%4 <- row a+dmf-2-pl of the last lane of tile V-1, plane pl
-            // A tile writes one mailbox word per plane (lane) and STEP, also for the rows around its nodes (value +MAX), so
-            // every word of steps 1 .. a_end exists sooner or later; the steps after a_end get +MAX.  Lane l runs one U
-            // stream and (l < PUT) one V stream of IG independent slots each: a slot polls the word of ITS step until the
-            // tag of this sweep shows up, hands it to the ring and moves IG steps on.  No slot ever waits for another one,
-            // so a word is seen one poll (an L2 round trip) after it was written, whatever the words around it do.
-            static_assert(TW <= 32, "one U word per importer lane");
-            const bool ulane = T.has_u && lane < TW, vlane = T.has_v && lane < PUT;
-            const int vpl = lane < PUT ? lane : 0;
-            const int nA_left = (T.nrows_p + PUT + 1) & ~1;                                   // steps of tile V-1
-            const int endU = min(nA - 1, nA - PUT), endV = min(nA - 1, nA_left - T.dmf);      // last step with a mailbox word
-            const unsigned long long* const mu_p = mail.u + ((size_t)(T.has_u ? tile - p.nV : tile) * mail.rows + MG - 1) * TW + lane;                 // + a * TW
-            const unsigned long long* const mv_p = mail.v + ((size_t)(T.has_v ? tile - 1 : tile) * mail.rows + MG + (T.dmf - 2 - vpl)) * PUT + vpl;   // + a * PUT
-            const unsigned wU = a_ring + (unsigned)(lane >> 3) * RINGB + (lane & 7) * 8;
-            const unsigned wV = a_ring + (unsigned)((vpl >> 2) * WV) * RINGB + 64 + (vpl & 3) * 8;
-            const unsigned pU = a_prog + 4 * (lane >> 3), pV = a_prog + 4 * ((vpl >> 2) * WV);   // progress of the warp that reads the word
-            unsigned long long qu[IG], qv[IG];
-            int au[IG], av[IG];   // step each slot is working on
+        if (warp == NW || warp == NW + 1) {
+            // ================= importers: warp NW feeds the U words, warp NW + 1 the V words ==================================
+            // Mailboxes are indexed by the STEP of the tile that writes them (one word per lane / plane and step, also for
+            // the rows around its nodes, value +MAX):
+            //   U ring of warp (0, l/16), slot of step t, pair (l%16)/2  <- mail.u[tile U-1][step t + PUT - 1][lane l]
+            //   V ring of warp (pl/4, 0), slot of step t, word pl%4      <- mail.v[tile V-1][step t + dmf - 1][plane pl]
+            // and the steps after the last step of those tiles get +MAX.  A lane moves TWO words per access (16 bytes); the
+            // lanes of a warp are spread over S consecutive steps and every lane works on K steps at a time.  A round issues
+            // the polls of all K steps back to back and only then looks at what came back: a warp has six scoreboards, so
+            // polls that are issued and consumed one by one wait for each other (measured: 0.3 us per poll, and the importer
+            // paced every tile); a round costs ONE L2 round trip whatever K is.
+            constexpr int NPU = TW / 2, LU = NPU >= 32 ? 32 : NPU, SU = 32 / LU;       // pairs per step, lanes per step, steps per round and slot
+            constexpr int NPV = PUT / 2, LV = NPV > 8 ? 16 : 8, SV = 32 / LV;
+            static_assert(NPU <= 32 && NPV <= 16, "importer lane mapping");
+            const bool isU = warp == NW;
+            const int L_ = isU ? LU : LV, S = isU ? SU : SV;
+            const int h = lane / L_, j = lane % L_;
+            const bool act = isU ? (T.has_u != 0) : (T.has_v != 0 && j < NPV);
+            const int ja = act ? j : 0;
+            // last step with mailbox words; first word of step 0 for this lane; ring address of this lane's words; consumer progress
+            const int a_end = !act ? 0 : (isU ? nA - PUT + 1 : T.nA_left - T.dmf + 1);
+            const int stride = isU ? TW : PUT;
+            const unsigned long long* const base =
+                isU ? mail.u + ((size_t)(T.has_u ? tile - p.nV : tile) * mail.rows + (PUT - 1)) * TW + 2 * ja
+                    : mail.v + ((size_t)(T.has_v ? tile - 1 : tile) * mail.rows + (T.dmf - 1)) * PUT + 2 * ja;
+            const unsigned wring = isU ? a_ur + (unsigned)(ja >> 3) * URING + (unsigned)(ja & 7) * 16 : a_vr + (unsigned)((ja >> 1) * WV) * VRING + (unsigned)(ja & 1) * 16;
+            const unsigned slotb = isU ? USLOT : VSLOT;
+            const unsigned pcons = a_prog + 4 * (isU ? (ja >> 3) : (ja >> 1) * WV);
+            constexpr int K = 6;
+            uint4 q[K];
+            int a[K];
+            bool have[K];
 #pragma unroll
-            for (int s = 0; s < IG; ++s) {
-                au[s] = ulane ? 1 + s : nA; av[s] = vlane ? 1 + s : nA;
-                qu[s] = qv[s] = 0;
-                if (au[s] <= endU) qu[s] = ld_mail(mu_p + (size_t)au[s] * TW);
-                if (av[s] <= endV) qv[s] = ld_mail(mv_p + (size_t)av[s] * PUT);
-            }
-            // one visit of a slot: poll again / hand over and move on / wait for the ring slot.  Returns 1 if it delivered.
-            auto visit = [&](unsigned long long& q, int& a, const unsigned long long* base, int stride, int a_end, unsigned wring, unsigned pcons) {
-                if (a >= nA) return 0;
-                const bool real = a <= a_end;
-                if (real && (unsigned)(q >> 32) != serial) {
-                    q = ld_mail(base + (size_t)a * stride);
-                    return 0;
-                }
-                if (lds_i(pcons) < a + 1 - D) return 0;   // ring slot a % D still holds the word of step a - D
-                sts_u2(wring + (unsigned)(a & (D - 1)) * SLOTB, real ? (unsigned)q : __float_as_uint(MAXV), (unsigned)(a + 1));
-                a += IG;
-                if (a < nA && a <= a_end) q = ld_mail(base + (size_t)a * stride);
-                return 1;
-            };
-            long long t0 = clock64();
+            for (int k = 0; k < K; ++k) { a[k] = act ? 2 + h + S * k : nA + 1; have[k] = false; q[k] = make_uint4(0, 0, 0, 0); }
+            long long t0 = 0;
             unsigned idle = 0;
+            long long n_iter = 0, n_got = 0;
+            const long long ti0 = clock64();
             for (;;) {
+                ++n_iter;
+#pragma unroll
+                for (int k = 0; k < K; ++k)
+                    if (!have[k] && a[k] <= a_end) q[k] = ld_mail2(base + (size_t)a[k] * stride);
+                const int lim = lds_i(pcons) + D;   // ring slot (a - 1) % D holds the words of step a - D until the consumer has passed it
                 int done = 1, got = 0;
 #pragma unroll
-                for (int s = 0; s < IG; ++s) {
-                    got += visit(qu[s], au[s], mu_p, TW, endU, wU, pU);
-                    got += visit(qv[s], av[s], mv_p, PUT, endV, wV, pV);
-                    done &= (au[s] >= nA) & (av[s] >= nA);
+                for (int k = 0; k < K; ++k) {
+                    if (a[k] <= nA) {
+                        const bool real = a[k] <= a_end;
+                        const bool ok = !real || (q[k].y == serial && q[k].w == serial);
+                        if (ok && a[k] <= lim) {
+                            const unsigned tag = (unsigned)a[k], mx = __float_as_uint(MAXV);
+                            sts_u4(wring + (unsigned)((a[k] - 1) & (D - 1)) * slotb, real ? q[k].x : mx, tag, real ? q[k].z : mx, tag);
+                            a[k] += S * K;
+                            have[k] = false;
+                            got = 1;
+                        } else {
+                            have[k] = ok;   // (words that wait for their ring slot are kept)
+                        }
+                        done &= a[k] > nA;
+                    }
                 }
+                n_got += got;
                 if (done) break;
                 if (got) { idle = 0; continue; }
-                if ((++idle & 63u) == 0) {   // nothing moved for a while: is the march still alive?
+                if ((++idle & 15u) == 0) {   // nothing moved for a while: is the march still alive?
                     if (lds_i(a_dead)) break;
-                    if (idle == 64) t0 = clock64();
+                    if (idle == 16) t0 = clock64();
                     else if (clock64() - t0 > spin_cycles) {
-                        if (atomicCAS(&p.ctrl[1], 0, 31) == 0) { p.ctrl[2] = tile; p.ctrl[3] = au[0]; p.ctrl[4] = av[0]; p.ctrl[5] = NW; p.ctrl[6] = lane; }
+                        if (atomicCAS(&p.ctrl[1], 0, 31) == 0) { p.ctrl[2] = tile; p.ctrl[3] = a[0]; p.ctrl[4] = a[1]; p.ctrl[5] = warp; p.ctrl[6] = lane; }
                         sts_i(a_dead, 1);
                         break;
                     }
                 }
             }
+            if (p.trace && lane == 0) { p.trace[tile * 16 + (isU ? 8 : 11)] = n_iter; p.trace[tile * 16 + (isU ? 9 : 12)] = n_got; p.trace[tile * 16 + (isU ? 10 : 13)] = clock64() - ti0; }
             __syncwarp();
-        } else if (warp == NW + 1) {
+        } else if (warp == NW + 2) {
             // ================= loader ====================================================================================
-            // Chunk c of the tile lives in slot c % NCH.  Lane 0 issues (a chunk may go out once every warp has published the
-            // last step that reads the chunk it replaces), lane 1 waits for the boxes to land (suspended in try_wait, no
-            // polling) and publishes the rows that are there.  A slot's mbarrier is used once per chunk, in order: `par`
-            // keeps, per slot, the parity of the phase its next landing chunk completes.
-            const int nch = T.nch;
-            const unsigned a_bar = sbase + L::OFF_BAR;
+            // One thread.  Fill k of the CTA lives in slot k % NCH; it may be sent once every compute warp has arrived on the
+            // slot's "empty" barrier for fill k - NCH (the thread sleeps in try_wait: no polling).  Here cpar counts the
+            // rounds of the ring: round r >= 1 waits for the "empty" phase r - 1.
             if (lane == 0) {
+                const int nch = T.nch;
                 const int xb = G::box_x(p.d, T);
                 const int zT = G::box_z(p.d, T, 0), zS = G::box_z(p.d, T, 1);
                 const int yT0 = G::box_y(w, p.d, T, 0, 0), yS0 = G::box_y(w, p.d, T, 0, 1);
-                const int dyc = RJ ? -2 : 2;
-                int si = 0;
+                const int dyc = RJ ? -C : C;
                 for (int ci = 0; ci < nch; ++ci) {
-                    if (ci >= NCH) {
-                        // chunk ci - NCH (box rows 2(ci-NCH), +1) has been read by a warp once it has published step 2(ci-NCH)
-                        const int need = 2 * (ci - NCH);
+                    const unsigned slot = sbase + cslot * L::CHB;
+                    bool ok = true;
+                    if (cpar >= 1) {
                         const long long t0 = clock64();
-                        bool ok = true;
-                        for (;;) {
-                            int mp = BIG;
-#pragma unroll
-                            for (int i = 0; i < NW; i += 4) {
-                                const uint4 x = lds_u4(a_prog + 4 * i);
-                                mp = min(min(mp, (int)x.x), min(min((int)x.y, (int)x.z), (int)x.w));
-                            }
-                            if (mp >= need) break;
-                            __nanosleep(100);   // (a chunk is two steps, and the ring is NCH chunks deep)
+                        while (!mbar_test(slot + L::OFF_EMPTY, (cpar - 1u) & 1u)) {
                             if (lds_i(a_dead)) { ok = false; break; }
                             if (clock64() - t0 > spin_cycles) {
-                                if (atomicCAS(&p.ctrl[1], 0, 50) == 0) { p.ctrl[2] = tile; p.ctrl[3] = ci; p.ctrl[4] = mp; p.ctrl[5] = NW + 1; }
+                                if (atomicCAS(&p.ctrl[1], 0, 50) == 0) { p.ctrl[2] = tile; p.ctrl[3] = ci; p.ctrl[4] = (int)cslot; p.ctrl[5] = NW + 2; }
                                 sts_i(a_dead, 1);
                                 ok = false;
                                 break;
                             }
                         }
-                        if (!ok) break;
                     }
-                    const unsigned mb = a_bar + 8 * si;
-                    const unsigned dst = sbase + L::OFF_BOX + si * L::CHB;
-                    mbar_expect_tx(mb, L::TBYTES + L::SBYTES);
-                    tma_load_3d(dst, &tmT, xb, yT0 + ci * dyc, zT, mb);
-                    tma_load_3d(dst + L::CHB_T, &tmS, xb, yS0 + ci * dyc, zS, mb);
-                    sts_i(a_ctl + 12, ci + 1);   // chunks issued (what lane 1 may wait for)
-                    si = si + 1 == NCH ? 0 : si + 1;
-                }
-            } else if (lane == 1) {
-                int sl = 0;
-                for (int cl = 0; cl < nch; ++cl) {
-                    const long long t0 = clock64();
-                    bool ok = true;
-                    while (lds_i(a_ctl + 12) <= cl) {   // not issued yet
-                        __nanosleep(100);
-                        if (lds_i(a_dead) || clock64() - t0 > spin_cycles) { ok = false; break; }
+                    if (!ok) break;
+                    mbar_expect_tx(slot + L::OFF_FULL, L::TBYTES + L::SBYTES);
+                    tma_load_3d(slot, &tmT, xb, yT0 + ci * dyc, zT, slot + L::OFF_FULL);
+                    tma_load_3d(slot + L::CHB_T, &tmS, xb, yS0 + ci * dyc, zS, slot + L::OFF_FULL);
+                    if (p.pf_chunks > 0 && ci + p.pf_chunks < nch) {
+                        tma_prefetch_3d(&tmT, xb, yT0 + (ci + p.pf_chunks) * dyc, zT);
+                        tma_prefetch_3d(&tmS, xb, yS0 + (ci + p.pf_chunks) * dyc, zS);
                     }
-                    while (ok && !mbar_test(a_bar + 8 * sl, (par >> sl) & 1u)) {   // try_wait: suspended until the phase completes or a time limit
-                        if (lds_i(a_dead) || clock64() - t0 > spin_cycles) { ok = false; break; }
-                    }
-                    if (!ok) {   // give up; copies in flight still have to land before the CTA goes on
-                        sts_i(a_dead, 1);
-                        const int issued = lds_i(a_ctl + 12);
-                        const long long t1 = clock64();
-                        for (; cl < issued; ++cl) {
-                            while (!mbar_test(a_bar + 8 * sl, (par >> sl) & 1u) && clock64() - t1 < spin_cycles) {}
-                            par ^= 1u << sl;
-                            sl = sl + 1 == NCH ? 0 : sl + 1;
-                        }
-                        break;
-                    }
-                    par ^= 1u << sl;
-                    sl = sl + 1 == NCH ? 0 : sl + 1;
-                    sts_release_i(a_ctl, 2 * (cl + 1) - 3);   // (rows landed) - 3: an even step with tag tg needs row tg + 2
+                    if (++cslot == NCH) { cslot = 0; ++cpar; }
                 }
             }
-            par = __shfl_sync(0xffffffffu, par, 1);   // (lane 1 owns the parities; every lane keeps a copy for the next tile)
         } else {
             // ================= compute warps =============================================================================
             const int lw = warp;
             const int wu = lw / WV, wv = lw - wu * WV, lu = lane >> 3, lv = lane & 7;
-            const int pl = 4 * wu + lu, vl = 8 * wv + lv;
+            const int pl = 4 * wu + lu, vl = 16 * wv + 2 * lv;
             const int u = T.u0 + pl, vt = T.v0 + vl;
             const int ulast = w.nu - 1;
-            const bool ghost = vt >= p.d.kpad || u > ulast;   // TMA zero-fills these: `t < old` must never hold
+            // Lanes and planes beyond the arrays are filled with NaN by the TMA unit (the tensor maps ask for it): as an upwind
+            // or downwind neighbour a NaN drops out of the minima, as an old value it never lets `t < old` hold.
+            const bool ghost = vt >= p.d.kpad || u > ulast;
             const bool out_u_in = wu < WU - 1, out_v_in = wv < WV - 1;
-            // ring addresses: the output rings sit at compile-time distances from the input words (warp + WV, warp + 1)
-            unsigned rU = a_ring + (unsigned)lw * RINGB + lv * 8;        // U word lv of the slot of the even step
-            unsigned rV = a_ring + (unsigned)lw * RINGB + 64 + lu * 8;   // V word lu
-            constexpr unsigned OUT_U = WV * RINGB, OUT_V = RINGB;
+            const unsigned aUin = a_ur + (unsigned)lw * URING + lv * 16;   // pair lv of a slot of my U ring
+            const unsigned aVin = a_vr + (unsigned)lw * VRING + lu * 8;    // word lu of a slot of my V ring
+            constexpr unsigned OUT_U = WV * URING, OUT_V = VRING;          // the rings of the warp below / to the right
             const unsigned a_myprog = (unsigned)pin((int)(a_prog + 4 * lw));
-            const unsigned aJ0 = sbase + L::OFF_BOX + (unsigned)G::thread_off(pl, vl);
-            float* pg = tt + (w.base + (long long)min(u, ulast) * w.su + (long long)(T.m_first - 1 - pl) * w.sm + (long long)vt * w.sv);
-            // ---- slow-path conditions: last plane / last lane of the grid, frozen nodes (source box)
-            const bool edge_u = u >= ulast, edge_v = vt + 1 >= w.vhi;
-            const bool edge_w = __any_sync(0xffffffffu, edge_u || edge_v);
+            const unsigned toff = (unsigned)pin((int)G::thread_off(pl, vl));
+            float* pg = tt + (w.base + (long long)min(u, ulast) * w.su + (long long)(T.m_first - 1 - pl) * w.sm + (long long)(RK ? vt + 1 : vt) * w.sv);
+            const long long rowstride = w.sm;
+            // ---- slow-path condition: frozen nodes (source box)
             bool fzme = false;
             int wz_lo = 1 << 28, wz_hi = -(1 << 28);
-            if (p.fb.jhi >= p.fb.jlo && u <= ulast && vt >= w.vlo && vt < w.vhi) {
+            if (p.fb.jhi >= p.fb.jlo && u <= ulast) {
                 const int it = w.ri ? ulast - u : u;
-                const int ko = vt - w.vlo, kt = w.rk ? p.d.nk - 1 - ko : ko;
-                if (it >= p.fb.ilo && it <= p.fb.ihi && kt >= p.fb.klo && kt <= p.fb.khi) {
+                bool kin = false;
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int ve = vt + e;
+                    const int ko = ve - w.vlo, kt = w.rk ? p.d.nk - 1 - ko : ko;
+                    kin = kin || (ve >= w.vlo && ve < w.vhi && kt >= p.fb.klo && kt <= p.fb.khi);
+                }
+                if (it >= p.fb.ilo && it <= p.fb.ihi && kin) {
                     fzme = true;
                     const int jol = RJ ? w.nj - 1 - p.fb.jhi : p.fb.jlo, joh = RJ ? w.nj - 1 - p.fb.jlo : p.fb.jhi;
-                    // oriented j = m_first + r - v + joff, step a = r + 1 + pl
-                    wz_lo = jol - w.joff + vt - T.m_first + 1 + pl;
-                    wz_hi = joh - w.joff + vt - T.m_first + 1 + pl;
+                    // oriented j = m_first + r - v + joff on local row r, which is updated at step t = r + 2 + pl
+                    wz_lo = jol - w.joff + vt - T.m_first + 2 + pl;
+                    wz_hi = joh - w.joff + vt + 1 - T.m_first + 2 + pl;
                 }
             }
 #pragma unroll
@@ -398,156 +386,171 @@ k_sweep_march(const __grid_constant__ CUtensorMap tmT, const __grid_constant__ C
                 wz_hi = max(wz_hi, __shfl_xor_sync(0xffffffffu, wz_hi, o));
             }
             // lane roles, one bit each, in a register the compiler cannot rematerialise from %tid
-            enum : unsigned { F_L0 = 1, F_U0 = 2, F_V0 = 4, F_STU = 8, F_STV = 16, F_OMU = 32, F_OMV = 64, F_EU = 128, F_EV = 256, F_FZ = 512 };
+            enum : unsigned { F_L0 = 1, F_U0 = 2, F_V0 = 4, F_STU = 8, F_STV = 16, F_OMU = 32, F_OMV = 64, F_FZ = 512 };
             const unsigned fl = (unsigned)pin((int)((lane == 0 ? F_L0 : 0u) | (lu == 0 ? F_U0 : 0u) | (lv == 0 ? F_V0 : 0u) | ((lu == 3 && out_u_in) ? F_STU : 0u) |
                                                     ((lv == 7 && out_v_in) ? F_STV : 0u) | ((lu == 3 && !out_u_in && T.has_down) ? F_OMU : 0u) |
-                                                    ((lv == 7 && !out_v_in && T.has_right) ? F_OMV : 0u) | (edge_u ? F_EU : 0u) | (edge_v ? F_EV : 0u) |
+                                                    ((lv == 7 && !out_v_in && T.has_right) ? F_OMV : 0u) |
                                                     (fzme ? F_FZ : 0u)));
             const bool mail_warp = __any_sync(0xffffffffu, (fl & (F_OMU | F_OMV)) != 0);
             const float QNAN = __int_as_float(0x7fc00000);
 
             int dead = 0;
+            long long wcyc = 0, fcyc = 0, wcnt = 0;   // (trace) cycles spent waiting for ring words / for a chunk to land
             auto give_up = [&](int why, int x, int a) {
                 if (atomicCAS(&p.ctrl[1], 0, why) == 0) { p.ctrl[2] = tile; p.ctrl[3] = x; p.ctrl[4] = a; p.ctrl[5] = lw; p.ctrl[6] = lane; }
                 sts_i(a_dead, 1);
             };
-            // ---- prologue: chunk 0, operands of step 0
-            {
+            auto wait_full = [&](unsigned a_full, unsigned par, int why) {
+                if (mbar_test(a_full, par)) return;
                 const long long t0 = clock64();
-                while (lds_i(a_ctl) < 2 - 3) {
+                while (!mbar_test(a_full, par)) {
                     if (lds_i(a_dead)) { dead = 1; break; }
-                    if (clock64() - t0 > spin_cycles) { give_up(40, 0, 0); dead = 1; break; }
+                    if (clock64() - t0 > spin_cycles) { give_up(why, (int)cslot, (int)par); dead = 1; break; }
                 }
-            }
+                fcyc += clock64() - t0;
+            };
+            // ---- prologue: first chunk of the tile, operands of step 1
+            unsigned sb = sbase + cslot * L::CHB;   // chunk slot the current group reads
+            wait_full(sb + L::OFF_FULL, cpar, 40);
             int deadw = __any_sync(0xffffffffu, dead);
+            unsigned rB = sb + toff;
             const float ini = ghost ? 0.f : MAXV;
-            float nprev = ini, told = ini;
-            float j = lds_f(aJ0), h = lds_f(aJ0 + G::DH), up = lds_f(aJ0 + G::DUP), s = lds_f(aJ0 + G::DS);
-            float acc = 0.f;
-            if (p.trace && threadIdx.x == 0) p.trace[tile * 8 + 1] = gtime();
-
-            // The march runs in pairs of steps (tags tg, tg+1).  Pairs in [ts0, ts1) may touch the grid's last plane / lane
-            // or a frozen node and run the SLOW body; warps that feed a global mailbox run the MAILW bodies.
-            const unsigned tg_end = (unsigned)nA + 1u;
-            unsigned ts0 = tg_end, ts1 = tg_end;
-            if (edge_w) ts0 = 1;
-            else if (wz_hi >= wz_lo) {
-                ts0 = (unsigned)min(max((wz_lo & ~1) + 1, 1), (int)tg_end);
-                ts1 = (unsigned)min(max((wz_hi & ~1) + 3, 1), (int)tg_end);
+            float p0 = ini, p1 = ini, o0 = ini, o1 = ini;
+            float j0, j1, hh, up0, up1, s0, s1;
+            {
+                const float2 a = lds_f2(rB), b = lds_f2(rB + (unsigned)G::DUP), c = lds_f2(rB + (unsigned)G::DS);
+                hh = lds_f(rB + (unsigned)G::DH);
+                j0 = RK ? a.y : a.x; j1 = RK ? a.x : a.y;
+                up0 = RK ? b.y : b.x; up1 = RK ? b.x : b.y;
+                s0 = RK ? c.y : c.x; s1 = RK ? c.x : c.y;
             }
-            unsigned long long* mu = mail.u + ((size_t)tile * mail.rows + (MG - 1 - pl)) * TW + vl;
-            unsigned long long* mv = mail.v + ((size_t)tile * mail.rows + (MG - 1 - pl)) * PUT + pl;
-            unsigned rB = aJ0;       // thread's word in the chunk slot of the even step
-            unsigned tg = 1;
+            float acc = 0.f;
+            if (p.trace && threadIdx.x == 0) p.trace[tile * 16 + 1] = gtime();
 
-            // One march step: ring words at rUi / rVi carry tag `tgs` (= step + 1), outputs go to rUo / rVo, next operands at `ao`.
+            // Groups of C steps (tags t .. t+C-1) read chunk `sb`; groups in [ts0, ts1) may touch a frozen node and run the SLOW body; warps that feed a global mailbox run the MAILW bodies.
+            const unsigned t_end = (unsigned)nA + 1u;
+            unsigned ts0 = t_end, ts1 = t_end;
+            if (wz_hi >= wz_lo) {
+                ts0 = (unsigned)min(max(((wz_lo - 1) / C) * C + 1, 1), (int)t_end);
+                ts1 = (unsigned)min(max(((wz_hi - 1) / C + 1) * C + 1, 1), (int)t_end);
+            }
+            unsigned long long* mu = mail.u + ((size_t)tile * mail.rows + 1) * TW + vl;    // [tile][step][lane]
+            unsigned long long* mv = mail.v + ((size_t)tile * mail.rows + 1) * PUT + pl;   // [tile][step][plane]
+            unsigned t = 1;
+            unsigned so = 0;                  // byte offset of the group's first slot in a U ring (V ring: so / 4)
+            unsigned gU = aUin, gV = aVin;
+
+            // One march step: ring words at rUi / rVi must carry a tag >= tgs, outputs go to rUo / rVo with tag tgs + 1, the next
+            // step's operands are at `ao`.
             auto step = [&](const unsigned tgs, const unsigned rUi, const unsigned rVi, const unsigned rUo, const unsigned rVo, const unsigned ao,
-                            auto odd_c, auto slow_c, auto mail_c) {
-                constexpr bool ODD = decltype(odd_c)::value != 0, SLOW = decltype(slow_c)::value != 0, MAILW = decltype(mail_c)::value != 0;
-#if TTCR_MARCH_STEP_TRACE
-                long long* const tr = (p.trace && tile == p.trace_tile && lane == 0 && (unsigned)(tgs - 201u) < 64u) ? p.trace + (size_t)p.ntiles * 8 + ((lw * 64 + (tgs - 201u)) * 4) : nullptr;
-                if (tr) tr[0] = clock64();
-#endif
+                            auto slow_c, auto mail_c) {
+                constexpr bool SLOW = decltype(slow_c)::value != 0, MAILW = decltype(mail_c)::value != 0;
                 // ---- (1) everything this step reads from shared memory
-                uint2 xu = lds_u2(rUi), xv = lds_u2(rVi);
-                int landed = BIG;
-                if (!ODD) landed = lds_i(a_ctl);
-                const float j2 = lds_f(ao), h2 = lds_f(ao + G::DH), up2 = lds_f(ao + G::DUP), s2 = lds_f(ao + G::DS);
+                uint4 xu = lds_u4(rUi);
+                uint2 xv = lds_u2(rVi);
+                const float2 nj = lds_f2(ao), nup = lds_f2(ao + (unsigned)G::DUP), ns = lds_f2(ao + (unsigned)G::DS);
+                const float nh = lds_f(ao + (unsigned)G::DH);
                 // ---- (2) the upwind neighbours inside the patch
-                float um = __shfl_up_sync(0xffffffffu, nprev, 8);
-                float km = __shfl_up_sync(0xffffffffu, nprev, 1);
-                // (the shuffle is a convergence point: every lane has left the previous step, its ring slots and box rows are free)
-                if (!ODD) sts_i_if(a_myprog, (int)tgs - 1, fl & F_L0);
-                // ---- (3) the one branch: words not there yet / the chunk of the next pair has not landed
-                bool bad = xu.y < tgs || xv.y < tgs;
-                if (!ODD) bad = bad || landed < (int)tgs;
-                if (bad) {
+                float um0 = __shfl_up_sync(0xffffffffu, p0, 8);
+                float um1 = __shfl_up_sync(0xffffffffu, p1, 8);
+                float km0 = __shfl_up_sync(0xffffffffu, p1, 1);
+                // ---- (3) the one branch: words not there yet
+                if (min(min(xu.y, xu.w), xv.y) < tgs) {
                     long long t0 = 0;
+                    const long long tw0 = clock64();
+                    ++wcnt;
                     for (unsigned it = 1;; ++it) {
-                        if (pause_ns) __nanosleep(pause_ns);
-                        xu = lds_u2(rUi); xv = lds_u2(rVi);
-                        bool b2 = xu.y < tgs || xv.y < tgs;
-                        if (!ODD) b2 = b2 || lds_i(a_ctl) < (int)tgs;
-                        if (!b2) break;
-                        if ((it & 255u) == 0) {   // the expensive checks once in a while
+                        xu = lds_u4(rUi); xv = lds_u2(rVi);
+                        if (min(min(xu.y, xu.w), xv.y) >= tgs) break;
+                        if ((it & 15u) == 0) {   // the expensive checks once in a while
                             if (lds_i(a_dead)) { dead = 1; break; }
                             if (t0 == 0) t0 = clock64();
-                            else if (clock64() - t0 > spin_cycles) { give_up(41, (int)tgs, ODD); dead = 1; break; }
+                            else if (clock64() - t0 > spin_cycles) { give_up(41, (int)tgs, (int)min(xu.y, xv.y)); dead = 1; break; }
                         }
                     }
+                    wcyc += clock64() - tw0;
                 }
-#if TTCR_MARCH_STEP_TRACE
-                if (tr) tr[1] = clock64();
-#endif
                 if (SLOW) {
-                    if (fl & F_EU) up = MAXV;
-                    if (fl & F_EV) h = MAXV;
-                    if ((fl & F_FZ) && frozen_bit(frozen, (long long)(pg - tt))) s = QNAN;
+                    if (fl & F_FZ) {   // (the pair shares a mask word: e is even)
+                        const long long e = (long long)(pg - tt);
+                        const unsigned bits = frozen[e >> 5] >> (e & 31);
+                        if (bits & (RK ? 2u : 1u)) s0 = QNAN;
+                        if (bits & (RK ? 1u : 2u)) s1 = QNAN;
+                    }
                 }
-                if (fl & F_U0) um = __uint_as_float(xu.x);
-                if (fl & F_V0) km = __uint_as_float(xv.x);
-                // ---- (4) the update
-                const float tn = godunov(tmin(km, h), tmin(nprev, j), tmin(um, up), s * dx);
-                const float n = fminf(tn, told);   // (NaN -> told: slots that are no node, frozen nodes)
-#if TTCR_MARCH_STEP_TRACE
-                if (tr) tr[2] = clock64() + (long long)(n == 12345.f);   // (depends on n: stamped when the update is done)
-#endif
+                if (fl & F_U0) { um0 = __uint_as_float(xu.x); um1 = __uint_as_float(xu.z); }
+                if (fl & F_V0) km0 = __uint_as_float(xv.x);
+                // ---- (4) the two updates
+                const float tA = godunov(tmin(km0, j1), tmin(p0, j0), tmin(um0, up0), s0 * dx);
+                const float tB = godunov(tmin(p0, hh), tmin(p1, j1), tmin(um1, up1), s1 * dx);
+                const float n0 = fminf(tA, o0), n1 = fminf(tB, o1);   // (NaN -> old: slots that are no node, frozen nodes)
                 // ---- (5) hand-off: warp below / to the right (shared rings), tiles U+1 / V+1 (global mailboxes)
-                sts_u2_if(rUo, __float_as_uint(n), tgs + 1, fl & F_STU);
-                sts_u2_if(rVo, __float_as_uint(n), tgs + 1, fl & F_STV);
+                sts_u4_ifu(rUo, __float_as_uint(n0), tgs + 1, __float_as_uint(n1), tgs + 1, fl & F_STU);
+                sts_u2_ifu(rVo, __float_as_uint(n1), tgs + 1, fl & F_STV);
                 if (MAILW) {
-                    st_mail_if(mu, serial, n, fl & F_OMU);
-                    st_mail_if(mv, serial, n, fl & F_OMV);
+                    st_mail2_if(mu, serial, n0, n1, (int)(fl & F_OMU));
+                    st_mail_if(mv, serial, n1, (int)(fl & F_OMV));
                     mu += TW; mv += PUT;
                 }
                 // ---- (6) result, change sum, rotate the operands
-                stg_f_stream_if(pg, n, n < told ? 1 : 0);
-                pg += RJ ? -(long long)p.d.kpad : (long long)p.d.kpad;
-                acc += told - n;
-                nprev = n; told = j;
-                j = j2; h = h2; up = up2; s = s2;
-#if TTCR_MARCH_STEP_TRACE
-                if (tr) tr[3] = clock64();
-#endif
+                stg_f2_stream_if(pg, RK ? n1 : n0, RK ? n0 : n1, (n0 < o0 || n1 < o1) ? 1 : 0);
+                pg += rowstride;
+                acc += (o0 - n0) + (o1 - n1);
+                p0 = n0; p1 = n1; o0 = j0; o1 = j1;
+                j0 = RK ? nj.y : nj.x; j1 = RK ? nj.x : nj.y;
+                up0 = RK ? nup.y : nup.x; up1 = RK ? nup.x : nup.y;
+                s0 = RK ? ns.y : ns.x; s1 = RK ? ns.x : ns.y;
+                hh = nh;
             };
-            const unsigned rBend = aJ0 + NCH * L::CHB;
-            auto pair = [&](auto slow_c, auto mail_c) {
-                step(tg, rU, rV, rU + OUT_U + SLOTB, rV + OUT_V + SLOTB, rB + (unsigned)G::DR, IntC<0>(), slow_c, mail_c);
-                // slots of the next pair (rings are RINGB-aligned: wrap inside the low bits), chunk slot of the next pair
-                const unsigned rU2 = ring_next<RINGB, 2 * SLOTB>(rU), rV2 = ring_next<RINGB, 2 * SLOTB>(rV);
-                unsigned rB2 = rB + L::CHB;
-                if (rB2 == rBend) rB2 = aJ0;
-                step(tg + 1, rU + SLOTB, rV + SLOTB, rU2 + OUT_U, rV2 + OUT_V, rB2, IntC<1>(), slow_c, mail_c);
-                rU = rU2; rV = rV2; rB = rB2;
-                tg += 2;
+            auto group = [&](auto slow_c, auto mail_c) {
+                // chunk slot of the next group (and the parity of its "full" phase: it flips when the ring wraps)
+                unsigned nslot = cslot + 1, npar = cpar;
+                if (nslot == NCH) { nslot = 0; npar ^= 1u; }
+                const unsigned sbn = sbase + nslot * L::CHB;
+                const unsigned so_n = (so + C * USLOT) & (unsigned)(URING - 1);
+                const unsigned gUn = aUin + so_n, gVn = aVin + (so_n >> 2);
+#pragma unroll
+                for (int r = 0; r < C - 1; ++r)
+                    step(t + r, gU + r * USLOT, gV + r * VSLOT, gU + OUT_U + (r + 1) * USLOT, gV + OUT_V + (r + 1) * VSLOT,
+                         rB + (unsigned)((r + 1) * G::DR), slow_c, mail_c);
+                wait_full(sbn + L::OFF_FULL, npar, 42);   // the chunk the last step of the group takes the next operands from
+                step(t + C - 1, gU + (C - 1) * USLOT, gV + (C - 1) * VSLOT, gUn + OUT_U, gVn + OUT_V, sbn + toff, slow_c, mail_c);
+                // every lane has read the group's words and the chunk's last row (its values were used by the update above)
+                __syncwarp();
+                mbar_arrive_ifu(sb + L::OFF_EMPTY, fl & F_L0);
+                t += C;
+                sts_i_ifu(a_myprog, (int)t - 1, fl & F_L0);
+                sb = sbn; rB = sbn + toff; cslot = nslot; cpar = npar;
+                so = so_n; gU = gUn; gV = gVn;
                 deadw = __any_sync(0xffffffffu, dead);
-#if TTCR_MARCH_STEP_TRACE
-                if (p.trace && threadIdx.x == 0) {   // quarter times of the march
-                    const unsigned q = ((unsigned)nA / 8u) * 2u;
-                    if (tg == q + 1) p.trace[tile * 8 + 2] = gtime();
-                    if (tg == 2 * q + 1) p.trace[tile * 8 + 3] = gtime();
-                    if (tg == 3 * q + 1) p.trace[tile * 8 + 4] = gtime();
-                }
-#endif
             };
             auto march = [&](auto mail_c) {
 #pragma unroll 1
                 for (int seg = 0; seg < 3; ++seg) {
-                    const unsigned e = seg == 0 ? ts0 : (seg == 1 ? ts1 : tg_end);
+                    const unsigned e = seg == 0 ? ts0 : (seg == 1 ? ts1 : t_end);
                     if (seg == 1) {
-                        while (tg < e && !deadw) pair(IntC<1>(), mail_c);
+                        while (t < e && !deadw) group(IntC<1>(), mail_c);
                     } else {
-                        while (tg < e && !deadw) pair(IntC<0>(), mail_c);
+                        while (t < e && !deadw) group(IntC<0>(), mail_c);
                     }
                 }
             };
             if (mail_warp) march(IntC<1>()); else march(IntC<0>());
-            sts_i_if(a_myprog, BIG, fl & F_L0);   // release anybody still waiting for this warp
-            double dacc = (double)acc;
+            // the last chunk (only its first row was read, by the prefetch of the last step) goes back to the loader, too
+            if (!deadw) {
+                __syncwarp();
+                mbar_arrive_ifu(sb + L::OFF_EMPTY, fl & F_L0);
+                if (++cslot == NCH) { cslot = 0; cpar ^= 1u; }
+            }
+            sts_i_ifu(a_myprog, BIG, fl & F_L0);   // release an importer still waiting for this warp
+            double dacc = ghost ? 0.0 : (double)acc;   // (NaN - NaN in the ghosts)
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) dacc += __shfl_xor_sync(0xffffffffu, dacc, o);
             if (lane == 0) p.partial[(size_t)tile * NW + lw] = dacc;
-            if (p.trace && threadIdx.x == 0) p.trace[tile * 8 + 5] = gtime();
+            if (p.trace && lane == 0) {
+                if (lw == 0) { p.trace[tile * 16 + 5] = gtime(); p.trace[tile * 16 + 2] = wcyc; p.trace[tile * 16 + 3] = fcyc; p.trace[tile * 16 + 4] = wcnt; }
+                if (lw == NW - 1) p.trace[tile * 16 + 6] = wcyc;
+            }
         }
     }
 }
@@ -570,10 +573,10 @@ inline void march_free(MarchState& s) {
     s = MarchState{};
 }
 
-template <int WU, int WV, int NCH, int D>
+template <int WU, int WV, int NCH>
 inline int march_launch(TileState& s, MarchState& ms, const TileOptions& o, int sm_count, const SweepView& w, const Dims& d, float* tt,
                         const float* slo, const uint32_t* frozen, const FrozenBox& fb, float dx, double* d_change, cudaStream_t st) {
-    using L = MarchLayout<WU, WV, NCH, D>;
+    using L = MarchLayout<WU, WV, NCH>;
     constexpr int PUT = L::PUT, TW = L::TW, NW = L::NW;
     MarchParams p;
     p.w = w; p.d = d; p.fb = fb;
@@ -581,27 +584,22 @@ inline int march_launch(TileState& s, MarchState& ms, const TileOptions& o, int 
     p.nU = (w.nu + PUT - 1) / PUT;
     p.ntiles = p.nU * p.nV;
     p.spin_cycles = o.spin_limit << 9;
-    static const int pause_env = getenv("TTCR_B200_PAUSE") ? atoi(getenv("TTCR_B200_PAUSE")) : 0;
-    p.pause_ns = (unsigned)pause_env;
-    static const int lpause_env = getenv("TTCR_B200_LPAUSE") ? atoi(getenv("TTCR_B200_LPAUSE")) : 0;
-    p.lpause_ns = (unsigned)lpause_env;
     static const int pf_env = getenv("TTCR_B200_PF") ? atoi(getenv("TTCR_B200_PF")) : 0;
     p.pf_chunks = pf_env;
-    p.trace_tile = getenv("TTCR_B200_TRACE_TILE") ? atoi(getenv("TTCR_B200_TRACE_TILE")) : 0;
     p.ctrl = s.d_ctrl;
     const char* trace_path = getenv("TTCR_B200_TRACE");
     if (trace_path && ms.trace_cap < p.ntiles) {
         cudaFree(ms.d_trace);
-        TCK(cudaMalloc(&ms.d_trace, ((size_t)p.ntiles * 8 + 32 * 64 * 4) * sizeof(long long)));
+        ms.d_trace = nullptr;
+        TCK(cudaMalloc(&ms.d_trace, (size_t)p.ntiles * 16 * sizeof(long long)));
         ms.trace_cap = p.ntiles;
     }
     p.trace = trace_path ? ms.d_trace : nullptr;
-    const int rows = d.nj + TW + 2 * L::MARGIN + 8;
+    const int rows = d.nj + TW + PUT + 2 * L::C + 8;
     if (!ms.d_mbu || ms.mb_tiles < p.ntiles || ms.mb_rows != rows || ms.mb_tw != TW || ms.mb_put != PUT) {
         TCK(cudaStreamSynchronize(st));
-        auto occ_keep = ms.occ;
-        march_free(ms);
-        ms.occ = occ_keep;
+        cudaFree(ms.d_mbu); cudaFree(ms.d_mbv); cudaFree(ms.d_partial); cudaFree(ms.d_order);
+        ms.d_mbu = ms.d_mbv = nullptr; ms.d_partial = nullptr; ms.d_order = nullptr;
         ms.mb_rows = rows; ms.mb_tiles = p.ntiles; ms.mb_tw = TW; ms.mb_put = PUT;
         const size_t nu = (size_t)ms.mb_tiles * ms.mb_rows * TW, nv = (size_t)ms.mb_tiles * ms.mb_rows * PUT;
         TCK(cudaMalloc(&ms.d_mbu, nu * 8));
@@ -612,11 +610,6 @@ inline int march_launch(TileState& s, MarchState& ms, const TileOptions& o, int 
         TCK(cudaMemsetAsync(ms.d_mbv, 0, nv * 8, st));
         ms.serial = 0;
         ms.order_key = -1;
-        if (trace_path) {
-            TCK(cudaMalloc(&ms.d_trace, ((size_t)p.ntiles * 8 + 32 * 64 * 4) * sizeof(long long)));
-            ms.trace_cap = p.ntiles;
-            p.trace = ms.d_trace;
-        }
     }
     MarchMail mail;
     mail.u = ms.d_mbu; mail.v = ms.d_mbv; mail.rows = ms.mb_rows;
@@ -627,7 +620,7 @@ inline int march_launch(TileState& s, MarchState& ms, const TileOptions& o, int 
         mail.serial = ms.serial = 1;
     }
     p.order = ms.d_order; p.partial = ms.d_partial;
-    const int key = 6000000 + PUT * 10000 + TW * 40 + w.vlo;
+    const int key = 7000000 + PUT * 10000 + TW * 40 + w.vlo;
     if (ms.order_key != key || ms.ntiles != p.ntiles) {
         // ticket order: a linear extension of (U-1,V) < (U,V), (U,V-1) < (U,V), sorted by the step at which a tile can start
         std::vector<std::pair<long long, int>> k(p.ntiles);
@@ -652,7 +645,7 @@ inline int march_launch(TileState& s, MarchState& ms, const TileOptions& o, int 
         for (auto& e : ms.maps)
             if (e.first == kk) return e.second;
         if (ms.maps.size() > 64) ms.maps.clear();
-        ms.maps.push_back({kk, make_tile5_map(a, d, minus, L::BW, 2, bp)});
+        ms.maps.push_back({kk, make_tile5_map(a, d, minus, L::BW, L::C, bp, true)});
         return ms.maps.back().second;
     };
     const CUtensorMap tmT = get_map(tt, PUT + 1);
@@ -671,36 +664,33 @@ inline int march_launch(TileState& s, MarchState& ms, const TileOptions& o, int 
         }
         int per_sm = occ;
         if (o.ctas_per_sm > 0) per_sm = std::min(per_sm, o.ctas_per_sm);
-        const int grid = std::min(p.ntiles, per_sm * sm_count);
+        int grid = std::min(p.ntiles, per_sm * sm_count);
+        if (o.max_ctas > 0) grid = std::min(grid, o.max_ctas);
         kern<<<grid, L::NT, L::BYTES, st>>>(tmT, tmS, p, mail, tt, frozen, dx);
     };
     switch (variant) {
-        case 0: run(k_sweep_march<WU, WV, NCH, D, false, false, false>); break;
-        case 1: run(k_sweep_march<WU, WV, NCH, D, true, false, false>); break;
-        case 2: run(k_sweep_march<WU, WV, NCH, D, false, true, false>); break;
-        case 3: run(k_sweep_march<WU, WV, NCH, D, true, true, false>); break;
-        case 4: run(k_sweep_march<WU, WV, NCH, D, false, false, true>); break;
-        case 5: run(k_sweep_march<WU, WV, NCH, D, true, false, true>); break;
-        case 6: run(k_sweep_march<WU, WV, NCH, D, false, true, true>); break;
-        default: run(k_sweep_march<WU, WV, NCH, D, true, true, true>); break;
+        case 0: run(k_sweep_march<WU, WV, NCH, false, false, false>); break;
+        case 1: run(k_sweep_march<WU, WV, NCH, true, false, false>); break;
+        case 2: run(k_sweep_march<WU, WV, NCH, false, true, false>); break;
+        case 3: run(k_sweep_march<WU, WV, NCH, true, true, false>); break;
+        case 4: run(k_sweep_march<WU, WV, NCH, false, false, true>); break;
+        case 5: run(k_sweep_march<WU, WV, NCH, true, false, true>); break;
+        case 6: run(k_sweep_march<WU, WV, NCH, false, true, true>); break;
+        default: run(k_sweep_march<WU, WV, NCH, true, true, true>); break;
     }
     k_sum_partials<<<1, 256, 0, st>>>(ms.d_partial, p.ntiles * NW, d_change);
     TCK(cudaMemcpyAsync(s.h_abort, s.d_ctrl + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
     TCK(cudaGetLastError());
     if (trace_path) {
-        std::vector<long long> h((size_t)p.ntiles * 8 + 32 * 64 * 4);
+        std::vector<long long> h((size_t)p.ntiles * 16);
         TCK(cudaStreamSynchronize(st));
         TCK(cudaMemcpy(h.data(), ms.d_trace, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
         FILE* f = fopen(trace_path, "ab");
         if (f) {
-            const int hdr[4] = {p.ntiles, p.nU, p.nV, PUT};
+            const int hdr[4] = {p.ntiles, p.nU, p.nV, PUT + 1000 * 16};   // (record length in the thousands)
             fwrite(hdr, sizeof(int), 4, f);
-            fwrite(h.data(), sizeof(long long), (size_t)p.ntiles * 8, f);
+            fwrite(h.data(), sizeof(long long), h.size(), f);
             fclose(f);
-        }
-        if (const char* sp = getenv("TTCR_B200_TRACE_STEPS")) {   // [warp][step 200..263][4 stamps] of tile 0 (step-trace builds)
-            FILE* g = fopen(sp, "ab");
-            if (g) { fwrite(h.data() + (size_t)p.ntiles * 8, sizeof(long long), 32 * 64 * 4, g); fclose(g); }
         }
     }
     return 2;
@@ -717,10 +707,9 @@ inline int march_sweep(TileState&, MarchState&, const TileOptions&, int, const S
 template <>
 inline int march_sweep<float>(TileState& s, MarchState& ms, const TileOptions& o, int sm_count, const SweepView& w, const Dims& d, float* tt,
                               const float* slo, const uint32_t* frozen, const FrozenBox& fb, float dx, double* d_change, cudaStream_t st) {
-    // <warps along u, warps along v, chunk slots of the box ring, depth of the word rings>
-    if (o.depth == 4) return march_launch<4, 4, 4, 16>(s, ms, o, sm_count, w, d, tt, slo, frozen, fb, dx, d_change, st);
-    if (o.depth == 7) return march_launch<4, 4, 7, 16>(s, ms, o, sm_count, w, d, tt, slo, frozen, fb, dx, d_change, st);
-    return march_launch<4, 4, 6, 16>(s, ms, o, sm_count, w, d, tt, slo, frozen, fb, dx, d_change, st);                                     // 16 planes x 32 lanes
+    // <warps along u, warps along v, chunk slots of the box ring>; tile = 4 WU planes x 16 WV lanes
+    if (o.warps == 12) return march_launch<6, 2, 5>(s, ms, o, sm_count, w, d, tt, slo, frozen, fb, dx, d_change, st);
+    return march_launch<4, 2, 6>(s, ms, o, sm_count, w, d, tt, slo, frozen, fb, dx, d_change, st);
 }
 
 }  // namespace ttcrb200

@@ -53,6 +53,7 @@ struct TileOptions {
     int rows = 1;          // u rows per thread (R): 1 or 2
     int depth = 8;         // register queue depth (rows of loads in flight): 4 or 8
     long long spin_limit = 1ll << 22;   // polls before a wait is declared dead
+    int max_ctas = 0;      // k_sweep_march: cap on the grid size (0 = none); tests use it to make every CTA run several tiles
 };
 
 struct TileState {

@@ -781,7 +781,7 @@ __global__ void __launch_bounds__((NU + 2) * 32, ((NU <= 4 || (C == 2 && R == 1)
 
 // ---- host side -----------------------------------------------------------------------------------
 // 3-D map with the plane skew built in: plane z starts (qs -+ 1) rows after plane z-1
-inline CUtensorMap make_tile5_map(const void* base, const Dims& d, bool minus, int bw, int br, int bp) {
+inline CUtensorMap make_tile5_map(const void* base, const Dims& d, bool minus, int bw, int br, int bp, bool nan_fill = false) {
     CUtensorMap m;
     // "plus" map: row = y + z * (qs + 1) would need negative y for the rows of high planes; the base is moved ni rows
     // down instead and every y carries +ni (addresses of in-bounds coordinates the kernel uses stay inside the array)
@@ -792,7 +792,7 @@ inline CUtensorMap make_tile5_map(const void* base, const Dims& d, bool minus, i
     const cuuint32_t estr[3] = {1, 1, 1};
     const CUresult r = tmap_encoder()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base), gdim, gstr, box, estr,
                                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
-                                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                                      nan_fill ? CU_TENSOR_MAP_FLOAT_OOB_FILL_NAN_REQUEST_ZERO_FMA : CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) throw std::runtime_error("cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
     return m;
 }
