@@ -58,6 +58,7 @@ struct MarchParams {
     double* partial;   // [tile][NW]
     long long* trace;  // [tile][16] or nullptr
     int pf_chunks;     // L2 prefetch distance of the loader, in chunks beyond the box ring (0 = off)
+    unsigned spin_polls, sleep_ns;   // a waiting compute warp polls this often, then sleeps this long between polls
 };
 
 template <int WU, int WV, int NCH>
@@ -160,8 +161,38 @@ __device__ __forceinline__ void mbar_arrive_ifu(unsigned a, unsigned on) {
     asm volatile("{\n\t.reg .pred q;\n\t.reg .b64 t;\n\tsetp.ne.u32 q, %1, 0;\n\t@q mbarrier.arrive.shared::cta.b64 t, [%0];\n\t}" ::"r"(a), "r"(on) : "memory");
 }
 
+
+// Cold paths of a march step, out of line so that the hot loop stays small (it is unrolled four times in four variants).
+// Wait for the ring words of step `tgs`: 0 = there, 1 = another warp gave up, 2 = timeout.
+__device__ __noinline__ int march_wait_words(unsigned rUi, unsigned rVi, unsigned tgs, unsigned a_dead, long long spin_cycles, unsigned spin_polls,
+                                             unsigned sleep_ns) {
+    long long t0 = 0;
+    for (unsigned it = 1;; ++it) {
+        const uint4 xu = lds_u4(rUi);
+        const uint2 xv = lds_u2(rVi);
+        if (min(min(xu.y, xu.w), xv.y) >= tgs) return 0;
+        // a word that is a step late shows up within ~10 polls; a tile that waits for its neighbours to START waits for many
+        // microseconds and should not take issue slots from the warps that work
+        if (it > spin_polls) __nanosleep(sleep_ns);
+        if ((it & 15u) == 0) {   // the expensive checks once in a while
+            if (lds_i(a_dead)) return 1;
+            if (t0 == 0) t0 = clock64();
+            else if (clock64() - t0 > spin_cycles) return 2;
+        }
+    }
+}
+// Wait for a chunk to land (phase `par` of its "full" barrier): same return values.
+__device__ __noinline__ int march_wait_full(unsigned a_full, unsigned par, unsigned a_dead, long long spin_cycles) {
+    const long long t0 = clock64();
+    while (!mbar_test(a_full, par)) {
+        if (lds_i(a_dead)) return 1;
+        if (clock64() - t0 > spin_cycles) return 2;
+    }
+    return 0;
+}
+
 template <int WU, int WV, int NCH, bool RI, bool RJ, bool RK>
-__global__ void __launch_bounds__((WU * WV + 3) * 32, 1)
+__global__ void __launch_bounds__((WU * WV + 3) * 32, (MarchLayout<WU, WV, NCH>::BYTES <= 112 * 1024 ? 2 : 1))
 k_sweep_march(const __grid_constant__ CUtensorMap tmT, const __grid_constant__ CUtensorMap tmS, MarchParams p, MarchMail mail,
               float* __restrict__ tt, const uint32_t* __restrict__ frozen, float dx) {
     using L = MarchLayout<WU, WV, NCH>;
@@ -293,6 +324,7 @@ k_sweep_march(const __grid_constant__ CUtensorMap tmT, const __grid_constant__ C
                 n_got += got;
                 if (done) break;
                 if (got) { idle = 0; continue; }
+                if (idle >= 3) __nanosleep(p.sleep_ns);   // (nothing to deliver for three round trips: the neighbours are far behind)
                 if ((++idle & 15u) == 0) {   // nothing moved for a while: is the march still alive?
                     if (lds_i(a_dead)) break;
                     if (idle == 16) t0 = clock64();
@@ -395,19 +427,15 @@ k_sweep_march(const __grid_constant__ CUtensorMap tmT, const __grid_constant__ C
             const float QNAN = __int_as_float(0x7fc00000);
 
             int dead = 0;
-            long long wcyc = 0, fcyc = 0, wcnt = 0;   // (trace) cycles spent waiting for ring words / for a chunk to land
             auto give_up = [&](int why, int x, int a) {
                 if (atomicCAS(&p.ctrl[1], 0, why) == 0) { p.ctrl[2] = tile; p.ctrl[3] = x; p.ctrl[4] = a; p.ctrl[5] = lw; p.ctrl[6] = lane; }
                 sts_i(a_dead, 1);
             };
             auto wait_full = [&](unsigned a_full, unsigned par, int why) {
-                if (mbar_test(a_full, par)) return;
-                const long long t0 = clock64();
-                while (!mbar_test(a_full, par)) {
-                    if (lds_i(a_dead)) { dead = 1; break; }
-                    if (clock64() - t0 > spin_cycles) { give_up(why, (int)cslot, (int)par); dead = 1; break; }
-                }
-                fcyc += clock64() - t0;
+                if (__builtin_expect(mbar_test(a_full, par), 1)) return;
+                const int st = march_wait_full(a_full, par, a_dead, spin_cycles);
+                if (st == 2) give_up(why, (int)cslot, (int)par);
+                if (st) dead = 1;
             };
             // ---- prologue: first chunk of the tile, operands of step 1
             unsigned sb = sbase + cslot * L::CHB;   // chunk slot the current group reads
@@ -455,20 +483,11 @@ k_sweep_march(const __grid_constant__ CUtensorMap tmT, const __grid_constant__ C
                 float um1 = __shfl_up_sync(0xffffffffu, p1, 8);
                 float km0 = __shfl_up_sync(0xffffffffu, p1, 1);
                 // ---- (3) the one branch: words not there yet
-                if (min(min(xu.y, xu.w), xv.y) < tgs) {
-                    long long t0 = 0;
-                    const long long tw0 = clock64();
-                    ++wcnt;
-                    for (unsigned it = 1;; ++it) {
-                        xu = lds_u4(rUi); xv = lds_u2(rVi);
-                        if (min(min(xu.y, xu.w), xv.y) >= tgs) break;
-                        if ((it & 15u) == 0) {   // the expensive checks once in a while
-                            if (lds_i(a_dead)) { dead = 1; break; }
-                            if (t0 == 0) t0 = clock64();
-                            else if (clock64() - t0 > spin_cycles) { give_up(41, (int)tgs, (int)min(xu.y, xv.y)); dead = 1; break; }
-                        }
-                    }
-                    wcyc += clock64() - tw0;
+                if (__builtin_expect(min(min(xu.y, xu.w), xv.y) < tgs, 0)) {
+                    const int st = march_wait_words(rUi, rVi, tgs, a_dead, spin_cycles, p.spin_polls, p.sleep_ns);
+                    if (st == 2) give_up(41, (int)tgs, (int)min(xu.y, xv.y));
+                    if (st) dead = 1;
+                    xu = lds_u4(rUi); xv = lds_u2(rVi);
                 }
                 if (SLOW) {
                     if (fl & F_FZ) {   // (the pair shares a mask word: e is even)
@@ -548,8 +567,7 @@ k_sweep_march(const __grid_constant__ CUtensorMap tmT, const __grid_constant__ C
             for (int o = 16; o > 0; o >>= 1) dacc += __shfl_xor_sync(0xffffffffu, dacc, o);
             if (lane == 0) p.partial[(size_t)tile * NW + lw] = dacc;
             if (p.trace && lane == 0) {
-                if (lw == 0) { p.trace[tile * 16 + 5] = gtime(); p.trace[tile * 16 + 2] = wcyc; p.trace[tile * 16 + 3] = fcyc; p.trace[tile * 16 + 4] = wcnt; }
-                if (lw == NW - 1) p.trace[tile * 16 + 6] = wcyc;
+                if (lw == 0) p.trace[tile * 16 + 5] = gtime();
             }
         }
     }
@@ -586,6 +604,9 @@ inline int march_launch(TileState& s, MarchState& ms, const TileOptions& o, int 
     p.spin_cycles = o.spin_limit << 9;
     static const int pf_env = getenv("TTCR_B200_PF") ? atoi(getenv("TTCR_B200_PF")) : 0;
     p.pf_chunks = pf_env;
+    static const int spin_env = getenv("TTCR_B200_SPIN") ? atoi(getenv("TTCR_B200_SPIN")) : 24;
+    static const int sleep_env = getenv("TTCR_B200_SLEEP") ? atoi(getenv("TTCR_B200_SLEEP")) : 400;
+    p.spin_polls = (unsigned)spin_env; p.sleep_ns = (unsigned)sleep_env;
     p.ctrl = s.d_ctrl;
     const char* trace_path = getenv("TTCR_B200_TRACE");
     if (trace_path && ms.trace_cap < p.ntiles) {
@@ -709,6 +730,7 @@ inline int march_sweep<float>(TileState& s, MarchState& ms, const TileOptions& o
                               const float* slo, const uint32_t* frozen, const FrozenBox& fb, float dx, double* d_change, cudaStream_t st) {
     // <warps along u, warps along v, chunk slots of the box ring>; tile = 4 WU planes x 16 WV lanes
     if (o.warps == 12) return march_launch<6, 2, 5>(s, ms, o, sm_count, w, d, tt, slo, frozen, fb, dx, d_change, st);
+    if (o.depth == 3) return march_launch<4, 2, 3>(s, ms, o, sm_count, w, d, tt, slo, frozen, fb, dx, d_change, st);   // two CTAs per SM
     return march_launch<4, 2, 6>(s, ms, o, sm_count, w, d, tt, slo, frozen, fb, dx, d_change, st);
 }
 
