@@ -15,9 +15,14 @@ e2e     same metric through the public API Grid3d.raytrace(src, rcv, slowness): 
 roofline  dominant kernel = the directional-sweep kernel; 12 algorithmic bytes per node per launch
 cpu_baseline  the reference's own CPU FSM (oracle/_ref, built from /root/reference) on a bounded sample
 
-With N > 1 (torchrun, one rank per GPU) every rank solves its own source of the same model (weak
-scaling, source-parallel; no collective in the timed region; the model is broadcast once over NCCL).
---impl reference times the reference's own CPU implementation (rank 0 only).
+With N > 1 (torchrun, one rank per GPU) every rank solves its own source of the same model (weak scaling,
+source-parallel).  The device-resident arm has no collective in its timed region (the model is resident); the e2e arm
+is raytrace_sharded(): the model sits in pinned memory on rank 0 only, is uploaded once and broadcast over NCCL, the
+receiver times are all-gathered -- every step, inside the timed region.
+detail.config4 (every N): BASELINE.json configs[3], 511^3 cells -> Grid3Drcfs averaging, 64 sources sharded over the
+ranks through raytrace_sharded (strong scaling; model on rank 0, broadcast + all-gather inside its wall-clock time).
+--impl reference times the reference's own CPU implementation on rank 0: 1 thread for 1 source; for --gpus N > 1 the N
+sources of the N-GPU run through the reference's own threaded Grid3D::raytrace on min(cores, N) threads.
 """
 from __future__ import annotations
 
@@ -38,7 +43,7 @@ METRIC = "Mnodes/s (grid nodes x sweep-iters / s) on 512^3 FSM"
 UNIT = "Mnodes/s"
 BYTES_PER_NODE_SWEEP = 12.0   # tt read + tt write + slowness read, fp32
 CPU_SAMPLE_N = 192            # nodes per side of the bounded CPU sample
-KERNEL_NAMES = {1: "k_sweep_plane", 2: "k_sweep_tile", 3: "k_sweep_tile3", 4: "k_sweep_tile4", 5: "k_sweep_patch"}
+KERNEL_NAMES = {1: "k_sweep_plane", 2: "k_sweep_tile", 6: "k_sweep_planes_coop", 7: "k_sweep_march"}
 
 
 def gradient_model(n, dtype=np.float32):
@@ -168,20 +173,55 @@ def cpu_reference(n, steps, warmup, dtype=np.float32):
     return n ** 3 * 8 * niter / sec / 1e6, sec, kind, niter
 
 
+def cpu_reference_multi(n, n_src, steps, warmup, dtype=np.float32):
+    """The reference's own threaded multi-source fan-out (Grid3D::raytrace over a vector of sources, ttcr/Grid3D.h:810-853:
+    nt = min(n_threads, n_sources) worker threads, one traveltime slot each) on an n^3 sample: the sources bench.py gives
+    to ranks 0 .. n_src-1.  Returns (aggregate Mnodes/s, s/step, threads, iterations of source 0)."""
+    import oracle as O
+    x, s = gradient_model(n, dtype)
+    xt = x.astype(dtype)
+    dx = float(xt[1] - xt[0])
+    srcs = np.vstack([source_for_rank(x, r) for r in range(n_src)])
+    nt = max(1, min(os.cpu_count() or 1, n_src))
+    g = O.RefGrid(n - 1, n - 1, n - 1, dx, weno=False, dtype=dtype, eps=1e-5, maxit=50, n_threads=nt)
+    g.set_slowness(O.to_cxx(s))
+    times = []
+    for k in range(warmup + steps):
+        _, sec = g.raytrace_multi(srcs, 0.0, np.zeros((1, 3)))
+        if k >= warmup:
+            times.append(sec)
+    niter = g.niter()[0]
+    g.close()
+    sec = float(np.mean(times))
+    # (sources away from the corner may need another iteration; slot 0's count is used for all: the same approximation the
+    # GPU arm does not need, since it counts its sweeps)
+    return n ** 3 * 8 * niter * n_src / sec / 1e6, sec, nt, niter
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
+    import oracle as O
     n = CPU_SAMPLE_N
     t0 = time.perf_counter()
-    v, sec, kind, niter = cpu_reference(n, args.steps, args.warmup)
+    n_src = max(1, args.gpus)
+    if n_src > 1 and O.have_ref():
+        v, sec, cores, niter = cpu_reference_multi(n, n_src, args.steps, args.warmup)
+        kind = "reference"
+        what = (f"{n}^3-node sample of the workload (same model, eps), the {n_src} sources of the {n_src}-GPU run through the "
+                f"reference's own threaded Grid3D::raytrace (ttcr/Grid3D.h:810-853) on {cores} threads, Grid3Drnfs<float>, "
+                f"{niter} iterations")
+    else:
+        v, sec, kind, niter = cpu_reference(n, args.steps, args.warmup)
+        cores = 1
+        what = (f"{n}^3-node sample of the workload (same model, source, eps), Grid3Drnfs<float>, {niter} iterations, "
+                f"1 thread: the reference has no intra-source parallelism")
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args.n, extra={"sample": f"{n}^3"}),
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": 1, "kind": kind,
-                         "sample": f"{n}^3-node sample of the workload (same model, source, eps), Grid3Drnfs<float>, "
-                                   f"{niter} iterations, 1 thread: the reference has no intra-source parallelism"},
+        "config": workload_config(args.n, extra={"sample": f"{n}^3", "sources": n_src}),
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": what},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "wall_s": time.perf_counter() - t0,
     }
@@ -198,6 +238,46 @@ def workload_config(n, extra=None):
     return c
 
 
+def config4_side(torch, dist, rank, world, local_rank, n_src):
+    """BASELINE.json configs[3] as SURVEY section 8(d) words it: 512^3 nodes / 511^3 cells (Grid3Drcfs), cell slowness
+    1/(1+0.1 z_c) with 5 % lognormal noise (default_rng(12345)), `n_src` of the 64 sources uniform in [0.5,19.5]^3 from the
+    same generator, sharded source-parallel over the ranks, two slots per GPU.  Wall clock around raytrace_sharded()."""
+    from ttcr_b200 import Grid3d
+    from ttcr_b200.distributed import raytrace_sharded
+    n = 512
+    x = np.linspace(0.0, 20.0, n)
+    sc = None
+    srcs = torch.zeros((64, 3), dtype=torch.float64, device="cuda")
+    if rank == 0:
+        rng = np.random.default_rng(12345)
+        zc = 0.5 * (x[1:] + x[:-1])
+        sc = ((1.0 / (1.0 + 0.1 * zc))[None, None, :] * np.exp(0.05 * rng.standard_normal((n - 1, n - 1, n - 1), dtype=np.float32))).astype(np.float32)
+        sc = torch.from_numpy(sc).pin_memory().numpy()
+        srcs = torch.from_numpy(rng.uniform(0.5, 19.5, (64, 3))).cuda()
+    if world > 1:
+        dist.broadcast(srcs, src=0)
+    src = srcs.cpu().numpy()[:n_src]
+    rcv = np.array([[1.0, 1.0, 1.0], [19.0, 19.0, 19.0], [10.0, 10.0, 0.0], [3.3, 16.2, 8.7]])
+    g4 = Grid3d(x, x, x, n_threads=2, cell_slowness=1, method="FSM", tt_from_rp=0, eps=1e-5, maxit=50, weno=0,
+                dtype=np.float32, device=local_rank)
+    raytrace_sharded(g4, src[:2 * world], rcv, slowness=sc)          # warm-up: allocations, first launches
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    tt, it = raytrace_sharded(g4, src, rcv, slowness=sc)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    dt = time.perf_counter() - t0
+    g4.close()
+    sweeps = 8 * int(it.sum())
+    return {"workload": f"512^3 nodes / 511^3 cells (Grid3Drcfs), {len(src)} sources sharded over {world} GPU(s), 2 slots per GPU",
+            "scaling": "strong", "seconds": dt, "value": float(n) ** 3 * sweeps / dt / 1e6, "unit": UNIT,
+            "niter_min_max": [int(it[:, 0].min()), int(it[:, 0].max())],
+            "includes": "pinned upload of the 511^3 cells on rank 0, NCCL broadcast, cell-to-node averaging, solves, all-gather"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -206,6 +286,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n", type=int, default=512, help="nodes per side (512 = the headline workload)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--c4-sources", type=int, default=64, help="sources of the configs[3] side measurement (0 = skip)")
     ap.add_argument("--opt", action="append", default=[], help="library option key=value (development)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
@@ -270,24 +351,38 @@ def main():
     clk = clocks.stop()
 
     # ---- end-to-end arm: public API, pinned host slowness in, receiver traveltimes out ---------------
-    if rank == 0:
-        s_pinned = torch.from_numpy(s_host).pin_memory()
-    else:
-        s_pinned = torch.from_numpy(g.get_slowness()).pin_memory()
-    s_np = s_pinned.numpy()
+    # 1 GPU:  Grid3d.raytrace(src, rcv, slowness) with the model in pinned host memory.
+    # N GPUs: raytrace_sharded(grid, sources, rcv, slowness): the model lives on rank 0 only and is uploaded ONCE per step,
+    #         broadcast over NCCL (chunk-pipelined with the upload), every rank solves its source, the receiver times are
+    #         all-gathered -- all inside the timed region.
+    from ttcr_b200.distributed import raytrace_sharded
+    s_np = torch.from_numpy(s_host).pin_memory().numpy() if rank == 0 else None
     src4 = np.concatenate([[0.0], src[0]]).reshape(1, 4)
+    all_src = np.vstack([source_for_rank(x, r) for r in range(world)])
+
+    def e2e_step():
+        if world == 1:
+            out = g.raytrace(src4, rcv, s_np)
+            return out, g.get_stats()["sweeps"]
+        out, it = raytrace_sharded(g, all_src, rcv, slowness=s_np)
+        return out, 8 * int(it[rank].sum())
+
     for _ in range(min(warm, 2)):
-        g.raytrace(src4, rcv, s_np)
+        e2e_step()
     barrier()
     t_e2e = time.perf_counter()
     e2e_sweeps = 0
     for _ in range(args.steps):
-        tt = g.raytrace(src4, rcv, s_np)
-        e2e_sweeps += g.get_stats()["sweeps"]
+        tt, sw = e2e_step()
+        e2e_sweeps += sw
     barrier()
     e2e_ms = (time.perf_counter() - t_e2e) * 1e3
-    h2d = int(s_np.nbytes + src4.astype(np.float32).nbytes + rcv.astype(np.float32).nbytes)
-    d2h = int(tt.astype(np.float32).nbytes)
+    s_bytes = n ** 3 * 4
+    h2d = int(s_bytes + src4.astype(np.float32).nbytes + rcv.astype(np.float32).nbytes) if rank == 0 else int(
+        src4.astype(np.float32).nbytes + rcv.astype(np.float32).nbytes)
+    d2h = int(np.asarray(tt).astype(np.float32).nbytes)
+    if s_np is None:
+        s_np = g.get_slowness()
 
     # ---- side measurement (1 GPU, not the headline): two independent sources solved concurrently on two slots of one
     # grid (configs[3]'s situation: many sources per GPU); aggregate node-sweeps per second of the pair
@@ -312,6 +407,14 @@ def main():
             g2.close()
         except Exception as e:
             pair = {"error": str(e)}
+
+    # ---- side measurement: configs[3], strong scaling of 64 sources over the ranks
+    c4 = None
+    if args.c4_sources > 0 and n == 512:
+        try:
+            c4 = config4_side(torch, dist, rank, world, local_rank, min(64, args.c4_sources))
+        except Exception as e:   # a side line never costs the headline
+            c4 = {"error": str(e)}
 
     # ---- reduce over ranks: whole-job node-sweeps, max time ------------------------------------------
     nodes = float(n) ** 3
@@ -341,7 +444,9 @@ def main():
             "dtype": "f32", "data": "synthetic", "config": workload_config(n),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": mx[4] / args.steps,
-                    "call": "Grid3d.raytrace(src, rcv, slowness): slowness from pinned host memory, 441 receiver times back"},
+                    "call": ("Grid3d.raytrace(src, rcv, slowness): slowness from pinned host memory, 441 receiver times back" if world == 1 else
+                             "raytrace_sharded(grid, sources, rcv, slowness): one upload on rank 0 + NCCL broadcast + one solve per rank + "
+                             "all-gather of the receiver times; h2d/d2h bytes are rank 0's")},
             "gpu_launches": int(tot[7]),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "kernel": KERNEL_NAMES.get(st["kernel"], str(st["kernel"])) + " (one launch = one directional sweep)",
@@ -352,7 +457,7 @@ def main():
                        "sweep_ms_per_step": sweep_ms / args.steps, "wall_ms_per_step": mx[2] / args.steps,
                        "mnode_iters_per_s": value / 8.0, "kernel": st["kernel"],
                        "device_bytes": g.device_bytes(), "launches_per_step": launches / args.steps,
-                       "concurrent_sources": pair},
+                       "concurrent_sources": pair, "config4": c4},
         }
         if not args.no_cpu_baseline:
             try:

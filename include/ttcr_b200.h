@@ -69,7 +69,7 @@ typedef struct {
     int kernel;           /* sweep kernel actually used (TTCR_B200_KERNEL_*) */
 } ttcr_b200_stats;
 
-enum { TTCR_B200_KERNEL_AUTO = 0, TTCR_B200_KERNEL_PLANE = 1, TTCR_B200_KERNEL_TILE = 2, TTCR_B200_KERNEL_TILE3 = 3, TTCR_B200_KERNEL_TILE4 = 4, TTCR_B200_KERNEL_TILE5 = 5, TTCR_B200_KERNEL_COOP = 6, TTCR_B200_KERNEL_MARCH = 7 };
+enum { TTCR_B200_KERNEL_AUTO = 0, TTCR_B200_KERNEL_PLANE = 1, TTCR_B200_KERNEL_TILE = 2, TTCR_B200_KERNEL_COOP = 6, TTCR_B200_KERNEL_MARCH = 7 };   /* (3..5: earlier marching kernels, retired) */
 
 /* Replaces: new Grid3Drnfs<T,uint32_t>(nx,ny,nz,dx,xmin,ymin,zmin,eps,maxit,weno,ttrp,intVel,nt,
  * translateOrigin) (Grid3Drnfs.h:39-50, rgrid.pyx:256-261) and the Grid3Drcfs twin

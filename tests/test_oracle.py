@@ -306,3 +306,23 @@ def test_accuracy_study_constant_model_random_sources(oracle):
         tt, ni, nw = oracle.solve(n - 1, n - 1, n - 1, float(x[1] - x[0]), s_node, k["src"][i:i + 1], 0.0, weno=True)
         assert (ni, nw) == tuple(k["iters"][i])
         assert np.array_equal(oracle.interp(n - 1, n - 1, n - 1, float(x[1] - x[0]), tt, k["rcv"]), k["tt_rcv"][i])
+
+
+def test_headline_size_digests_float_restatement_vs_reference_double():
+    """tests/golden/digest (oracle/make_digest.py): at 512^3 the C restatement's fp32 field and the UNMODIFIED reference's
+    Grid3Drnfs<double> field agree to 1e-5 on three full planes and at the 441 receivers, same iteration count -- the
+    fp32-vs-reference-double distance the GPU tests' 1e-4 has to cover"""
+    import os
+    base = os.path.join(os.path.dirname(__file__), "golden", "digest")
+    a = np.load(os.path.join(base, "c3_512_f32.npz"))
+    r = np.load(os.path.join(base, "c3_512_ref_f64.npz"))
+    assert int(a["niter"]) == int(r["niter"]) == 2
+    assert np.array_equal(a["planes_i"], r["planes_i"]) and np.array_equal(a["rcv"], r["rcv"])
+    floor = (20.0 / 511.0) / 3.0
+    e = np.abs(a["planes"].astype(np.float64) - r["planes"]) / np.maximum(r["planes"], floor)
+    assert e.max() <= 1e-5
+    e = np.abs(a["tt_rcv"].astype(np.float64) - r["tt_rcv"]) / np.maximum(r["tt_rcv"], floor)
+    assert e.max() <= 1e-5
+    for name in ("c4_511c_f32", "c5_1024_f32"):
+        d = np.load(os.path.join(base, name + ".npz"))
+        assert d["planes_i"].size == 1 and np.all(np.isfinite(d["planes" if "planes" in d else "planes_0"]))

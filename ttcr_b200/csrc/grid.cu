@@ -21,9 +21,7 @@
 #include "../../include/ttcr_b200.h"
 #include "kernels.cuh"
 #include "sweep_tile.cuh"
-#include "sweep_tile3.cuh"
 #include "raypath.cuh"
-#include "sweep_tile5.cuh"
 #include "sweep_march.cuh"
 
 namespace ttcrb200 {
@@ -122,7 +120,7 @@ class Grid final : public GridBase {
         const size_t ne = d_.elems();
         for (int l = 0; l < 2; ++l) {
             slo_[l] = alloc_field(ne);
-            // slots that are no node hold NaN: their update is NaN and never passes `t < old` (sweep_tile5.cuh)
+            // slots that are no node hold NaN: their update is NaN and never passes `t < old` (sweep_march.cuh)
             CK(cudaMemset(slo_[l], 0xFF, ne * sizeof(T)));
         }
         slots_.resize(nslots);
@@ -162,7 +160,6 @@ class Grid final : public GridBase {
                     if (b.exec) cudaGraphExecDestroy(b.exec);
             cudaFree(s.d_pts); cudaFreeHost(s.h_pts);
             tile_free(s.tile);
-            tile5_free(s.tile5);
             march_free(s.march);
             cudaEventDestroy(s.e0); cudaEventDestroy(s.e1);
             cudaStreamDestroy(s.stream);
@@ -400,7 +397,7 @@ class Grid final : public GridBase {
         if (key == "tt_from_rp") ttrp_ = v != 0;
         else if (key == "kernel") {
             if (v != TTCR_B200_KERNEL_AUTO && v != TTCR_B200_KERNEL_PLANE && v != TTCR_B200_KERNEL_TILE &&
-                v != TTCR_B200_KERNEL_TILE3 && v != TTCR_B200_KERNEL_TILE4 && v != TTCR_B200_KERNEL_TILE5 && v != TTCR_B200_KERNEL_COOP && v != TTCR_B200_KERNEL_MARCH)
+                v != TTCR_B200_KERNEL_COOP && v != TTCR_B200_KERNEL_MARCH)
                 throw Err(TTCR_B200_ERR_INVALID, "unknown kernel id");
             kernel_ = (int)v;
         } else if (key == "tile_rows") tile_opt_.chunk = std::max(1, (int)v);
@@ -435,7 +432,6 @@ class Grid final : public GridBase {
         T* h_pts = nullptr;
         size_t pts_cap = 0;
         TileState tile;
-        Tile5State tile5;
         MarchState march;
         ttcr_b200_stats st{};
         unsigned* d_bar = nullptr;           // arrival counter of k_sweep_planes_coop's grid barrier
@@ -448,7 +444,7 @@ class Grid final : public GridBase {
     };
 
     // Field arrays (traveltime, slowness) carry ni rows of front padding: the skewed tensor map of k_sweep_patch
-    // (make_tile5_map, "plus" variant) is based that far below the array and the TMA unit wants a mapped base.
+    // (make_skew_map, "plus" variant) is based that far below the array and the TMA unit wants a mapped base.
     size_t front_pad() const { return (size_t)d_.ni * d_.kpad; }
     T* alloc_field(size_t ne) {
         T* raw = nullptr;
@@ -530,24 +526,6 @@ class Grid final : public GridBase {
         if (kernel == TTCR_B200_KERNEL_MARCH) {
             const int nl = march_sweep<T>(s.tile, s.march, tile_opt_, sm_count_, w, d_, tt, slo_[w.layout], s.mask[w.layout], fb,
                                          g_.dx, s.d_change, s.stream);
-            s.st.launches += nl; s.st.sweep_launches += nl;
-            return;
-        }
-        if (kernel == TTCR_B200_KERNEL_TILE5) {
-            const int nl = tile5_sweep<T>(s.tile, s.tile5, tile_opt_, sm_count_, w, d_, tt, slo_[w.layout], s.mask[w.layout], fb,
-                                         g_.dx, s.d_change, s.stream);
-            s.st.launches += nl; s.st.sweep_launches += nl;
-            return;
-        }
-        if (kernel == TTCR_B200_KERNEL_TILE4) {
-            const int nl = tile4_sweep<T>(s.tile, tile_opt_, sm_count_, w, d_, tt, slo_[w.layout], s.mask[w.layout], fb, g_.dx,
-                                         s.d_change, s.stream);
-            s.st.launches += nl; s.st.sweep_launches += nl;
-            return;
-        }
-        if (kernel == TTCR_B200_KERNEL_TILE3) {
-            const int nl = tile3_sweep<T>(s.tile, tile_opt_, sm_count_, w, d_, tt, slo_[w.layout], s.mask[w.layout], fb, g_.dx,
-                                         s.d_change, s.stream);
             s.st.launches += nl; s.st.sweep_launches += nl;
             return;
         }
@@ -653,14 +631,12 @@ class Grid final : public GridBase {
     int pick_kernel(bool weno_stage) const {
         const int weno_kernel_ = plane_kernel();
         if (kernel_ != TTCR_B200_KERNEL_AUTO) {
-            if ((kernel_ == TTCR_B200_KERNEL_TILE3 || kernel_ == TTCR_B200_KERNEL_TILE4 || kernel_ == TTCR_B200_KERNEL_TILE5 ||
-                 kernel_ == TTCR_B200_KERNEL_MARCH) &&
-                !tile3_supported<T>(weno_stage))
+            if (kernel_ == TTCR_B200_KERNEL_MARCH && !march_supported<T>(weno_stage))
                 return tile_supported<T>(weno_stage) ? TTCR_B200_KERNEL_TILE : weno_kernel_;
             if (kernel_ == TTCR_B200_KERNEL_TILE && !tile_supported<T>(weno_stage)) return weno_kernel_;
             return kernel_;
         }
-        if (tile5_supported<T>(weno_stage)) return TTCR_B200_KERNEL_TILE5;   // fp32, first order: register-patch march (sweep_tile5.cuh)
+        if (march_supported<T>(weno_stage)) return TTCR_B200_KERNEL_MARCH;   // fp32, first order: the marching kernel (sweep_march.cuh)
         if (!tile_supported<T>(weno_stage)) return weno_kernel_;                // WENO stage: plane kernels
         return TTCR_B200_KERNEL_TILE;                                           // fp64, first order
     }
@@ -734,7 +710,6 @@ class Grid final : public GridBase {
                 CK(cudaGetLastError());
                 CK(cudaMemcpyAsync(s.h_change, s.d_change, sizeof(double), cudaMemcpyDeviceToHost, s.stream));
                 CK(cudaStreamSynchronize(s.stream));
-                if (s.tile.h_abort && *s.tile.h_abort) tile5_dump(s.tile5);
                 tile_check(s.tile);
                 const double c = *s.h_change;
                 s.st.last_change = c;

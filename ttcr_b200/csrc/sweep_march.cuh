@@ -36,7 +36,7 @@
 //
 // fp32, first-order stage.  Same DAG and same arithmetic (update.cuh) as every other sweep kernel: bit-identical field.
 #pragma once
-#include "sweep_tile5.cuh"
+#include "tma_helpers.cuh"
 
 namespace ttcrb200 {
 
@@ -69,7 +69,7 @@ struct MarchLayout {
     static constexpr int TBYTES = (PUT + 1) * PSB, SBYTES = PUT * PSB;                // bytes a box delivers
     // the two mbarriers of a chunk slot live in the padding behind its T box
     static constexpr int OFF_EMPTY = TBYTES, OFF_FULL = TBYTES + 8;
-    static constexpr int CHB_T = t5_round128(TBYTES + 16), CHB_S = t5_round128(SBYTES), CHB = CHB_T + CHB_S;
+    static constexpr int CHB_T = round128(TBYTES + 16), CHB_S = round128(SBYTES), CHB = CHB_T + CHB_S;
     static constexpr int USLOT = 128, VSLOT = 32;                                     // 8 x {A, tag, B, tag} | 4 x {B, tag}
     static constexpr int URING = D * USLOT, VRING = D * VSLOT;
     static constexpr int OFF_UR = NCH * CHB;
@@ -666,7 +666,7 @@ inline int march_launch(TileState& s, MarchState& ms, const TileOptions& o, int 
         for (auto& e : ms.maps)
             if (e.first == kk) return e.second;
         if (ms.maps.size() > 64) ms.maps.clear();
-        ms.maps.push_back({kk, make_tile5_map(a, d, minus, L::BW, L::C, bp, true)});
+        ms.maps.push_back({kk, make_skew_map(a, d, minus, L::BW, L::C, bp, true)});
         return ms.maps.back().second;
     };
     const CUtensorMap tmT = get_map(tt, PUT + 1);

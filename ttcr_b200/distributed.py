@@ -27,11 +27,13 @@ def shard_sources(n_sources: int, world_size: int, rank: int) -> np.ndarray:
     return np.arange(start, start + sizes[rank], dtype=np.int64)
 
 
-def broadcast_slowness(grid, slowness, src_rank: int = 0):
+def broadcast_slowness(grid, slowness, src_rank: int = 0, chunks: int = 8):
     """Give every rank's ``grid`` the slowness model held by ``src_rank`` (``slowness`` may be None elsewhere).
 
-    With the NCCL backend the model travels GPU to GPU and is handed to the solver as a device pointer;
-    with gloo it travels as a host tensor."""
+    With the NCCL backend the model is uploaded ONCE (on ``src_rank``; asynchronously when it sits in pinned host memory),
+    travels GPU to GPU and is handed to the solver as a device pointer.  Upload and broadcast are pipelined chunk by chunk
+    (the broadcast of chunk c runs on NCCL's stream while chunk c+1 is copied), so N ranks pay one host-to-device copy,
+    not N concurrent ones.  With gloo the model travels as a host tensor."""
     import torch
     import torch.distributed as dist
 
@@ -41,18 +43,34 @@ def broadcast_slowness(grid, slowness, src_rank: int = 0):
     nx, ny, nz = grid.shape
     tdtype = torch.float32 if grid.dtype == np.float32 else torch.float64
     use_cuda = dist.get_backend() == "nccl"
-    dev = torch.device("cuda", torch.cuda.current_device()) if use_cuda else torch.device("cpu")
-    if dist.get_rank() == src_rank:
-        s = np.ascontiguousarray(np.asarray(slowness, dtype=grid.dtype).reshape(nx, ny, nz))
-        t = torch.from_numpy(s).to(dev)
-    else:
-        t = torch.empty((nx, ny, nz), dtype=tdtype, device=dev)
-    dist.broadcast(t, src=src_rank)
-    if use_cuda:
-        torch.cuda.synchronize()
-        grid.set_slowness_device(t.data_ptr(), t.numel())
-    else:
+    if not use_cuda:
+        if dist.get_rank() == src_rank:
+            t = torch.from_numpy(np.ascontiguousarray(np.asarray(slowness, dtype=grid.dtype).reshape(nx, ny, nz)))
+        else:
+            t = torch.empty((nx, ny, nz), dtype=tdtype)
+        dist.broadcast(t, src=src_rank)
         grid.set_slowness(t.numpy())
+        return
+    dev = torch.device("cuda", torch.cuda.current_device())
+    t = getattr(grid, "_bcast_buf", None)
+    if t is None or t.numel() != nx * ny * nz or t.dtype != tdtype or t.device != dev:
+        t = torch.empty(nx * ny * nz, dtype=tdtype, device=dev)
+        grid._bcast_buf = t          # landing buffer, kept for the next model
+    src = None
+    if dist.get_rank() == src_rank:
+        src = torch.from_numpy(np.ascontiguousarray(np.asarray(slowness, dtype=grid.dtype)).reshape(-1))
+    n = t.numel()
+    step = -(-n // max(1, chunks))
+    works = []
+    for a in range(0, n, step):
+        b = min(n, a + step)
+        if src is not None:
+            t[a:b].copy_(src[a:b], non_blocking=True)
+        works.append(dist.broadcast(t[a:b], src=src_rank, async_op=True))
+    for w in works:
+        w.wait()
+    torch.cuda.synchronize()
+    grid.set_slowness_device(t.data_ptr(), n)
 
 
 def raytrace_sharded(grid, sources, rcv, slowness=None, t0=None):
