@@ -72,8 +72,7 @@ def timing(sizes, combos=None):
         g = Grid3d(x, x, x, cell_slowness=0, tt_from_rp=False, weno=0, dtype=np.float32)
         g.set_slowness(s)
         print(f"--- {n}^3 device bytes {g.device_bytes() / 2**30:.2f} GiB", flush=True)
-        combos_n = combos or [dict(kernel=MARCH), dict(kernel=MARCH, tile_depth=3), dict(kernel=MARCH, tile_depth=3, ctas_per_sm=1), dict(kernel=MARCH, tile_warps=12),
-                              dict(kernel=TILE5, tile_warps=8, tile_urows=1)]
+        combos_n = combos or [dict(kernel=MARCH), dict(kernel=MARCH, tile_depth=3), dict(kernel=MARCH, tile_depth=3, ctas_per_sm=1), dict(kernel=MARCH, tile_warps=12)]
         for src in ([0.0, 0.0, 0.0],):
             for c in combos_n:
                 g.set_option("tile_warps", 8); g.set_option("tile_urows", 1); g.set_option("ctas_per_sm", 0); g.set_option("tile_depth", 8)
