@@ -424,6 +424,8 @@ class Grid final : public GridBase {
     struct Slot {
         T* tt[2] = {nullptr, nullptr};          // traveltime field in layouts L1, L2 (padding = MAX)
         uint32_t* mask[2] = {nullptr, nullptr}; // frozen bit per slot, both layouts
+        FrozenBox prev_fb{};                    // bounding box of the bits that may be set (the previous source's)
+        bool have_prev_fb = false;
         cudaStream_t stream = nullptr;
         cudaEvent_t e0 = nullptr, e1 = nullptr;
         double* d_change = nullptr;
@@ -658,8 +660,18 @@ class Grid final : public GridBase {
         CK(cudaMemcpyAsync(s.d_pts, s.h_pts, 4 * ntx * sizeof(T), cudaMemcpyHostToDevice, s.stream));
         // Node3Dn::reinit: every node +MAX; the slots that are no node hold +MAX anyway, so this is a plain fill
         k_fill16<T><<<nblocks(ne / (16 / sizeof(T)), 256, 148 * 32), 256, 0, s.stream>>>(s.tt[0], ne, Lim<T>::max());
-        CK(cudaMemsetAsync(s.mask[0], 0, ne / 8, s.stream));
-        CK(cudaMemsetAsync(s.mask[1], 0, ne / 8, s.stream));
+        // frozen bits: only the previous source's box can hold any (the masks were zeroed when the slot was made)
+        if (s.have_prev_fb) {
+            const FrozenBox& pb = s.prev_fb;
+            const long long vol = (long long)(pb.ihi - pb.ilo + 1) * (pb.jhi - pb.jlo + 1) * (pb.khi - pb.klo + 1);
+            if (vol > 0 && vol <= (long long)d_.nodes() / 64) {
+                k_clear_frozen_box<<<(unsigned)std::min<long long>((vol + 255) / 256, 1184), 256, 0, s.stream>>>(d_, pb, s.mask[0], s.mask[1]);
+            } else if (vol > 0) {
+                CK(cudaMemsetAsync(s.mask[0], 0, ne / 8, s.stream));
+                CK(cudaMemsetAsync(s.mask[1], 0, ne / 8, s.stream));
+            }
+        }
+        s.prev_fb = fb; s.have_prev_fb = true;
         k_init_fsm<T><<<1, 32, 0, s.stream>>>(g_, d_, s.d_pts, s.d_pts + 3 * ntx, (int)ntx, npts, s.tt[0], slo_[0], s.mask[0],
                                               s.mask[1]);
         CK(cudaGetLastError());

@@ -332,6 +332,19 @@ struct FrozenBox {   // conservative bounding box (true i,j,k) of all frozen nod
     int ilo, ihi, jlo, jhi, klo, khi;
 };
 
+// Clears the frozen bits of the previous source: they all lie inside its (conservative) bounding box, so a solve does not
+// have to zero the two whole bit masks (2 x 37 MB at 512^3: 0.37 ms of a 12 ms solve).
+__global__ void k_clear_frozen_box(Dims d, FrozenBox fb, uint32_t* __restrict__ m1, uint32_t* __restrict__ m2) {
+    const int nx = fb.ihi - fb.ilo + 1, ny = fb.jhi - fb.jlo + 1, nz = fb.khi - fb.klo + 1;
+    const long long n = (long long)nx * ny * nz;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
+        const int k = fb.klo + (int)(t % nz), j = fb.jlo + (int)((t / nz) % ny), i = fb.ilo + (int)(t / ((long long)nz * ny));
+        const size_t e1 = d.l1(i, j, k), e2 = d.l2(i, j, k);
+        atomicAnd(&m1[e1 >> 5], ~(1u << (e1 & 31)));
+        atomicAnd(&m2[e2 >> 5], ~(1u << (e2 & 31)));
+    }
+}
+
 // The update of node (u, p - u, v) of wavefront plane p in oriented coordinates, first order (Grid3Drn.h:2902-2959) or
 // WENO (:3078-3484); returns the decrease of its traveltime (0 if the slot is no node, frozen or unchanged).
 template <typename T, bool WENO>

@@ -38,6 +38,7 @@
 #pragma once
 #include "tma_helpers.cuh"
 
+
 namespace ttcrb200 {
 
 struct MarchMail {
@@ -390,8 +391,10 @@ k_sweep_march(const __grid_constant__ CUtensorMap tmT, const __grid_constant__ C
             constexpr unsigned OUT_U = WV * URING, OUT_V = VRING;          // the rings of the warp below / to the right
             const unsigned a_myprog = (unsigned)pin((int)(a_prog + 4 * lw));
             const unsigned toff = (unsigned)pin((int)G::thread_off(pl, vl));
-            float* pg = tt + (w.base + (long long)min(u, ulast) * w.su + (long long)(T.m_first - 1 - pl) * w.sm + (long long)(RK ? vt + 1 : vt) * w.sv);
-            const long long rowstride = w.sm;
+            // the thread's pair of step 1 (a row before the tile's first one), and the byte offset of the current step's pair from it
+            char* const pg0 = (char*)(tt + (w.base + (long long)min(u, ulast) * w.su + (long long)(T.m_first - 1 - pl) * w.sm + (long long)(RK ? vt + 1 : vt) * w.sv));
+            const int rowbytes = (int)w.sm * 4;
+            int poff = 0;
             // ---- slow-path condition: frozen nodes (source box)
             bool fzme = false;
             int wz_lo = 1 << 28, wz_hi = -(1 << 28);
@@ -470,7 +473,7 @@ k_sweep_march(const __grid_constant__ CUtensorMap tmT, const __grid_constant__ C
 
             // One march step: ring words at rUi / rVi must carry a tag >= tgs, outputs go to rUo / rVo with tag tgs + 1, the next
             // step's operands are at `ao`.
-            auto step = [&](const unsigned tgs, const unsigned rUi, const unsigned rVi, const unsigned rUo, const unsigned rVo, const unsigned ao,
+            auto step = [&](const int r, const unsigned tgs, const unsigned rUi, const unsigned rVi, const unsigned rUo, const unsigned rVo, const unsigned ao,
                             auto slow_c, auto mail_c) {
                 constexpr bool SLOW = decltype(slow_c)::value != 0, MAILW = decltype(mail_c)::value != 0;
                 // ---- (1) everything this step reads from shared memory
@@ -483,7 +486,7 @@ k_sweep_march(const __grid_constant__ CUtensorMap tmT, const __grid_constant__ C
                 float um1 = __shfl_up_sync(0xffffffffu, p1, 8);
                 float km0 = __shfl_up_sync(0xffffffffu, p1, 1);
                 // ---- (3) the one branch: words not there yet
-                if (__builtin_expect(min(min(xu.y, xu.w), xv.y) < tgs, 0)) {
+                if (__builtin_expect(__any_sync(0xffffffffu, min(min(xu.y, xu.w), xv.y) < tgs), 0)) {
                     const int st = march_wait_words(rUi, rVi, tgs, a_dead, spin_cycles, p.spin_polls, p.sleep_ns);
                     if (st == 2) give_up(41, (int)tgs, (int)min(xu.y, xv.y));
                     if (st) dead = 1;
@@ -491,7 +494,7 @@ k_sweep_march(const __grid_constant__ CUtensorMap tmT, const __grid_constant__ C
                 }
                 if (SLOW) {
                     if (fl & F_FZ) {   // (the pair shares a mask word: e is even)
-                        const long long e = (long long)(pg - tt);
+                        const long long e = (long long)((float*)(pg0 + poff) - tt);
                         const unsigned bits = frozen[e >> 5] >> (e & 31);
                         if (bits & (RK ? 2u : 1u)) s0 = QNAN;
                         if (bits & (RK ? 1u : 2u)) s1 = QNAN;
@@ -507,13 +510,12 @@ k_sweep_march(const __grid_constant__ CUtensorMap tmT, const __grid_constant__ C
                 sts_u4_ifu(rUo, __float_as_uint(n0), tgs + 1, __float_as_uint(n1), tgs + 1, fl & F_STU);
                 sts_u2_ifu(rVo, __float_as_uint(n1), tgs + 1, fl & F_STV);
                 if (MAILW) {
-                    st_mail2_if(mu, serial, n0, n1, (int)(fl & F_OMU));
-                    st_mail_if(mv, serial, n1, (int)(fl & F_OMV));
-                    mu += TW; mv += PUT;
+                    st_mail2_if(mu + r * TW, serial, n0, n1, (int)(fl & F_OMU));   // (mu, mv: the group's first step)
+                    st_mail_if(mv + r * PUT, serial, n1, (int)(fl & F_OMV));
                 }
                 // ---- (6) result, change sum, rotate the operands
-                stg_f2_stream_if(pg, RK ? n1 : n0, RK ? n0 : n1, (n0 < o0 || n1 < o1) ? 1 : 0);
-                pg += rowstride;
+                stg_f2_stream_if((float*)(pg0 + poff), RK ? n1 : n0, RK ? n0 : n1, (n0 < o0 || n1 < o1) ? 1 : 0);
+                poff += rowbytes;
                 acc += (o0 - n0) + (o1 - n1);
                 p0 = n0; p1 = n1; o0 = j0; o1 = j1;
                 j0 = RK ? nj.y : nj.x; j1 = RK ? nj.x : nj.y;
@@ -530,10 +532,11 @@ k_sweep_march(const __grid_constant__ CUtensorMap tmT, const __grid_constant__ C
                 const unsigned gUn = aUin + so_n, gVn = aVin + (so_n >> 2);
 #pragma unroll
                 for (int r = 0; r < C - 1; ++r)
-                    step(t + r, gU + r * USLOT, gV + r * VSLOT, gU + OUT_U + (r + 1) * USLOT, gV + OUT_V + (r + 1) * VSLOT,
+                    step(r, t + r, gU + r * USLOT, gV + r * VSLOT, gU + OUT_U + (r + 1) * USLOT, gV + OUT_V + (r + 1) * VSLOT,
                          rB + (unsigned)((r + 1) * G::DR), slow_c, mail_c);
                 wait_full(sbn + L::OFF_FULL, npar, 42);   // the chunk the last step of the group takes the next operands from
-                step(t + C - 1, gU + (C - 1) * USLOT, gV + (C - 1) * VSLOT, gUn + OUT_U, gVn + OUT_V, sbn + toff, slow_c, mail_c);
+                step(C - 1, t + C - 1, gU + (C - 1) * USLOT, gV + (C - 1) * VSLOT, gUn + OUT_U, gVn + OUT_V, sbn + toff, slow_c, mail_c);
+                if (decltype(mail_c)::value) { mu += C * TW; mv += C * PUT; }
                 // every lane has read the group's words and the chunk's last row (its values were used by the update above)
                 __syncwarp();
                 mbar_arrive_ifu(sb + L::OFF_EMPTY, fl & F_L0);
@@ -730,6 +733,7 @@ inline int march_sweep<float>(TileState& s, MarchState& ms, const TileOptions& o
                               const float* slo, const uint32_t* frozen, const FrozenBox& fb, float dx, double* d_change, cudaStream_t st) {
     // <warps along u, warps along v, chunk slots of the box ring>; tile = 4 WU planes x 16 WV lanes
     if (o.warps == 12) return march_launch<6, 2, 5>(s, ms, o, sm_count, w, d, tt, slo, frozen, fb, dx, d_change, st);
+    if (o.depth == 7) return march_launch<4, 2, 7>(s, ms, o, sm_count, w, d, tt, slo, frozen, fb, dx, d_change, st);
     if (o.depth == 3) return march_launch<4, 2, 3>(s, ms, o, sm_count, w, d, tt, slo, frozen, fb, dx, d_change, st);   // two CTAs per SM
     return march_launch<4, 2, 6>(s, ms, o, sm_count, w, d, tt, slo, frozen, fb, dx, d_change, st);
 }
