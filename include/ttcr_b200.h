@@ -98,6 +98,13 @@ int ttcr_b200_set_slowness(ttcr_b200_grid* g, const void* s, size_t n, int order
  * work on that buffer only if the caller has synchronised; the call itself returns when done. */
 int ttcr_b200_set_slowness_device(ttcr_b200_grid* g, const void* s_dev, size_t n, int order);
 
+/* Extension: the x planes [i_first, i_first + i_count) of a NODE model that is arriving piecewise in the device buffer
+ * `s_dev` (the whole (nx+1)(ny+1)(nz+1) array, numpy order = TTCR_B200_ORDER_Z_FASTEST only): lets the caller import each
+ * chunk of a pipelined upload / NCCL broadcast while the next chunk is still travelling.  The caller has synchronised the
+ * chunk's arrival; the call enqueues the import and returns, except for the chunk that ends at the last plane, which
+ * waits for all of them and makes the model current.  Cell models: TTCR_B200_ERR_INVALID (use set_slowness_device). */
+int ttcr_b200_set_slowness_device_planes(ttcr_b200_grid* g, const void* s_dev, size_t n, int i_first, int i_count);
+
 /* Replaces: Grid3Drn::getSlowness (Grid3Drn.h:90-97): NODE slowness, (nx+1)(ny+1)(nz+1) values. */
 int ttcr_b200_get_slowness(ttcr_b200_grid* g, void* out, int order);
 

@@ -21,7 +21,7 @@ KERNEL_AUTO, KERNEL_PLANE, KERNEL_TILE, KERNEL_TILE3 = 0, 1, 2, 3
 # every symbol include/ttcr_b200.h declares (tests check that the library exports all of them)
 SYMBOLS = (
     "ttcr_b200_create", "ttcr_b200_destroy", "ttcr_b200_last_error", "ttcr_b200_set_slowness",
-    "ttcr_b200_set_slowness_device", "ttcr_b200_get_tt_device", "ttcr_b200_get_slowness", "ttcr_b200_raytrace", "ttcr_b200_raytrace_multi", "ttcr_b200_get_tt",
+    "ttcr_b200_set_slowness_device", "ttcr_b200_set_slowness_device_planes", "ttcr_b200_get_tt_device", "ttcr_b200_get_slowness", "ttcr_b200_raytrace", "ttcr_b200_raytrace_multi", "ttcr_b200_get_tt",
     "ttcr_b200_get_niter", "ttcr_b200_set_option", "ttcr_b200_n_slots", "ttcr_b200_solve",
     "ttcr_b200_get_stats", "ttcr_b200_device_bytes", "ttcr_b200_version", "ttcr_b200_raytrace_rays", "ttcr_b200_get_rays",
 )
@@ -63,6 +63,7 @@ def load() -> C.CDLL:
     lib.ttcr_b200_destroy.restype = None
     lib.ttcr_b200_set_slowness.argtypes = [vp, vp, sz, i32]
     lib.ttcr_b200_set_slowness_device.argtypes = [vp, vp, sz, i32]
+    lib.ttcr_b200_set_slowness_device_planes.argtypes = [vp, vp, sz, i32, i32]
     lib.ttcr_b200_get_tt_device.argtypes = [vp, vp, sz, i32]
     lib.ttcr_b200_get_slowness.argtypes = [vp, vp, i32]
     lib.ttcr_b200_raytrace.argtypes = [vp, vp, vp, sz, vp, sz, vp, sz]

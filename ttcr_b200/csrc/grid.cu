@@ -69,6 +69,7 @@ struct GridBase {
     virtual ~GridBase() {}
     virtual void set_slowness(const void* s, size_t n, int order) = 0;
     virtual void set_slowness_device(const void* s, size_t n, int order) = 0;
+    virtual void set_slowness_device_planes(const void* s, size_t n, int i0, int cnt) = 0;
     virtual void get_tt_device(void* out, size_t slot, int order) = 0;
     virtual void get_slowness(void* out, int order) = 0;
     virtual void solve(const void* tx, const void* t0, size_t ntx, size_t slot) = 0;
@@ -178,6 +179,23 @@ class Grid final : public GridBase {
     // ---- model -------------------------------------------------------------------------------
     void set_slowness(const void* s, size_t n, int order) override { set_slowness_any(s, n, order, cudaMemcpyHostToDevice); }
     void set_slowness_device(const void* s, size_t n, int order) override { set_slowness_any(s, n, order, cudaMemcpyDeviceToDevice); }
+
+    void set_slowness_device_planes(const void* s, size_t n, int i0, int cnt) override {
+        CK(cudaSetDevice(dev_));
+        if (cell_) throw Err(TTCR_B200_ERR_INVALID, "set_slowness_device_planes: node models only");
+        if (n != d_.nodes()) throw Err(TTCR_B200_ERR_LENGTH, "Error: slowness vectors of incompatible size.");
+        if (i0 < 0 || cnt <= 0 || i0 + cnt > d_.ni) throw Err(TTCR_B200_ERR_INVALID, "bad plane range");
+        std::lock_guard<std::mutex> lk(lin_mu_);
+        cudaStream_t st = slots_[0].stream;
+        if (i0 == 0) have_slowness_ = false;
+        const size_t ne = (size_t)cnt * d_.qs * d_.kpad;
+        for (int l = 0; l < 2; ++l) k_import<T><<<nblocks(ne), 256, 0, st>>>((const T*)s, 1, slo_[l], l, d_, i0, i0 + cnt);
+        CK(cudaGetLastError());
+        if (i0 + cnt == d_.ni) {
+            CK(cudaStreamSynchronize(st));
+            have_slowness_ = true;
+        }
+    }
 
     void set_slowness_any(const void* s, size_t n, int order, cudaMemcpyKind kind) {
         CK(cudaSetDevice(dev_));
@@ -855,6 +873,11 @@ int ttcr_b200_set_slowness(ttcr_b200_grid* g, const void* s, size_t n, int order
     NEED(g);
     return guard([&] { g->impl->set_slowness(s, n, order); });
 }
+int ttcr_b200_set_slowness_device_planes(ttcr_b200_grid* g, const void* s, size_t n, int i_first, int i_count) {
+    NEED(g);
+    return guard([&] { g->impl->set_slowness_device_planes(s, n, i_first, i_count); });
+}
+
 int ttcr_b200_set_slowness_device(ttcr_b200_grid* g, const void* s, size_t n, int order) {
     NEED(g);
     return guard([&] { g->impl->set_slowness_device(s, n, order); });

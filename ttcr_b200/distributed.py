@@ -60,17 +60,29 @@ def broadcast_slowness(grid, slowness, src_rank: int = 0, chunks: int = 8):
     if dist.get_rank() == src_rank:
         src = torch.from_numpy(np.ascontiguousarray(np.asarray(slowness, dtype=grid.dtype)).reshape(-1))
     n = t.numel()
-    step = -(-n // max(1, chunks))
+    # chunks of whole x planes: copies (rank `src_rank`) and broadcasts of all chunks are queued on a side stream up front;
+    # the host then follows the broadcasts chunk by chunk and hands each chunk to the solver's import while the next
+    # ones are still on the bus / the links.  (Cell models are averaged as a whole: one import at the end.)
+    plane = ny * nz
+    piecewise = not getattr(grid, "cell_slowness", False) and nx >= 4 * chunks
+    bounds = [nx * c // chunks for c in range(chunks + 1)] if piecewise else [0, nx]
+    side = torch.cuda.Stream(device=dev)
+    side.wait_stream(torch.cuda.current_stream(dev))
     works = []
-    for a in range(0, n, step):
-        b = min(n, a + step)
-        if src is not None:
-            t[a:b].copy_(src[a:b], non_blocking=True)
-        works.append(dist.broadcast(t[a:b], src=src_rank, async_op=True))
-    for w in works:
-        w.wait()
-    torch.cuda.synchronize()
-    grid.set_slowness_device(t.data_ptr(), n)
+    with torch.cuda.stream(side):
+        for a, b in zip(bounds[:-1], bounds[1:]):
+            if src is not None:
+                t[a * plane:b * plane].copy_(src[a * plane:b * plane], non_blocking=True)
+            works.append(dist.broadcast(t[a * plane:b * plane], src=src_rank, async_op=True))
+    for (a, b), w in zip(zip(bounds[:-1], bounds[1:]), works):
+        w.wait()                                    # the current stream waits for this chunk's broadcast ...
+        ev = torch.cuda.Event()
+        ev.record()
+        ev.synchronize()                            # ... and so does the host
+        if piecewise:
+            grid.set_slowness_device_planes(t.data_ptr(), n, a, b - a)
+    if not piecewise:
+        grid.set_slowness_device(t.data_ptr(), n)
 
 
 def raytrace_sharded(grid, sources, rcv, slowness=None, t0=None):

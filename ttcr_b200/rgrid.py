@@ -210,6 +210,12 @@ class _Grid3d:
         self._chk(self._lib.ttcr_b200_set_slowness_device(self._h, int(device_ptr), int(n_elements),
                                                           _lib.ORDER_Z_FASTEST))
 
+    def set_slowness_device_planes(self, device_ptr, n_elements, i_first, i_count):
+        """Import the x planes ``[i_first, i_first + i_count)`` of a NODE model that is arriving piecewise in a device buffer
+        holding the whole array (numpy C order): the chunks of a pipelined upload or broadcast.  The chunk ending at the last
+        plane completes the model."""
+        self._chk(self._lib.ttcr_b200_set_slowness_device_planes(self._h, int(device_ptr), int(n_elements), int(i_first), int(i_count)))
+
     def get_grid_traveltimes_device(self, device_ptr, thread_no=0):
         """Write the traveltime field (numpy C order, grid dtype) into a DEVICE buffer of nx*ny*nz elements."""
         if thread_no >= self._n_threads:
