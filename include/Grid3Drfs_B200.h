@@ -38,7 +38,7 @@ public:
                    const T1 eps, const int maxit, const bool w, const bool ttrp = true, const bool intVel = false,
                    const size_t nt = 1, const bool _translateOrigin = false, const int device = -1)
         : Grid3D<T1, T2>(ttrp, static_cast<size_t>(nx) * ny * nz, nt, _translateOrigin), h(nullptr),
-          nnodes(static_cast<size_t>(nx + 1) * (ny + 1) * (nz + 1)) {
+          nnodes(static_cast<size_t>(nx + 1) * (ny + 1) * (nz + 1)), ncx_(nx), ncy_(ny), ncz_(nz), dx_(ddx), xmin_(minx), ymin_(miny), zmin_(minz) {
         check(ttcr_b200_create(&h, nx, ny, nz, ddx, minx, miny, minz, eps, maxit, w, ttrp, intVel, nt, _translateOrigin,
                                CELL_SLOWNESS, std::is_same<T1, double>::value ? TTCR_B200_F64 : TTCR_B200_F32, device));
     }
@@ -125,9 +125,33 @@ public:
         check(ttcr_b200_set_option(h, "tt_from_rp", ttrp ? 1.0 : 0.0));
     }
 
+    // Grid3Drn::saveTT (Grid3Drn.h:2678-2760): format 1 = text "x\ty\tz\ttt" (precision 12), format 3 = binary records of four
+    // T1; every node of this grid is a primary node, so `all` makes no difference.  Format 2 (VTK) is written by the Python
+    // surface (ttcr_b200/vtr.py); here it reports what the reference reports without VTK.
+    void saveTT(const std::string& fname, const int, const size_t nt = 0, const int format = 1) const override {
+        if (format == 2) { std::cerr << "VTK not included during compilation.\nNothing saved.\n"; return; }
+        if (format != 1 && format != 3) throw std::runtime_error("Unsupported format for saving traveltimes");
+        std::vector<T1> tt;
+        getTT(tt, nt);
+        std::ofstream fout;
+        if (format == 1) { fout.open((fname + ".dat").c_str()); fout.precision(12); }
+        else fout.open((fname + ".bin").c_str(), std::ios::out | std::ios::binary | std::ios::trunc);
+        size_t n = 0;
+        for (T2 k = 0; k <= ncz_; ++k)
+            for (T2 j = 0; j <= ncy_; ++j)
+                for (T2 i = 0; i <= ncx_; ++i, ++n) {   // node order and coordinates of Grid3Drn::buildGridNodes (Grid3Drn.h:2823)
+                    const T1 rec[4] = {xmin_ + i * dx_, ymin_ + j * dx_, zmin_ + k * dx_, tt[n]};
+                    if (format == 1) fout << rec[0] << '\t' << rec[1] << '\t' << rec[2] << '\t' << rec[3] << '\n';
+                    else fout.write((const char*)rec, 4 * sizeof(T1));
+                }
+        fout.close();
+    }
+
 private:
     ttcr_b200_grid* h;
     size_t nnodes;
+    T2 ncx_, ncy_, ncz_;
+    T1 dx_, xmin_, ymin_, zmin_;
 
     static std::vector<T1> flatten(const std::vector<sxyz<T1>>& p) {
         std::vector<T1> v(3 * p.size());

@@ -12,6 +12,9 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <fstream>
+#include <iterator>
+#include <string>
 #include <memory>
 #include <vector>
 
@@ -83,6 +86,16 @@ static int run(bool weno, const char* name) {
     ref->getSlowness(sr);
     gpu->getSlowness(sg);
     bad += sr.size() != sg.size() || std::memcmp(sr.data(), sg.data(), sr.size() * sizeof(T)) != 0;   // cell -> node averaging: bit-exact
+    if (exact && !weno) {   // Grid3Drn::saveTT formats 1 and 3: byte-identical files
+        for (int fmt : {1, 3}) {
+            ref->saveTT("/tmp/ttcr_adapter_ref", 0, 1, fmt);
+            gpu->saveTT("/tmp/ttcr_adapter_gpu", 0, 1, fmt);
+            const char* ext = fmt == 1 ? ".dat" : ".bin";
+            std::ifstream a(std::string("/tmp/ttcr_adapter_ref") + ext, std::ios::binary), b(std::string("/tmp/ttcr_adapter_gpu") + ext, std::ios::binary);
+            const std::string sa((std::istreambuf_iterator<char>(a)), std::istreambuf_iterator<char>()), sb((std::istreambuf_iterator<char>(b)), std::istreambuf_iterator<char>());
+            if (sa.empty() || sa != sb) { ++bad; std::printf("  saveTT format %d differs (%zu vs %zu bytes)\n", fmt, sa.size(), sb.size()); }
+        }
+    }
     if (!exact && worst > (weno ? 2e-3 : 1e-4)) ++bad;
     std::printf("%-28s %s  max rel diff %.3g\n", name, bad ? "MISMATCH" : "ok", worst);
     return bad;

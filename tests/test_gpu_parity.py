@@ -387,3 +387,27 @@ def test_fp32_weno_iteration_counts_match_the_float_oracle_128(oracle):
     assert g.get_niter() == (ni, nw)
     assert nw < 50                                  # converged, not stopped by maxit
     check_fp32(g.get_grid_traveltimes(), oracle.from_cxx(ref, (n, n, n)), dx * float(s.min()), True)
+
+
+def test_save_tt_formats_1_and_3(tmp_path):
+    """Grid3Drn::saveTT formats 1 (text) and 3 (binary), ttcr/Grid3Drn.h:2683-2695, 2747-2756: x-fastest node records (x, y, z, tt).
+    (The C++ adapter's files are compared byte for byte with the reference's own in oracle/adapter_run.cpp.)"""
+    from ttcr_b200 import Grid3d
+    n = (9, 7, 11)
+    x, y, z = (np.arange(m) * 0.25 for m in n)
+    rng = np.random.default_rng(11)
+    s = rng.uniform(0.3, 1.0, n)
+    g = Grid3d(x, y, z, cell_slowness=0, tt_from_rp=False, weno=0, dtype=np.float64)
+    g.raytrace(np.array([[0.5, 0.75, 1.0]]), np.array([[1.0, 1.0, 1.0]]), s)
+    tt = g.get_grid_traveltimes()
+    base = str(tmp_path / "tt")
+    g.save_tt(base, fmt=3)
+    rec = np.fromfile(base + ".bin", dtype=np.float64).reshape(-1, 4)
+    assert rec.shape[0] == tt.size
+    assert np.array_equal(rec[:, 3], tt.flatten(order="F"))
+    assert np.array_equal(rec[:n[0], 0], x) and rec[n[0], 1] == y[1] and rec[n[0] * n[1], 2] == z[1]
+    g.save_tt(base, fmt=1)
+    txt = np.loadtxt(base + ".dat")
+    assert np.allclose(txt, rec, rtol=1e-11, atol=0)
+    with pytest.raises(RuntimeError):
+        g.save_tt(base, fmt=4)

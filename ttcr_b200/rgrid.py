@@ -462,9 +462,24 @@ class _Grid3d:
                 raise ValueError("Field {0:s} has incorrect size".format(name))
         write_vtr(filename + ".vtr", self._x, self._y, self._z, pd, cd)
 
-    def save_tt(self, filename, thread_no=0):
-        """Grid3Drn::saveTT format 2: point array "Travel time" in a ``.vtr``"""
-        self.to_vtk({"Travel time": self.get_grid_traveltimes(thread_no)}, filename)
+    def save_tt(self, filename, thread_no=0, fmt=2):
+        """Grid3Drn::saveTT (ttcr/Grid3Drn.h:2678-2760).  ``fmt`` 1: text ``filename + '.dat'``, one line "x\\ty\\tz\\ttt" per node
+        (12 significant digits, x fastest); 2: point array "Travel time" in ``filename + '.vtr'``; 3: binary
+        ``filename + '.bin'``, records of four values (x, y, z, tt) of the grid's dtype."""
+        if fmt == 2:
+            self.to_vtk({"Travel time": self.get_grid_traveltimes(thread_no)}, filename)
+            return
+        if fmt not in (1, 3):
+            raise RuntimeError("Unsupported format for saving traveltimes")
+        tt = self.get_grid_traveltimes(thread_no)
+        X, Y, Z = np.meshgrid(self._x, self._y, self._z, indexing="ij")
+        rec = np.stack([a.flatten(order="F") for a in (X, Y, Z, tt)], axis=1).astype(self.dtype)   # x fastest, as the reference's nodes
+        if fmt == 3:
+            rec.tofile(filename + ".bin")
+        else:
+            with open(filename + ".dat", "w") as f:
+                for r in rec:
+                    f.write("\t".join("%.12g" % v for v in r) + "\n")
 
     @staticmethod
     def builder(filename, n_threads=1, method="FSM", tt_from_rp=1, interp_vel=0, eps=1.e-5, maxit=50, weno=1,
