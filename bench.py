@@ -278,6 +278,29 @@ def config4_side(torch, dist, rank, world, local_rank, n_src):
             "includes": "pinned upload of the 511^3 cells on rank 0, NCCL broadcast, cell-to-node averaging, solves, all-gather"}
 
 
+def grid2d_side():
+    """SURVEY section 8 row f4 side line: the reference's published 2-D GPU table (docs/performance.rst:125-217: homogeneous
+    square grid, source at the centre, fp32, default weno=1, minimum of three runs) at 1000 x 1000 cells on ttcr_b200.Grid2d."""
+    from ttcr_b200 import Grid2d
+    n = 1000
+    x = np.arange(n + 1, dtype=np.float64)
+    g = Grid2d(x, x, cell_slowness=0, method="FSM", weno=1, dtype=np.float32)
+    g.set_slowness(np.ones((n + 1, n + 1), dtype=np.float32))
+    src = np.array([[n / 2.0, n / 2.0]])
+    rcv = np.array([[1.0, 1.0], [n - 1.0, n - 2.0]])
+    g.raytrace(src, rcv)
+    best = 1e9
+    for _ in range(3):
+        t0 = time.perf_counter()
+        g.raytrace(src, rcv)
+        best = min(best, time.perf_counter() - t0)
+    ni = g.get_niter()
+    g.close()
+    return {"workload": "Grid2d 1000 x 1000 cells, homogeneous, centre source, fp32, weno=1 (docs/performance.rst:125-217)",
+            "seconds": best, "niter": list(ni), "published_cpu_s": 5.105, "published_opencl_gpu_s": 1.381,
+            "note": "one CTA per source; independent sources run on different SMs"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -416,6 +439,13 @@ def main():
         except Exception as e:   # a side line never costs the headline
             c4 = {"error": str(e)}
 
+    g2 = None
+    if rank == 0 and n == 512:
+        try:
+            g2 = grid2d_side()
+        except Exception as e:
+            g2 = {"error": str(e)}
+
     # ---- reduce over ranks: whole-job node-sweeps, max time ------------------------------------------
     nodes = float(n) ** 3
     mine = torch.tensor([nodes * sweeps, dev_ms, wall_ms, nodes * e2e_sweeps, e2e_ms, sweep_ms, float(sweeps),
@@ -457,7 +487,7 @@ def main():
                        "sweep_ms_per_step": sweep_ms / args.steps, "wall_ms_per_step": mx[2] / args.steps,
                        "mnode_iters_per_s": value / 8.0, "kernel": st["kernel"],
                        "device_bytes": g.device_bytes(), "launches_per_step": launches / args.steps,
-                       "concurrent_sources": pair, "config4": c4},
+                       "concurrent_sources": pair, "config4": c4, "grid2d": g2},
         }
         if not args.no_cpu_baseline:
             try:

@@ -167,6 +167,34 @@ size_t ttcr_b200_device_bytes(const ttcr_b200_grid* g);
 /* Library version string. */
 const char* ttcr_b200_version(void);
 
+/* ---- 2-D twins: Grid2Drnfs / Grid2Drcfs (ttcr/Grid2Drnfs.h, ttcr/Grid2Drcfs.h; OpenCL: ttcr/Grid2Drn_OpenCL.h:405-600) ----
+ * Arrays are numpy C order of shape (nx+1, nz+1) nodes / (nx, nz) cells = the reference's own node / cell index
+ * (n = i * (nz+1) + j, Grid2Drnfs.h buildGridNodes; cell i * nz + j).  Points are (x, z) pairs. */
+typedef struct ttcr_b200_grid2d ttcr_b200_grid2d;
+
+/* Replaces: the Grid2Drnfs / Grid2Drcfs constructors (Grid2Drnfs.h:44-58, Grid2Drcfs.h:42-56; selected in
+ * src/ttcrpy/rgrid.pyx Grid2d.__cinit__ for method='FSM').  nx, nz are CELL counts; `weno` and `rotated_template` as there;
+ * n_slots = the reference's nt (one traveltime field per slot). */
+int ttcr_b200_create2d(ttcr_b200_grid2d** out, uint32_t nx, uint32_t nz, double dx, double dz, double xmin, double zmin, double eps,
+                       int maxit, int weno, int rotated_template, size_t n_slots, int cell_slowness, int dtype, int device);
+void ttcr_b200_destroy2d(ttcr_b200_grid2d* g);
+/* Replaces: Grid2Drn::setSlowness / Grid2Drcfs::setSlowness (Grid2Drcfs.h:99-138: cell -> node averaging). */
+int ttcr_b200_set_slowness2d(ttcr_b200_grid2d* g, const void* s, size_t n);
+/* Replaces: Grid2Drn::getSlowness: NODE slowness. */
+int ttcr_b200_get_slowness2d(ttcr_b200_grid2d* g, void* out);
+/* Replaces: Grid2Drnfs::raytrace(Tx, t0, Rx, traveltimes, threadNo) (Grid2Drnfs.h:195-299) + getTraveltime (Grid2Drn.h:359-415). */
+int ttcr_b200_raytrace2d(ttcr_b200_grid2d* g, const void* tx, const void* t0, size_t ntx, const void* rx, size_t nrx, void* tt_out, size_t slot);
+/* Replaces: Grid2D::raytrace over a vector of sources (the thread fan-out of ttcr/Grid2D.h): up to n_slots sources per launch,
+ * one CTA each.  niter_out: (niter, niterw) per source, or NULL. */
+int ttcr_b200_raytrace2d_multi(ttcr_b200_grid2d* g, size_t n_sources, const size_t* tx_off, const void* tx, const void* t0, const size_t* rx_off,
+                               const void* rx, void* tt_out, int* niter_out);
+/* Replaces: Grid2Drn::getTT. */
+int ttcr_b200_get_tt2d(ttcr_b200_grid2d* g, void* out, size_t slot);
+/* Replaces: Grid2Drnfs::get_niter / get_niterw. */
+int ttcr_b200_get_niter2d(ttcr_b200_grid2d* g, size_t slot, int* niter, int* niterw);
+/* Extension: device time (CUDA events) of the solves of the last raytrace call, milliseconds. */
+double ttcr_b200_last_solve_ms2d(const ttcr_b200_grid2d* g);
+
 #ifdef __cplusplus
 }
 #endif

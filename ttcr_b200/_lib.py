@@ -24,6 +24,8 @@ SYMBOLS = (
     "ttcr_b200_set_slowness_device", "ttcr_b200_set_slowness_device_planes", "ttcr_b200_get_tt_device", "ttcr_b200_get_slowness", "ttcr_b200_raytrace", "ttcr_b200_raytrace_multi", "ttcr_b200_get_tt",
     "ttcr_b200_get_niter", "ttcr_b200_set_option", "ttcr_b200_n_slots", "ttcr_b200_solve",
     "ttcr_b200_get_stats", "ttcr_b200_device_bytes", "ttcr_b200_version", "ttcr_b200_raytrace_rays", "ttcr_b200_get_rays",
+    "ttcr_b200_create2d", "ttcr_b200_destroy2d", "ttcr_b200_set_slowness2d", "ttcr_b200_get_slowness2d", "ttcr_b200_raytrace2d",
+    "ttcr_b200_raytrace2d_multi", "ttcr_b200_get_tt2d", "ttcr_b200_get_niter2d", "ttcr_b200_last_solve_ms2d",
 )
 
 
@@ -79,6 +81,17 @@ def load() -> C.CDLL:
     lib.ttcr_b200_get_stats.argtypes = [vp, sz, C.POINTER(Stats)]
     lib.ttcr_b200_device_bytes.argtypes = [vp]
     lib.ttcr_b200_device_bytes.restype = sz
+    lib.ttcr_b200_create2d.argtypes = [C.POINTER(vp), C.c_uint32, C.c_uint32, dbl, dbl, dbl, dbl, dbl, i32, i32, i32, sz, i32, i32, i32]
+    lib.ttcr_b200_destroy2d.argtypes = [vp]
+    lib.ttcr_b200_destroy2d.restype = None
+    lib.ttcr_b200_set_slowness2d.argtypes = [vp, vp, sz]
+    lib.ttcr_b200_get_slowness2d.argtypes = [vp, vp]
+    lib.ttcr_b200_raytrace2d.argtypes = [vp, vp, vp, sz, vp, sz, vp, sz]
+    lib.ttcr_b200_raytrace2d_multi.argtypes = [vp, sz, vp, vp, vp, vp, vp, vp, vp]
+    lib.ttcr_b200_get_tt2d.argtypes = [vp, vp, sz]
+    lib.ttcr_b200_get_niter2d.argtypes = [vp, sz, C.POINTER(i32), C.POINTER(i32)]
+    lib.ttcr_b200_last_solve_ms2d.argtypes = [vp]
+    lib.ttcr_b200_last_solve_ms2d.restype = dbl
     _lib = lib
     return lib
 

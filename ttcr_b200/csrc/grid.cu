@@ -23,6 +23,7 @@
 #include "sweep_tile.cuh"
 #include "raypath.cuh"
 #include "sweep_march.cuh"
+#include "grid2d.cuh"
 
 namespace ttcrb200 {
 
@@ -797,6 +798,162 @@ class Grid final : public GridBase {
     size_t bytes_ = 0;
 };
 
+// ---- 2-D twins (grid2d.cuh) ------------------------------------------------------------------------
+struct Grid2Base {
+    virtual ~Grid2Base() {}
+    virtual void set_slowness(const void* s, size_t n) = 0;
+    virtual void get_slowness(void* out) = 0;
+    virtual void raytrace_multi(size_t ns, const size_t* txo, const void* tx, const void* t0, const size_t* rxo, const void* rx, void* out,
+                                int* niter, size_t first_slot) = 0;
+    virtual void get_tt(void* out, size_t slot) = 0;
+    virtual void get_niter(size_t slot, int* a, int* b) = 0;
+    virtual size_t n_slots() const = 0;
+    virtual double last_ms() const = 0;
+};
+
+template <typename T>
+class Grid2 final : public Grid2Base {
+public:
+    Grid2(uint32_t ncx, uint32_t ncz, double dx, double dz, double xmin, double zmin, double eps, int maxit, bool weno, bool rotated,
+          size_t nslots, bool cell, int dev)
+        : ncx_((int)ncx), ncz_((int)ncz), cell_(cell), dev_(dev), nslots_(std::max<size_t>(nslots, 1)) {
+        if (ncx == 0 || ncz == 0) throw Err(TTCR_B200_ERR_INVALID, "grid needs at least one cell per axis");
+        CK(cudaSetDevice(dev_));
+        N_ = (size_t)(ncx + 1) * (ncz + 1);
+        p_.ncx = ncx_; p_.ncz = ncz_;
+        p_.dx = (T)dx; p_.dz = (T)dz; p_.xmin = (T)xmin; p_.zmin = (T)zmin;
+        p_.eps_total = (T)eps;
+        p_.eps_total *= static_cast<T>(N_);          // Grid2Drnfs.h:92
+        p_.maxit = maxit; p_.weno = weno; p_.rotated = rotated;
+        CK(cudaMalloc(&d_s_, N_ * sizeof(T)));
+        CK(cudaMalloc(&d_tt_, nslots_ * N_ * sizeof(T)));
+        CK(cudaMalloc(&d_frozen_, nslots_ * N_));
+        CK(cudaStreamCreateWithFlags(&st_, cudaStreamNonBlocking));
+        CK(cudaEventCreate(&e0_)); CK(cudaEventCreate(&e1_));
+        niter_.assign(2 * nslots_, 0);
+    }
+    ~Grid2() override {
+        cudaSetDevice(dev_);
+        cudaFree(d_s_); cudaFree(d_tt_); cudaFree(d_frozen_);
+        cudaEventDestroy(e0_); cudaEventDestroy(e1_);
+        cudaStreamDestroy(st_);
+    }
+    size_t n_slots() const override { return nslots_; }
+    double last_ms() const override { return last_ms_; }
+
+    void set_slowness(const void* s, size_t n) override {
+        CK(cudaSetDevice(dev_));
+        const size_t want = cell_ ? (size_t)ncx_ * ncz_ : N_;
+        if (n != want) throw Err(TTCR_B200_ERR_LENGTH, "Error: slowness vectors of incompatible size.");
+        if (cell_) {
+            ScratchBuf c;
+            c.alloc(n * sizeof(T), st_);
+            CK(cudaMemcpyAsync(c.p, s, n * sizeof(T), cudaMemcpyHostToDevice, st_));
+            k2d_cell_to_node<T><<<nblocks(N_), 256, 0, st_>>>(c.as<T>(), ncx_, ncz_, d_s_);
+            CK(cudaGetLastError());
+            CK(cudaStreamSynchronize(st_));
+        } else {
+            CK(cudaMemcpyAsync(d_s_, s, n * sizeof(T), cudaMemcpyHostToDevice, st_));
+            CK(cudaStreamSynchronize(st_));
+        }
+        have_s_ = true;
+    }
+    void get_slowness(void* out) override {
+        CK(cudaSetDevice(dev_));
+        CK(cudaMemcpy(out, d_s_, N_ * sizeof(T), cudaMemcpyDeviceToHost));
+    }
+    void get_tt(void* out, size_t slot) override {
+        if (slot >= nslots_) throw Err(TTCR_B200_ERR_INVALID, "Thread number is larger than number of threads");
+        CK(cudaSetDevice(dev_));
+        CK(cudaMemcpy(out, d_tt_ + slot * N_, N_ * sizeof(T), cudaMemcpyDeviceToHost));
+    }
+    void get_niter(size_t slot, int* a, int* b) override {
+        if (slot >= nslots_) throw Err(TTCR_B200_ERR_INVALID, "Thread number is larger than number of threads");
+        *a = niter_[2 * slot]; *b = niter_[2 * slot + 1];
+    }
+
+    // sources n = 0 .. ns-1 (Tx points txo[n] .. txo[n+1], receivers rxo[n] .. rxo[n+1]) in rounds of up to n_slots - first_slot
+    // sources per launch, source n of a round on slot first_slot + (n - round start): the fan-out of Grid2D::raytrace over a
+    // vector of sources (one slot = one of the reference's threadNo)
+    void raytrace_multi(size_t ns, const size_t* txo, const void* tx, const void* t0, const size_t* rxo, const void* rx, void* out, int* niter,
+                        size_t first_slot) override {
+        CK(cudaSetDevice(dev_));
+        if (!have_s_) throw Err(TTCR_B200_ERR_LOGIC, "slowness has not been set");
+        if (first_slot >= nslots_) throw Err(TTCR_B200_ERR_INVALID, "Thread number is larger than number of threads");
+        if (ns == 0) return;
+        int ntx_max = 0;
+        for (size_t n = 0; n < ns; ++n) {
+            if (txo[n + 1] <= txo[n]) throw Err(TTCR_B200_ERR_INVALID, "source has no Tx point");
+            ntx_max = std::max(ntx_max, (int)(txo[n + 1] - txo[n]));
+        }
+        // pack the Tx points per source
+        std::vector<T> htx((size_t)ns * ntx_max * 2, T(0)), ht0((size_t)ns * ntx_max, T(0));
+        std::vector<int> hn(ns);
+        for (size_t n = 0; n < ns; ++n) {
+            hn[n] = (int)(txo[n + 1] - txo[n]);
+            std::memcpy(&htx[n * ntx_max * 2], (const T*)tx + 2 * txo[n], (size_t)hn[n] * 2 * sizeof(T));
+            std::memcpy(&ht0[n * ntx_max], (const T*)t0 + txo[n], (size_t)hn[n] * sizeof(T));
+        }
+        const size_t nrx = rxo[ns];
+        ScratchBuf btx, bt0, bn, bit, berr, brx, bout;
+        btx.alloc(htx.size() * sizeof(T), st_); bt0.alloc(ht0.size() * sizeof(T), st_); bn.alloc(ns * sizeof(int), st_);
+        bit.alloc(2 * ns * sizeof(int), st_); berr.alloc(ns * sizeof(int), st_);
+        brx.alloc(std::max<size_t>(nrx, 1) * 2 * sizeof(T), st_); bout.alloc(std::max<size_t>(nrx, 1) * sizeof(T), st_);
+        CK(cudaMemcpyAsync(btx.p, htx.data(), htx.size() * sizeof(T), cudaMemcpyHostToDevice, st_));
+        CK(cudaMemcpyAsync(bt0.p, ht0.data(), ht0.size() * sizeof(T), cudaMemcpyHostToDevice, st_));
+        CK(cudaMemcpyAsync(bn.p, hn.data(), ns * sizeof(int), cudaMemcpyHostToDevice, st_));
+        if (nrx) CK(cudaMemcpyAsync(brx.p, rx, nrx * 2 * sizeof(T), cudaMemcpyHostToDevice, st_));
+        CK(cudaMemsetAsync(bit.p, 0, 2 * ns * sizeof(int), st_));
+        P2<T> p = p_;
+        p.s = d_s_; p.tx = btx.as<T>(); p.t0 = bt0.as<T>(); p.ntx = bn.as<int>(); p.ntx_max = ntx_max;
+        p.niter = bit.as<int>(); p.err = berr.as<int>();
+        const size_t per = nslots_ - first_slot;
+        CK(cudaEventRecord(e0_, st_));
+        for (size_t n0 = 0; n0 < ns; n0 += per) {
+            const size_t nb = std::min(per, ns - n0);
+            p.tt = d_tt_ + first_slot * N_;
+            p.frozen = d_frozen_ + first_slot * N_;
+            k2d_solve<T><<<(unsigned)nb, 1024, 0, st_>>>(p, (int)n0);
+            for (size_t b = 0; b < nb; ++b) {
+                const size_t n = n0 + b, m = rxo[n + 1] - rxo[n];
+                if (m) k2d_interp<T><<<(unsigned)((m + 127) / 128), 128, 0, st_>>>(p, d_tt_ + (first_slot + b) * N_, brx.as<T>() + 2 * rxo[n], (int)m,
+                                                                                    bout.as<T>() + rxo[n]);
+            }
+        }
+        CK(cudaEventRecord(e1_, st_));
+        CK(cudaGetLastError());
+        std::vector<int> hit(2 * ns), herr(ns);
+        CK(cudaMemcpyAsync(hit.data(), bit.p, 2 * ns * sizeof(int), cudaMemcpyDeviceToHost, st_));
+        CK(cudaMemcpyAsync(herr.data(), berr.p, ns * sizeof(int), cudaMemcpyDeviceToHost, st_));
+        if (nrx) CK(cudaMemcpyAsync(out, bout.p, nrx * sizeof(T), cudaMemcpyDeviceToHost, st_));
+        CK(cudaStreamSynchronize(st_));
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, e0_, e1_));
+        last_ms_ = ms;
+        for (size_t n = 0; n < ns; ++n)
+            if (herr[n]) throw Err(TTCR_B200_ERR_RUNTIME, "Error: Point outside grid.");   // checkPts, Grid2Drn.h:333-342
+        for (size_t n = 0; n < ns; ++n) {
+            const size_t slot = first_slot + n % per;
+            niter_[2 * slot] = hit[2 * n]; niter_[2 * slot + 1] = hit[2 * n + 1];
+        }
+        if (niter) std::memcpy(niter, hit.data(), 2 * ns * sizeof(int));
+    }
+
+private:
+    int ncx_, ncz_;
+    bool cell_, have_s_ = false;
+    int dev_;
+    size_t nslots_, N_ = 0;
+    P2<T> p_{};
+    T* d_s_ = nullptr;
+    T* d_tt_ = nullptr;
+    unsigned char* d_frozen_ = nullptr;
+    cudaStream_t st_ = nullptr;
+    cudaEvent_t e0_ = nullptr, e1_ = nullptr;
+    std::vector<int> niter_;
+    double last_ms_ = 0.0;
+};
+
 }  // namespace ttcrb200
 
 // =============================================================================================
@@ -806,6 +963,9 @@ using namespace ttcrb200;
 
 struct ttcr_b200_grid {
     GridBase* impl = nullptr;
+};
+struct ttcr_b200_grid2d {
+    ttcrb200::Grid2Base* impl = nullptr;
 };
 
 static thread_local std::string g_last_error;
@@ -944,4 +1104,57 @@ int ttcr_b200_get_stats(ttcr_b200_grid* g, size_t slot, ttcr_b200_stats* out) {
 }
 size_t ttcr_b200_device_bytes(const ttcr_b200_grid* g) { return g && g->impl ? g->impl->device_bytes() : 0; }
 
+
+/* ---- 2-D twins ---------------------------------------------------------------------------------- */
+int ttcr_b200_create2d(ttcr_b200_grid2d** out, uint32_t nx, uint32_t nz, double dx, double dz, double xmin, double zmin, double eps,
+                       int maxit, int weno, int rotated_template, size_t n_slots, int cell_slowness, int dtype, int device) {
+    if (!out) { g_last_error = "null output pointer"; return TTCR_B200_ERR_INVALID; }
+    *out = nullptr;
+    return guard([&] {
+        int ndev = 0;
+        if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) throw Err(TTCR_B200_ERR_CUDA, "no CUDA device: ttcr_b200 has no CPU path");
+        int dev = device;
+        if (dev < 0) { if (cudaGetDevice(&dev) != cudaSuccess) dev = 0; }
+        if (dev >= ndev) throw Err(TTCR_B200_ERR_INVALID, "device index out of range");
+        std::unique_ptr<ttcr_b200_grid2d> g(new ttcr_b200_grid2d);
+        if (dtype == TTCR_B200_F64) g->impl = new ttcrb200::Grid2<double>(nx, nz, dx, dz, xmin, zmin, eps, maxit, weno != 0, rotated_template != 0, n_slots, cell_slowness != 0, dev);
+        else if (dtype == TTCR_B200_F32) g->impl = new ttcrb200::Grid2<float>(nx, nz, dx, dz, xmin, zmin, eps, maxit, weno != 0, rotated_template != 0, n_slots, cell_slowness != 0, dev);
+        else throw Err(TTCR_B200_ERR_INVALID, "dtype must be TTCR_B200_F32 or TTCR_B200_F64");
+        *out = g.release();
+    });
+}
+void ttcr_b200_destroy2d(ttcr_b200_grid2d* g) {
+    if (!g) return;
+    delete g->impl;
+    delete g;
+}
+int ttcr_b200_set_slowness2d(ttcr_b200_grid2d* g, const void* s, size_t n) {
+    NEED(g);
+    return guard([&] { g->impl->set_slowness(s, n); });
+}
+int ttcr_b200_get_slowness2d(ttcr_b200_grid2d* g, void* out) {
+    NEED(g);
+    return guard([&] { g->impl->get_slowness(out); });
+}
+int ttcr_b200_raytrace2d(ttcr_b200_grid2d* g, const void* tx, const void* t0, size_t ntx, const void* rx, size_t nrx, void* tt_out, size_t slot) {
+    NEED(g);
+    return guard([&] {
+        const size_t txo[2] = {0, ntx}, rxo[2] = {0, nrx};
+        g->impl->raytrace_multi(1, txo, tx, t0, rxo, rx, tt_out, nullptr, slot);
+    });
+}
+int ttcr_b200_raytrace2d_multi(ttcr_b200_grid2d* g, size_t n_sources, const size_t* tx_off, const void* tx, const void* t0, const size_t* rx_off,
+                               const void* rx, void* tt_out, int* niter_out) {
+    NEED(g);
+    return guard([&] { g->impl->raytrace_multi(n_sources, tx_off, tx, t0, rx_off, rx, tt_out, niter_out, 0); });
+}
+int ttcr_b200_get_tt2d(ttcr_b200_grid2d* g, void* out, size_t slot) {
+    NEED(g);
+    return guard([&] { g->impl->get_tt(out, slot); });
+}
+int ttcr_b200_get_niter2d(ttcr_b200_grid2d* g, size_t slot, int* niter, int* niterw) {
+    NEED(g);
+    return guard([&] { g->impl->get_niter(slot, niter, niterw); });
+}
+double ttcr_b200_last_solve_ms2d(const ttcr_b200_grid2d* g) { return (g && g->impl) ? g->impl->last_ms() : 0.0; }
 }  // extern "C"
