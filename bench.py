@@ -301,6 +301,25 @@ def grid2d_side():
             "note": "one CTA per source; independent sources run on different SMs"}
 
 
+def default_path_side(local_rank):
+    """Side lines for the reference's DEFAULT arguments (dtype float64, weno=1), which do not run the headline kernel:
+    fp64 first-order (k_sweep_tile) and fp32 / fp64 with the WENO stage (plane kernels) at 256^3, same model and source."""
+    from ttcr_b200 import Grid3d
+    n = 256
+    x, s = gradient_model(n, np.float64)
+    src = np.array([[0.0, 0.0, 0.0]])
+    out = {"workload": "256^3 gradient model, corner source", "unit": UNIT}
+    for name, dtype, weno in (("fp64_first_order", np.float64, 0), ("fp32_weno", np.float32, 1), ("fp64_weno", np.float64, 1)):
+        g = Grid3d(x, x, x, cell_slowness=0, tt_from_rp=0, eps=1e-5, maxit=50, weno=weno, dtype=dtype, device=local_rank)
+        g.set_slowness(s.astype(dtype))
+        g.solve(src)
+        st = g.solve(src)
+        out[name] = {"solve_ms": st["solve_ms"], "niter": st["niter"], "niterw": st["niterw"],
+                     "value": float(n) ** 3 * st["sweeps"] / (st["solve_ms"] * 1e-3) / 1e6}
+        g.close()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -439,12 +458,16 @@ def main():
         except Exception as e:   # a side line never costs the headline
             c4 = {"error": str(e)}
 
-    g2 = None
+    g2 = dflt = None
     if rank == 0 and n == 512:
         try:
             g2 = grid2d_side()
         except Exception as e:
             g2 = {"error": str(e)}
+        try:
+            dflt = default_path_side(local_rank)
+        except Exception as e:
+            dflt = {"error": str(e)}
 
     # ---- reduce over ranks: whole-job node-sweeps, max time ------------------------------------------
     nodes = float(n) ** 3
@@ -487,7 +510,7 @@ def main():
                        "sweep_ms_per_step": sweep_ms / args.steps, "wall_ms_per_step": mx[2] / args.steps,
                        "mnode_iters_per_s": value / 8.0, "kernel": st["kernel"],
                        "device_bytes": g.device_bytes(), "launches_per_step": launches / args.steps,
-                       "concurrent_sources": pair, "config4": c4, "grid2d": g2},
+                       "concurrent_sources": pair, "config4": c4, "grid2d": g2, "default_arguments": dflt},
         }
         if not args.no_cpu_baseline:
             try:
