@@ -66,6 +66,47 @@ def check(quick=False):
     return ok
 
 
+def wcheck(quick=False):
+    """WENO stage: the marching kernel's WENO variant against the plane kernels, bit for bit (fp32, weno=1)"""
+    rng = np.random.default_rng(0)
+    ok = True
+    shapes = [((40, 33, 70), [3.3, 2.2, 9.1]), ((65, 64, 31), [0, 0, 0]), ((33, 100, 45), [8.0, 20.0, 11.0]),
+              ((129, 128, 130), [16.0, 16.0, 16.0]), ((21, 30, 200), [2.6, 3.1, 30.2]), ((16, 16, 16), [3.75, 3.75, 3.75]), ((7, 6, 5), [0.5, 0.25, 0.1])]
+    if quick:
+        shapes = shapes[:2]
+    for shape, src in shapes:
+        x, y, z = (np.arange(m) * 0.25 for m in shape)
+        X, Y, Z = np.meshgrid(x, y, z, indexing="ij")
+        s = (1 + 0.3 * np.sin(0.7 * X) * np.cos(0.9 * Y)) / (1 + 0.1 * Z) + 0.02 * rng.uniform(0, 1, shape)
+        res = []
+        for opts in ({"weno_kernel": PLANE}, {"weno_kernel": MARCH}, {"weno_kernel": MARCH, "max_ctas": 3}):
+            g = Grid3d(x, y, z, cell_slowness=0, tt_from_rp=False, weno=1, maxit=8, dtype=np.float32)
+            g.set_option("spin_limit", 1 << 16)
+            for k, v in opts.items():
+                g.set_option(k, v)
+            try:
+                g.raytrace(np.array([src]), np.array([src]), s)
+            except Exception as e:  # noqa: BLE001
+                print(shape, opts, "FAILED:", e, flush=True)
+                ok = False
+                res.append(None)
+                continue
+            st = g.get_stats()
+            res.append((g.get_grid_traveltimes(), g.get_niter()))
+            print(shape, opts, "niter", g.get_niter(), f"solve {st['solve_ms']:.2f} ms", flush=True)
+        for r in res[1:]:
+            if r is None or res[0] is None:
+                continue
+            same = np.array_equal(r[0], res[0][0]) and r[1] == res[0][1]
+            if not same:
+                d = np.abs(r[0].astype(np.float64) - res[0][0])
+                bad = np.argwhere(d > 0)
+                print("   MISMATCH max", d.max(), "count", np.count_nonzero(d), "of", d.size, "niter", r[1], res[0][1], "first", bad[:6].tolist(), flush=True)
+            ok &= same
+    print("WCHECK", "OK" if ok else "FAILED", flush=True)
+    return ok
+
+
 def timing(sizes, combos=None):
     for n in sizes:
         x, s = gradient(n)
@@ -115,6 +156,8 @@ if __name__ == "__main__":
     if sys.argv[1] == "one":
         one(tuple(int(a) for a in sys.argv[2].split("x")), sys.argv[3:])
         sys.exit(0)
+    if sys.argv[1] == "wcheck":
+        sys.exit(0 if wcheck(len(sys.argv) > 2 and sys.argv[2] == "quick") else 1)
     if sys.argv[1] == "check":
         sys.exit(0 if check(len(sys.argv) > 2 and sys.argv[2] == "quick") else 1)
     timing([int(a) for a in sys.argv[2:]])

@@ -23,6 +23,7 @@
 #include "sweep_tile.cuh"
 #include "raypath.cuh"
 #include "sweep_march.cuh"
+#include "sweep_march_weno.cuh"
 #include "grid2d.cuh"
 
 namespace ttcrb200 {
@@ -163,6 +164,7 @@ class Grid final : public GridBase {
             cudaFree(s.d_pts); cudaFreeHost(s.h_pts);
             tile_free(s.tile);
             march_free(s.march);
+            marchw_free(s.marchw);
             cudaEventDestroy(s.e0); cudaEventDestroy(s.e1);
             cudaStreamDestroy(s.stream);
         }
@@ -429,8 +431,8 @@ class Grid final : public GridBase {
         else if (key == "plane_graph") plane_graph_ = v != 0;
         else if (key == "coop_ctas") coop_ctas_ = std::max(1, std::min(8, (int)v));
         else if (key == "weno_kernel") {
-            if (v != TTCR_B200_KERNEL_AUTO && v != TTCR_B200_KERNEL_PLANE && v != TTCR_B200_KERNEL_COOP)
-                throw Err(TTCR_B200_ERR_INVALID, "weno_kernel: AUTO, PLANE or COOP");
+            if (v != TTCR_B200_KERNEL_AUTO && v != TTCR_B200_KERNEL_PLANE && v != TTCR_B200_KERNEL_COOP && v != TTCR_B200_KERNEL_MARCH)
+                throw Err(TTCR_B200_ERR_INVALID, "weno_kernel: AUTO, PLANE, COOP or MARCH");
             weno_kernel_ = (int)v;
         }
         else if (key == "plane_pdl") plane_pdl_ = v != 0;
@@ -454,6 +456,7 @@ class Grid final : public GridBase {
         size_t pts_cap = 0;
         TileState tile;
         MarchState march;
+        MarchWState marchw;
         ttcr_b200_stats st{};
         unsigned* d_bar = nullptr;           // arrival counter of k_sweep_planes_coop's grid barrier
         FrozenBox* d_fb = nullptr;           // the source's frozen box, for k_sweep_plane (launch arguments stay source independent)
@@ -544,6 +547,12 @@ class Grid final : public GridBase {
     void launch_sweep(Slot& s, int dir, bool weno_stage, const FrozenBox& fb, int kernel) {
         const SweepView w = make_view(d_, dir);
         T* tt = s.tt[w.layout];
+        if (kernel == TTCR_B200_KERNEL_MARCH && weno_stage) {
+            const int nl = marchw_sweep<T>(s.tile, s.marchw, tile_opt_, sm_count_, w, d_, tt, slo_[w.layout], s.mask[w.layout], fb,
+                                          g_.dx, s.d_change, s.stream);
+            s.st.launches += nl; s.st.sweep_launches += nl;
+            return;
+        }
         if (kernel == TTCR_B200_KERNEL_MARCH) {
             const int nl = march_sweep<T>(s.tile, s.march, tile_opt_, sm_count_, w, d_, tt, slo_[w.layout], s.mask[w.layout], fb,
                                          g_.dx, s.d_change, s.stream);
@@ -644,7 +653,11 @@ class Grid final : public GridBase {
     }
 
     int plane_kernel() const {
-        if (weno_kernel_ != TTCR_B200_KERNEL_AUTO) return weno_kernel_;
+        if (weno_kernel_ == TTCR_B200_KERNEL_MARCH) {
+            if (marchw_supported<T>()) return TTCR_B200_KERNEL_MARCH;   // fp32: the marching kernel's WENO variant (sweep_march_weno.cuh)
+        } else if (weno_kernel_ != TTCR_B200_KERNEL_AUTO) {
+            return weno_kernel_;
+        }
         const int widest = (d_.kpad / 32) * ((std::min(d_.ni, d_.q) + 7) / 8);
         return widest >= 4 * sm_count_ ? TTCR_B200_KERNEL_COOP : TTCR_B200_KERNEL_PLANE;
     }
