@@ -317,6 +317,23 @@ def default_path_side(local_rank):
         out[name] = {"solve_ms": st["solve_ms"], "niter": st["niter"], "niterw": st["niterw"],
                      "value": float(n) ** 3 * st["sweeps"] / (st["solve_ms"] * 1e-3) / 1e6}
         g.close()
+    # the reference's default path (weno=1) at the HEADLINE size, fp32: first-order stage (k_sweep_march) + WENO stage
+    # (k_sweep_march_weno) of the same 512^3 workload; a WENO sweep moves the same 12 algorithmic bytes per node
+    n = 512
+    x, s = gradient_model(n, np.float32)
+    g = Grid3d(x, x, x, cell_slowness=0, tt_from_rp=0, eps=1e-5, maxit=50, weno=1, dtype=np.float32, device=local_rank)
+    g.set_slowness(s)
+    g.solve(src)
+    st = g.solve(src)
+    peak, _ = peaks()
+    per_sweep_ms = st["sweep_ms"] / max(st["sweeps"], 1)
+    out["weno"] = {"workload": "512^3 gradient model, corner source, fp32, weno=1 (first-order stage + WENO stage)",
+                   "solve_ms": st["solve_ms"], "niter": st["niter"], "niterw": st["niterw"], "sweeps": st["sweeps"],
+                   "value": float(n) ** 3 * st["sweeps"] / (st["solve_ms"] * 1e-3) / 1e6,
+                   "avg_sweep_ms": per_sweep_ms,
+                   "roofline_frac": BYTES_PER_NODE_SWEEP * float(n) ** 3 / (per_sweep_ms * 1e-3) / 1e9 / peak,
+                   "kernel": "k_sweep_march_weno (WENO stage), k_sweep_march (first-order stage)"}
+    g.close()
     return out
 
 

@@ -372,8 +372,14 @@ def test_cxx_adapter_linked_and_run():
 
 def test_fp32_weno_iteration_counts_match_the_float_oracle_128(oracle):
     """The reference's default (weno=1) in float at 128^3: first-order and WENO iteration counts equal the float oracle's
-    (Grid3Drnfs.h:125-136), field within the fp32 WENO tolerance.  Pins that the device's WENO stage converges exactly when
-    the reference's float build does."""
+    (Grid3Drnfs.h:125-136), i.e. the device's WENO stage converges exactly when the reference's float build does.
+
+    Field tolerance.  The WENO weights switch between stencils where second differences are at rounding level, so two fp32
+    evaluations of the scheme settle on fixed points that differ at isolated nodes: at this size the reference's own
+    Grid3Drnfs<float> and Grid3Drnfs<double> differ by 2.6e-3 max / 7.6e-5 mean / 4.9e-4 at the 99.9 % quantile (measured;
+    asserted below as the yardstick).  The device is held to (a) the float reference: mean <= 1e-5, 99 % of the nodes <= 1e-4,
+    99.9 % <= 2e-4 (measured 4.1e-6 / 6.0e-5 / 1.2e-4), max <= 2e-3; (b) the DOUBLE reference: no further from it than the
+    reference's float build is, quantile by quantile (+5 %)."""
     from ttcr_b200 import Grid3d
     n = 128
     x = np.linspace(0.0, 20.0, n)
@@ -382,11 +388,48 @@ def test_fp32_weno_iteration_counts_match_the_float_oracle_128(oracle):
     src = np.array([[x[n // 3], x[n // 2], x[n // 5]]])
     g = Grid3d(x, x, x, cell_slowness=0, tt_from_rp=False, weno=1, dtype=np.float32)
     g.raytrace(src, src, s)
+    f = g.get_grid_traveltimes().astype(np.float64)
     dx = float(np.float32(x[1]) - np.float32(x[0]))
     ref, ni, nw = oracle.solve(n - 1, n - 1, n - 1, dx, oracle.to_cxx(s), src.astype(np.float32), 0.0, weno=True, dtype=np.float32)
+    ref = oracle.from_cxx(ref, (n, n, n)).astype(np.float64)
     assert g.get_niter() == (ni, nw)
     assert nw < 50                                  # converged, not stopped by maxit
-    check_fp32(g.get_grid_traveltimes(), oracle.from_cxx(ref, (n, n, n)), dx * float(s.min()), True)
+    xd = x.astype(np.float32).astype(np.float64)    # the same float-valued problem in double
+    refd, _, _ = oracle.solve(n - 1, n - 1, n - 1, float(xd[1] - xd[0]), oracle.to_cxx(s.astype(np.float64)),
+                              src.astype(np.float32).astype(np.float64), 0.0, weno=True, dtype=np.float64)
+    refd = oracle.from_cxx(refd, (n, n, n))
+    floor = dx * float(s.min())
+
+    def err(a, b):
+        e = np.abs(a - b) / np.maximum(b, floor)
+        return e.mean(), np.quantile(e, 0.99), np.quantile(e, 0.999), e.max()
+
+    dev_f, dev_d, ref_d = err(f, ref), err(f, refd), err(ref, refd)
+    assert dev_f[0] <= 1e-5 and dev_f[1] <= RTOL32 and dev_f[2] <= 2e-4 and dev_f[3] <= 2e-3, dev_f
+    assert all(a <= 1.05 * b for a, b in zip(dev_d, ref_d)), (dev_d, ref_d)
+    assert ref_d[2] > RTOL32                        # the yardstick: float vs double reference exceeds 1e-4 at the 99.9 % quantile
+
+
+@pytest.mark.parametrize("shape,src", [((40, 33, 70), [3.3, 2.2, 9.1]), ((65, 64, 31), [0, 0, 0]), ((33, 100, 45), [8.0, 20.0, 11.0]),
+                                       ((129, 128, 130), [16.0, 16.0, 16.0]), ((21, 30, 200), [2.6, 3.1, 30.2]), ((7, 6, 5), [0.5, 0.25, 0.1])])
+def test_weno_march_and_plane_kernels_agree_bitwise(shape, src):
+    """fp32 WENO stage: k_sweep_march_weno (the default) against the per-plane kernel (the OpenCL design), bit for bit, on ragged
+    shapes (tiles cut by the grid's faces, sources on and off nodes, fewer CTAs than tiles)"""
+    from ttcr_b200 import Grid3d
+    rng = np.random.default_rng(0)
+    x, y, z = (np.arange(m) * 0.25 for m in shape)
+    X, Y, Z = np.meshgrid(x, y, z, indexing="ij")
+    s = (1 + 0.3 * np.sin(0.7 * X) * np.cos(0.9 * Y)) / (1 + 0.1 * Z) + 0.02 * rng.uniform(0, 1, shape)
+    res = []
+    for opts in ({"weno_kernel": 1}, {"weno_kernel": 7}, {"weno_kernel": 7, "max_ctas": 3}):
+        g = Grid3d(x, y, z, cell_slowness=0, tt_from_rp=False, weno=1, maxit=8, dtype=np.float32)
+        for k, v in opts.items():
+            g.set_option(k, v)
+        g.raytrace(np.array([src]), np.array([src]), s)
+        res.append((g.get_grid_traveltimes(), g.get_niter()))
+    for f, it in res[1:]:
+        assert it == res[0][1]
+        assert np.array_equal(f, res[0][0])
 
 
 def test_save_tt_formats_1_and_3(tmp_path):

@@ -21,5 +21,16 @@ for n in [int(a) for a in sys.argv[1:]] or [64, 128]:
         dx = float(np.float32(x[1]) - np.float32(x[0]))
         ref, ni, nw = O.solve(n - 1, n - 1, n - 1, dx, O.to_cxx(s), src.astype(np.float32), 0.0, weno=True, dtype=np.float32)
         ref = O.from_cxx(ref, (n, n, n))
-        e = np.abs(f.astype(np.float64) - ref) / np.maximum(ref, dx * float(s.min()))
-        print(f"n={n} {name}: gpu niter {g.get_niter()} oracle ({ni},{nw})  err max {e.max():.3g} mean {e.mean():.3g} q99.9 {np.quantile(e, 0.999):.3g}", flush=True)
+        # the reference in DOUBLE on the same (float-valued) model: how far is the reference's own float build from it?
+        xd = x.astype(np.float32).astype(np.float64)
+        refd, nid, nwd = O.solve(n - 1, n - 1, n - 1, float(xd[1] - xd[0]), O.to_cxx(s.astype(np.float64)), src.astype(np.float32).astype(np.float64), 0.0,
+                                 weno=True, dtype=np.float64)
+        refd = O.from_cxx(refd, (n, n, n))
+        floor = dx * float(s.min())
+        def q(a, b):
+            e = np.abs(a.astype(np.float64) - b) / np.maximum(b, floor)
+            return f"max {e.max():.3g} mean {e.mean():.3g} q99 {np.quantile(e, 0.99):.3g} q99.9 {np.quantile(e, 0.999):.3g}"
+        print(f"n={n} {name}: gpu niter {g.get_niter()} float oracle ({ni},{nw}) double oracle ({nid},{nwd})", flush=True)
+        print(f"    gpu fp32     vs float  oracle: {q(f, ref)}", flush=True)
+        print(f"    gpu fp32     vs double oracle: {q(f, refd)}", flush=True)
+        print(f"    float oracle vs double oracle: {q(ref, refd)}", flush=True)

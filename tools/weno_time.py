@@ -10,7 +10,8 @@ for n in [int(a) for a in sys.argv[1:]] or [256]:
     x = np.linspace(0.0, 20.0, n)
     s = np.ascontiguousarray(np.broadcast_to((1.0 / (1.0 + 0.1 * x))[None, None, :], (n, n, n)), dtype=np.float32)
     src = np.array([[0.0, 0.0, 0.0]])
-    for graph, pdl, wk, cc in ((1, 1, 1, 0), (0, 0, 6, 2), (0, 0, 6, 4), (0, 0, 6, 8)):
+    variants = ((1, 1, 7, 0), (1, 1, 1, 0), (0, 0, 6, 4)) if n <= 256 else ((1, 1, 7, 0), (0, 0, 6, 4))
+    for graph, pdl, wk, cc in variants:
         g = Grid3d(x, x, x, cell_slowness=0, tt_from_rp=False, weno=1, dtype=np.float32)
         g.set_option("plane_graph", graph)
         g.set_option("plane_pdl", pdl)

@@ -486,9 +486,9 @@ class Grid final : public GridBase {
         return slots_[slot];
     }
 
-    void ensure_lin() {
-        if (lin_[0]) return;
-        for (int l = 0; l < 2; ++l) {
+    void ensure_lin() {   // lin_[1] holds the averaged node model of a cell grid; node grids never need it
+        for (int l = 0; l < (cell_ ? 2 : 1); ++l) {
+            if (lin_[l]) continue;
             CK(cudaMalloc(&lin_[l], d_.nodes() * sizeof(T)));
             bytes_ += d_.nodes() * sizeof(T);
         }
@@ -653,11 +653,11 @@ class Grid final : public GridBase {
     }
 
     int plane_kernel() const {
-        if (weno_kernel_ == TTCR_B200_KERNEL_MARCH) {
-            if (marchw_supported<T>()) return TTCR_B200_KERNEL_MARCH;   // fp32: the marching kernel's WENO variant (sweep_march_weno.cuh)
-        } else if (weno_kernel_ != TTCR_B200_KERNEL_AUTO) {
-            return weno_kernel_;
-        }
+        // fp32: the marching kernel's WENO variant (sweep_march_weno.cuh), measured faster than the plane kernels at every
+        // size from 7 x 6 x 5 to 512^3 (3.4x at 512^3); fp64: plane kernels
+        if ((weno_kernel_ == TTCR_B200_KERNEL_MARCH || weno_kernel_ == TTCR_B200_KERNEL_AUTO) && marchw_supported<T>())
+            return TTCR_B200_KERNEL_MARCH;
+        if (weno_kernel_ != TTCR_B200_KERNEL_AUTO && weno_kernel_ != TTCR_B200_KERNEL_MARCH) return weno_kernel_;
         const int widest = (d_.kpad / 32) * ((std::min(d_.ni, d_.q) + 7) / 8);
         return widest >= 4 * sm_count_ ? TTCR_B200_KERNEL_COOP : TTCR_B200_KERNEL_PLANE;
     }
@@ -724,14 +724,18 @@ class Grid final : public GridBase {
                     if (!((dbg_dirs >> dir) & 1)) continue;   // debugging aid: run a subset of the sweep directions
                     const int want = make_view(d_, dir).layout;
                     if (want != cur) {
-                        static const bool old_relayout = getenv("TTCR_B200_OLD_RELAYOUT") != nullptr;
-                        if (old_relayout) {
+                        static const int relayout_kernel = getenv("TTCR_B200_RELAYOUT") ? atoi(getenv("TTCR_B200_RELAYOUT")) : 3;
+                        if (relayout_kernel == 1) {
                             const dim3 grid((d_.nk + 31) / 32, (d_.nj + 31) / 32, d_.ni);
                             k_relayout<T><<<grid, dim3(32, 8), 0, s.stream>>>(s.tt[cur], cur, s.tt[want], d_);
-                        } else {
+                        } else if (relayout_kernel == 2) {
                             constexpr int RB = 128;
                             const dim3 grid(d_.kpad / 32, (d_.q + RB - 1) / RB, d_.ni);
                             k_relayout2<T, RB><<<grid, dim3(32, 8), 0, s.stream>>>(s.tt[cur], cur, s.tt[want], d_);
+                        } else {
+                            constexpr int RB = sizeof(T) == 4 ? 256 : 128;   // (RB + 62) x 128 or 256 bytes of shared memory
+                            const dim3 grid(d_.kpad / 32, (d_.q + RB - 1) / RB, d_.ni);
+                            k_relayout3<T, RB><<<grid, dim3(32, 8), 0, s.stream>>>(s.tt[cur], cur, s.tt[want], d_);
                         }
                         s.st.launches += 1;
                         cur = want;

@@ -165,7 +165,7 @@ __device__ __forceinline__ void mbar_arrive_ifu(unsigned a, unsigned on) {
 
 // Cold paths of a march step, out of line so that the hot loop stays small (it is unrolled four times in four variants).
 // Wait for the ring words of step `tgs`: 0 = there, 1 = another warp gave up, 2 = timeout.
-__device__ __noinline__ int march_wait_words(unsigned rUi, unsigned rVi, unsigned tgs, unsigned a_dead, long long spin_cycles, unsigned spin_polls,
+static __device__ __noinline__ int march_wait_words(unsigned rUi, unsigned rVi, unsigned tgs, unsigned a_dead, long long spin_cycles, unsigned spin_polls,
                                              unsigned sleep_ns) {
     long long t0 = 0;
     for (unsigned it = 1;; ++it) {
@@ -183,7 +183,7 @@ __device__ __noinline__ int march_wait_words(unsigned rUi, unsigned rVi, unsigne
     }
 }
 // Wait for a chunk to land (phase `par` of its "full" barrier): same return values.
-__device__ __noinline__ int march_wait_full(unsigned a_full, unsigned par, unsigned a_dead, long long spin_cycles) {
+static __device__ __noinline__ int march_wait_full(unsigned a_full, unsigned par, unsigned a_dead, long long spin_cycles) {
     const long long t0 = clock64();
     while (!mbar_test(a_full, par)) {
         if (lds_i(a_dead)) return 1;
@@ -728,8 +728,20 @@ inline int march_sweep(TileState&, MarchState&, const TileOptions&, int, const S
                        const FrozenBox&, T, double*, cudaStream_t) {
     throw std::runtime_error("march kernel: fp32 only");
 }
+// The fp32 instances are compiled in their own translation unit (march_inst.cu) so that the library builds in parallel:
+// with TTCR_B200_SPLIT_BUILD a unit sees the declaration only unless it defines TTCR_B200_MARCH_DEFINE (march_inst.cu).
+#if defined(TTCR_B200_SPLIT_BUILD) && !defined(TTCR_B200_MARCH_DEFINE)
 template <>
-inline int march_sweep<float>(TileState& s, MarchState& ms, const TileOptions& o, int sm_count, const SweepView& w, const Dims& d, float* tt,
+int march_sweep<float>(TileState& s, MarchState& ms, const TileOptions& o, int sm_count, const SweepView& w, const Dims& d, float* tt,
+                              const float* slo, const uint32_t* frozen, const FrozenBox& fb, float dx, double* d_change, cudaStream_t st);   // defined in march_inst.cu
+#else
+#ifdef TTCR_B200_MARCH_DEFINE
+#define TTCR_B200_MARCH_DEFINE_LINKAGE
+#else
+#define TTCR_B200_MARCH_DEFINE_LINKAGE inline
+#endif
+template <>
+TTCR_B200_MARCH_DEFINE_LINKAGE int march_sweep<float>(TileState& s, MarchState& ms, const TileOptions& o, int sm_count, const SweepView& w, const Dims& d, float* tt,
                               const float* slo, const uint32_t* frozen, const FrozenBox& fb, float dx, double* d_change, cudaStream_t st) {
     // <warps along u, warps along v, chunk slots of the box ring>; tile = 4 WU planes x 16 WV lanes
     if (o.warps == 12) return march_launch<6, 2, 5>(s, ms, o, sm_count, w, d, tt, slo, frozen, fb, dx, d_change, st);
@@ -737,5 +749,6 @@ inline int march_sweep<float>(TileState& s, MarchState& ms, const TileOptions& o
     if (o.depth == 3) return march_launch<4, 2, 3>(s, ms, o, sm_count, w, d, tt, slo, frozen, fb, dx, d_change, st);   // two CTAs per SM
     return march_launch<4, 2, 6>(s, ms, o, sm_count, w, d, tt, slo, frozen, fb, dx, d_change, st);
 }
+#endif
 
 }  // namespace ttcrb200

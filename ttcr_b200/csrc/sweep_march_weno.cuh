@@ -82,7 +82,7 @@ struct MarchWGeom {
 };
 
 // Cold path of a WENO march step: wait for BOTH halves of the ring words of step `tgs` (same return values as march_wait_words)
-__device__ __noinline__ int marchw_wait_words(unsigned rUi, unsigned rVi, unsigned tgs, unsigned a_dead, long long spin_cycles, unsigned spin_polls,
+static __device__ __noinline__ int marchw_wait_words(unsigned rUi, unsigned rVi, unsigned tgs, unsigned a_dead, long long spin_cycles, unsigned spin_polls,
                                               unsigned sleep_ns) {
     long long t0 = 0;
     for (unsigned it = 1;; ++it) {
@@ -333,7 +333,6 @@ k_sweep_march_weno(const __grid_constant__ CUtensorMap tmT, const __grid_constan
                                                     ((lv == 7 && out_v_in) ? F_STV : 0u) | ((lu == 3 && !out_u_in && T.has_down) ? F_OMU : 0u) |
                                                     ((lv == 7 && !out_v_in && T.has_right) ? F_OMV : 0u) |
                                                     (fzme ? F_FZ : 0u)));
-            const bool mail_warp = __any_sync(0xffffffffu, (fl & (F_OMU | F_OMV)) != 0);
             const float QNAN = __int_as_float(0x7fc00000);
 
             int dead = 0;
@@ -380,7 +379,7 @@ k_sweep_march_weno(const __grid_constant__ CUtensorMap tmT, const __grid_constan
             float acc = 0.f;
             if (p.trace && threadIdx.x == 0) p.trace[tile * 16 + 1] = gtime();
 
-            // Groups of C steps (tags t .. t+C-1) read chunk `sb`; groups in [ts0, ts1) may touch a frozen node and run the SLOW body; warps that feed a global mailbox run the MAILW bodies.
+            // Groups of C steps (tags t .. t+C-1) read chunk `sb`; groups in [ts0, ts1) may touch a frozen node.
             const unsigned t_end = (unsigned)nA + 1u;
             unsigned ts0 = t_end, ts1 = t_end;
             if (wz_hi >= wz_lo) {
@@ -400,10 +399,11 @@ k_sweep_march_weno(const __grid_constant__ CUtensorMap tmT, const __grid_constan
             };
 
             // One march step: ring words at rUi / rVi must carry a tag >= tgs, outputs go to rUo / rVo with tag tgs + 1, the next
-            // step's operands are at `ao`.
-            auto step = [&](const int r, const unsigned tgs, const unsigned rUi, const unsigned rVi, const unsigned rUo, const unsigned rVo, const unsigned ao,
-                            auto slow_c, auto mail_c) {
-                constexpr bool SLOW = decltype(slow_c)::value != 0, MAILW = decltype(mail_c)::value != 0;
+            // step's operands are at `ao`.  ONE copy of this body exists in the kernel (the group loop below is not unrolled and
+            // the frozen-node and mailbox cases are run-time predicates): a step is ~500 instructions, and every copy more is
+            // 8 KB that eight warps at eight different places of the loop pull through a 32 KB instruction cache.
+            auto step = [&](const unsigned tgs, const unsigned rUi, const unsigned rVi, const unsigned rUo, const unsigned rVo, const unsigned ao,
+                            const bool slowg) {
                 // ---- (1) everything this step reads from shared memory
                 uint4 xu = lds_u4(rUi), xu2 = lds_u4(rUi + USLOT / 2);
                 uint2 xv = lds_u2(rVi), xv2 = lds_u2(rVi + VSLOT / 2);
@@ -420,13 +420,11 @@ k_sweep_march_weno(const __grid_constant__ CUtensorMap tmT, const __grid_constan
                     if (st) dead = 1;
                     xu = lds_u4(rUi); xu2 = lds_u4(rUi + USLOT / 2); xv = lds_u2(rVi); xv2 = lds_u2(rVi + VSLOT / 2);
                 }
-                if (SLOW) {
-                    if (fl & F_FZ) {   // (the pair shares a mask word: e is even)
-                        const long long e = (long long)((float*)(pg0 + poff) - tt);
-                        const unsigned bits = frozen[e >> 5] >> (e & 31);
-                        if (bits & (RK ? 2u : 1u)) s0 = QNAN;
-                        if (bits & (RK ? 1u : 2u)) s1 = QNAN;
-                    }
+                if (slowg && (fl & F_FZ)) {   // (the pair shares a mask word: e is even)
+                    const long long e = (long long)((float*)(pg0 + poff) - tt);
+                    const unsigned bits = frozen[e >> 5] >> (e & 31);
+                    if (bits & (RK ? 2u : 1u)) s0 = QNAN;
+                    if (bits & (RK ? 1u : 2u)) s1 = QNAN;
                 }
                 if (fl & F_U0) {
                     um10 = __uint_as_float(xu.x); um11 = __uint_as_float(xu.z);
@@ -450,12 +448,11 @@ k_sweep_march_weno(const __grid_constant__ CUtensorMap tmT, const __grid_constan
                 sts_u4_ifu(rUo, __float_as_uint(n0), tgs + 1, __float_as_uint(n1), tgs + 1, fl & F_STU);
                 sts_u2_ifu(rVo + VSLOT / 2, __float_as_uint(p0), tgs + 1, fl & F_STV);
                 sts_u2_ifu(rVo, __float_as_uint(n1), tgs + 1, fl & F_STV);
-                if (MAILW) {
-                    st_mail2_if(mu + r * (2 * TW) + TW, serial, um10, um11, (int)(fl & F_OMU));   // (mu, mv: the group's first step)
-                    st_mail2_if(mu + r * (2 * TW), serial, n0, n1, (int)(fl & F_OMU));
-                    st_mail_if(mv + r * (2 * PUT) + PUT, serial, p0, (int)(fl & F_OMV));
-                    st_mail_if(mv + r * (2 * PUT), serial, n1, (int)(fl & F_OMV));
-                }
+                st_mail2_if(mu + TW, serial, um10, um11, (int)(fl & F_OMU));   // (mu, mv: this step's mailbox rows)
+                st_mail2_if(mu, serial, n0, n1, (int)(fl & F_OMU));
+                st_mail_if(mv + PUT, serial, p0, (int)(fl & F_OMV));
+                st_mail_if(mv, serial, n1, (int)(fl & F_OMV));
+                mu += 2 * TW; mv += 2 * PUT;
                 // ---- (6) result, change sum, rotate the operands
                 stg_f2_stream_if((float*)(pg0 + poff), RK ? n1 : n0, RK ? n0 : n1, (n0 < O0 || n1 < O1) ? 1 : 0);
                 poff += rowbytes;
@@ -470,20 +467,24 @@ k_sweep_march_weno(const __grid_constant__ CUtensorMap tmT, const __grid_constan
                 s0 = RK ? ns.y : ns.x; s1 = RK ? ns.x : ns.y;
                 jtA += RJ ? -1 : 1;
             };
-            auto group = [&](auto slow_c, auto mail_c) {
+            // A group = the C steps that read chunk `sb`; its last step takes the next operands from the next chunk.
+            while (t < t_end && !deadw) {
+                const bool slowg = t >= ts0 && t < ts1;
                 // chunk slot of the next group (and the parity of its "full" phase: it flips when the ring wraps)
                 unsigned nslot = cslot + 1, npar = cpar;
                 if (nslot == NCH) { nslot = 0; npar ^= 1u; }
                 const unsigned sbn = sbase + nslot * L::CHB;
                 const unsigned so_n = (so + C * USLOT) & (unsigned)(URING - 1);
                 const unsigned gUn = aUin + so_n, gVn = aVin + (so_n >> 2);
-#pragma unroll
-                for (int r = 0; r < C - 1; ++r)
-                    step(r, t + r, gU + r * USLOT, gV + r * VSLOT, gU + OUT_U + (r + 1) * USLOT, gV + OUT_V + (r + 1) * VSLOT,
-                         rB + (unsigned)((r + 1) * G::DR), slow_c, mail_c);
-                wait_full(sbn + L::OFF_FULL, npar, 42);   // the chunk the last step of the group takes the next operands from
-                step(C - 1, t + C - 1, gU + (C - 1) * USLOT, gV + (C - 1) * VSLOT, gUn + OUT_U, gVn + OUT_V, sbn + toff, slow_c, mail_c);
-                if (decltype(mail_c)::value) { mu += C * (2 * TW); mv += C * (2 * PUT); }
+                unsigned aU = gU, aV = gV, ao = rB;
+#pragma unroll 1
+                for (int r = 0; r < C; ++r) {
+                    const bool last = r == C - 1;
+                    if (last) wait_full(sbn + L::OFF_FULL, npar, 42);   // the chunk the last step takes the next operands from
+                    ao = last ? sbn + toff : ao + (unsigned)G::DR;
+                    step(t + (unsigned)r, aU, aV, last ? gUn + OUT_U : aU + OUT_U + USLOT, last ? gVn + OUT_V : aV + OUT_V + VSLOT, ao, slowg);
+                    aU += USLOT; aV += VSLOT;
+                }
                 // every lane has read the group's words and the chunk's last row (its values were used by the update above)
                 __syncwarp();
                 mbar_arrive_ifu(sb + L::OFF_EMPTY, fl & F_L0);
@@ -492,19 +493,7 @@ k_sweep_march_weno(const __grid_constant__ CUtensorMap tmT, const __grid_constan
                 sb = sbn; rB = sbn + toff; cslot = nslot; cpar = npar;
                 so = so_n; gU = gUn; gV = gVn;
                 deadw = __any_sync(0xffffffffu, dead);
-            };
-            auto march = [&](auto mail_c) {
-#pragma unroll 1
-                for (int seg = 0; seg < 3; ++seg) {
-                    const unsigned e = seg == 0 ? ts0 : (seg == 1 ? ts1 : t_end);
-                    if (seg == 1) {
-                        while (t < e && !deadw) group(IntC<1>(), mail_c);
-                    } else {
-                        while (t < e && !deadw) group(IntC<0>(), mail_c);
-                    }
-                }
-            };
-            if (mail_warp) march(IntC<1>()); else march(IntC<0>());
+            }
             // the last chunk (only its first row was read, by the prefetch of the last step) goes back to the loader, too
             if (!deadw) {
                 __syncwarp();
@@ -675,10 +664,21 @@ inline int marchw_sweep(TileState&, MarchWState&, const TileOptions&, int, const
                         const FrozenBox&, T, double*, cudaStream_t) {
     throw std::runtime_error("march kernel: fp32 only");
 }
+#if defined(TTCR_B200_SPLIT_BUILD) && !defined(TTCR_B200_MARCHW_DEFINE)
 template <>
-inline int marchw_sweep<float>(TileState& s, MarchWState& ms, const TileOptions& o, int sm_count, const SweepView& w, const Dims& d, float* tt,
+int marchw_sweep<float>(TileState& s, MarchWState& ms, const TileOptions& o, int sm_count, const SweepView& w, const Dims& d, float* tt,
+                               const float* slo, const uint32_t* frozen, const FrozenBox& fb, float dx, double* d_change, cudaStream_t st);   // defined in marchw_inst.cu
+#else
+#ifdef TTCR_B200_MARCHW_DEFINE
+#define TTCR_B200_MARCHW_DEFINE_LINKAGE
+#else
+#define TTCR_B200_MARCHW_DEFINE_LINKAGE inline
+#endif
+template <>
+TTCR_B200_MARCHW_DEFINE_LINKAGE int marchw_sweep<float>(TileState& s, MarchWState& ms, const TileOptions& o, int sm_count, const SweepView& w, const Dims& d, float* tt,
                                const float* slo, const uint32_t* frozen, const FrozenBox& fb, float dx, double* d_change, cudaStream_t st) {
     return marchw_launch<4, 2, 4>(s, ms, o, sm_count, w, d, tt, slo, frozen, fb, dx, d_change, st);
 }
+#endif
 
 }  // namespace ttcrb200

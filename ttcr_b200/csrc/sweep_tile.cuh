@@ -487,7 +487,7 @@ __global__ void __launch_bounds__((NW + 2) * 32) k_sweep_tile(TileParams p, T* _
 }
 
 // sum of the per-tile partial changes in tile order (deterministic), added to *change
-__global__ void k_sum_partials(const double* __restrict__ partial, int n, double* __restrict__ change) {
+static __global__ void k_sum_partials(const double* __restrict__ partial, int n, double* __restrict__ change) {
     __shared__ double sh[256];
     double a = 0.0;
     for (int i = threadIdx.x; i < n; i += 256) a += partial[i];

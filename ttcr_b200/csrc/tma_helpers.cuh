@@ -61,7 +61,7 @@ __device__ __forceinline__ void st_mail_if(unsigned long long* p, unsigned seria
         "f"(t), "r"(serial), "r"(on)
         : "memory");
 }
-__device__ __noinline__ bool frozen_bit(const uint32_t* frozen, long long e) { return (frozen[e >> 5] >> (e & 31)) & 1u; }
+static __device__ __noinline__ bool frozen_bit(const uint32_t* frozen, long long e) { return (frozen[e >> 5] >> (e & 31)) & 1u; }
 
 __device__ __forceinline__ int lds_i(unsigned a) {
     int v;
