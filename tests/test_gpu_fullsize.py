@@ -53,17 +53,19 @@ def test_config3_512_gradient_properties():
     x, s = _gradient(n)
     src = np.array([[0.0, 0.0, 0.0]])
     fields = []
-    for kernel in (7, 2):
+    for kernel, nodes in ((7, 2), (7, 4), (2, 0)):                 # k_sweep_march, k_sweep_march4, k_sweep_tile
         g = Grid3d(x, x, x, cell_slowness=0, tt_from_rp=False, weno=0, dtype=np.float32)
         g.set_option("kernel", kernel)
+        g.set_option("march_nodes", nodes)
         g.raytrace(src, src, s)
         fields.append(g.get_grid_traveltimes())
         assert g.get_niter() == (2, 0)
-        if kernel == 7:
+        if kernel == 7 and nodes == 2:
             g.raytrace(src, src)                                   # idempotence: same call, same field
             assert np.array_equal(g.get_grid_traveltimes(), fields[0])
         del g
-    assert np.array_equal(fields[0], fields[1])                    # two independent marching kernels, bit for bit
+    assert np.array_equal(fields[0], fields[1])                    # independently written marching kernels, bit for bit
+    assert np.array_equal(fields[0], fields[2])
     f = fields[0]
     assert np.all(np.isfinite(f)) and f[0, 0, 0] == 0.0
     exact = _gradient_exact(x, src[0])

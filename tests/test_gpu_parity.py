@@ -34,17 +34,25 @@ def rel_err(a, ref, floor):
     return float(np.max(np.abs(a - ref) / np.maximum(np.abs(ref), floor)))
 
 
+def set_kernel(grid, kernel):
+    """kernel ids of include/ttcr_b200.h; 7 = the marching kernel with two nodes per thread (k_sweep_march), 74 = with four
+    (k_sweep_march4, which the library itself only picks for grids of ~700^3 and more)"""
+    grid.set_option("kernel", 7 if kernel == 74 else kernel)
+    if kernel in (7, 74):
+        grid.set_option("march_nodes", 4 if kernel == 74 else 2)
+
+
 def make_grid(g, kernel=None, n_threads=1):
     from ttcr_b200 import Grid3d
     grid = Grid3d(g["x"], g["y"], g["z"], n_threads=n_threads, cell_slowness=g["cell_slowness"], method="FSM",
                   tt_from_rp=False, eps=g["eps"], maxit=g["maxit"], weno=g["weno"], translate_grid=g["translate"],
                   dtype=g["dtype"])
     if kernel is not None:
-        grid.set_option("kernel", kernel)
+        set_kernel(grid, kernel)
     return grid
 
 
-@pytest.mark.parametrize("kernel", [1, 2, 6, 7])
+@pytest.mark.parametrize("kernel", [1, 2, 6, 7, 74])
 @pytest.mark.parametrize("name", golden_names())
 def test_golden(name, kernel):
     g = load_golden(name)
@@ -77,7 +85,7 @@ def _model(n, seed):
     return x, s
 
 
-@pytest.mark.parametrize("kernel", [1, 2, 6, 7])
+@pytest.mark.parametrize("kernel", [1, 2, 6, 7, 74])
 @pytest.mark.parametrize("dtype,weno,n", [(np.float32, 0, 64), (np.float32, 1, 64), (np.float64, 0, 48),
                                           (np.float64, 1, 40), (np.float32, 0, 97)])
 def test_against_oracle_seeded(oracle, kernel, dtype, weno, n):
@@ -86,7 +94,7 @@ def test_against_oracle_seeded(oracle, kernel, dtype, weno, n):
     x, s = _model(n, 100 + n)
     src = np.array([[x[n // 3], x[n // 2], x[n // 5]]])
     grid = Grid3d(x, x, x, cell_slowness=0, tt_from_rp=False, weno=weno, dtype=dtype)
-    grid.set_option("kernel", kernel)
+    set_kernel(grid, kernel)
     grid.raytrace(src, src, s)
     field = grid.get_grid_traveltimes()
     xt = x.astype(dtype)
@@ -112,7 +120,10 @@ def test_plane_and_tile_kernels_agree_bitwise():
     src = np.array([[0.1, 3.0, 2.0, 11.1]])
     out = []
     for kernel, opts in ((1, {}), (2, {}), (2, {"tile_urows": 2, "tile_depth": 4, "tile_rows": 2}),
-                         (7, {}), (7, {"tile_warps": 12}), (7, {"tile_depth": 3}), (7, {"max_ctas": 3}), (7, {"ctas_per_sm": 1, "max_ctas": 1}),
+                         (7, {"march_nodes": 2}), (7, {"march_nodes": 2, "tile_warps": 12}), (7, {"march_nodes": 2, "tile_depth": 3}),
+                         (7, {"march_nodes": 2, "max_ctas": 3}), (7, {"march_nodes": 2, "ctas_per_sm": 1, "max_ctas": 1}),
+                         (7, {"march_nodes": 4}), (7, {"march_nodes": 4, "max_ctas": 3}), (7, {"march_nodes": 4, "tile_warps": 4}),
+                         (7, {"march_nodes": 4, "tile_urows": 2}),
                          (1, {"plane_graph": 0, "plane_pdl": 0}), (1, {"plane_graph": 1, "plane_pdl": 0}),
                          (1, {"plane_graph": 0, "plane_pdl": 1}), (6, {}), (6, {"coop_ctas": 1}), (6, {"coop_ctas": 8}),
                          (7, {"weno_kernel": 1})):

@@ -35,7 +35,7 @@ def check(quick=False):
         x, y, z = (np.arange(m) * 0.25 for m in shape)
         s = rng.uniform(0.3, 1.0, shape)
         res = []
-        for kernel, opts in ((PLANE, {}), (MARCH, {}), (MARCH, {"tile_warps": 12}), (MARCH, {"tile_depth": 3}), (MARCH, {"max_ctas": 3})):
+        for kernel, opts in ((PLANE, {}), (MARCH, {"march_nodes": 4}), (MARCH, {"march_nodes": 4, "max_ctas": 3}), (MARCH, {"march_nodes": 2}), (MARCH, {"march_nodes": 2, "tile_warps": 12}), (MARCH, {"march_nodes": 2, "tile_depth": 3}), (MARCH, {"march_nodes": 2, "max_ctas": 3})):
             g = Grid3d(x, y, z, cell_slowness=0, tt_from_rp=False, weno=0, dtype=np.float32)
             g.set_option("kernel", kernel)
             g.set_option("spin_limit", 1 << 16)   # x 512 cycles = 17 ms per wait
@@ -113,10 +113,10 @@ def timing(sizes, combos=None):
         g = Grid3d(x, x, x, cell_slowness=0, tt_from_rp=False, weno=0, dtype=np.float32)
         g.set_slowness(s)
         print(f"--- {n}^3 device bytes {g.device_bytes() / 2**30:.2f} GiB", flush=True)
-        combos_n = combos or [dict(kernel=MARCH), dict(kernel=MARCH, tile_depth=3), dict(kernel=MARCH, tile_depth=3, ctas_per_sm=1), dict(kernel=MARCH, tile_warps=12)]
+        combos_n = combos or [dict(kernel=MARCH, march_nodes=4), dict(kernel=MARCH, march_nodes=2)]
         for src in ([0.0, 0.0, 0.0],):
             for c in combos_n:
-                g.set_option("tile_warps", 8); g.set_option("tile_urows", 1); g.set_option("ctas_per_sm", 0); g.set_option("tile_depth", 8)
+                g.set_option("tile_warps", 8); g.set_option("tile_urows", 1); g.set_option("ctas_per_sm", 0); g.set_option("tile_depth", 8); g.set_option("march_nodes", 0)
                 for k, v in c.items():
                     g.set_option(k, v)
                 best = None

@@ -23,6 +23,7 @@
 #include "sweep_tile.cuh"
 #include "raypath.cuh"
 #include "sweep_march.cuh"
+#include "sweep_march4.cuh"
 #include "sweep_march_weno.cuh"
 #include "grid2d.cuh"
 
@@ -164,6 +165,7 @@ class Grid final : public GridBase {
             cudaFree(s.d_pts); cudaFreeHost(s.h_pts);
             tile_free(s.tile);
             march_free(s.march);
+            march_free(s.march4);
             marchw_free(s.marchw);
             cudaEventDestroy(s.e0); cudaEventDestroy(s.e1);
             cudaStreamDestroy(s.stream);
@@ -428,6 +430,10 @@ class Grid final : public GridBase {
         else if (key == "tile_depth") tile_opt_.depth = (int)v;
         else if (key == "spin_limit") tile_opt_.spin_limit = (long long)v;
         else if (key == "max_ctas") tile_opt_.max_ctas = std::max(0, (int)v);
+        else if (key == "march_nodes") {
+            if (v != 0 && v != 2 && v != 4) throw Err(TTCR_B200_ERR_INVALID, "march_nodes: 0 (by grid size), 2 or 4");
+            tile_opt_.nodes = (int)v;
+        }
         else if (key == "plane_graph") plane_graph_ = v != 0;
         else if (key == "coop_ctas") coop_ctas_ = std::max(1, std::min(8, (int)v));
         else if (key == "weno_kernel") {
@@ -456,6 +462,7 @@ class Grid final : public GridBase {
         size_t pts_cap = 0;
         TileState tile;
         MarchState march;
+        MarchState march4;
         MarchWState marchw;
         ttcr_b200_stats st{};
         unsigned* d_bar = nullptr;           // arrival counter of k_sweep_planes_coop's grid barrier
@@ -549,6 +556,18 @@ class Grid final : public GridBase {
         T* tt = s.tt[w.layout];
         if (kernel == TTCR_B200_KERNEL_MARCH && weno_stage) {
             const int nl = marchw_sweep<T>(s.tile, s.marchw, tile_opt_, sm_count_, w, d_, tt, slo_[w.layout], s.mask[w.layout], fb,
+                                          g_.dx, s.d_change, s.stream);
+            s.st.launches += nl; s.st.sweep_launches += nl;
+            return;
+        }
+        // Two or four nodes per thread: the four-node step is 1.7x as long and does twice the work.  Where a sweep is bound by
+        // its chain of dependent steps (512^3: 3.5 tiles per SM) the two-node kernel wins (0.69 against 0.80 ms), where it is
+        // bound by the SMs' throughput the four-node kernel does (measured cross-over between 640^3 and 768^3; 1024^3: 3.39
+        // against 3.77 ms).
+        const long long tiles2 = (long long)((w.nu + 15) / 16) * (d_.kpad / 32);
+        const int nodes = tile_opt_.nodes ? tile_opt_.nodes : (tiles2 >= 1000 ? 4 : 2);
+        if (kernel == TTCR_B200_KERNEL_MARCH && nodes == 4) {
+            const int nl = march4_sweep<T>(s.tile, s.march4, tile_opt_, sm_count_, w, d_, tt, slo_[w.layout], s.mask[w.layout], fb,
                                           g_.dx, s.d_change, s.stream);
             s.st.launches += nl; s.st.sweep_launches += nl;
             return;
@@ -724,18 +743,16 @@ class Grid final : public GridBase {
                     if (!((dbg_dirs >> dir) & 1)) continue;   // debugging aid: run a subset of the sweep directions
                     const int want = make_view(d_, dir).layout;
                     if (want != cur) {
-                        static const int relayout_kernel = getenv("TTCR_B200_RELAYOUT") ? atoi(getenv("TTCR_B200_RELAYOUT")) : 3;
-                        if (relayout_kernel == 1) {
+                        // (a shared-memory version that reads whole row segments was measured 50 % slower than these gathers
+                        // through the L1: 0.43 ms instead of 0.28 ms per relayout at 512^3)
+                        static const bool old_relayout = getenv("TTCR_B200_OLD_RELAYOUT") != nullptr;
+                        if (old_relayout) {
                             const dim3 grid((d_.nk + 31) / 32, (d_.nj + 31) / 32, d_.ni);
                             k_relayout<T><<<grid, dim3(32, 8), 0, s.stream>>>(s.tt[cur], cur, s.tt[want], d_);
-                        } else if (relayout_kernel == 2) {
+                        } else {
                             constexpr int RB = 128;
                             const dim3 grid(d_.kpad / 32, (d_.q + RB - 1) / RB, d_.ni);
                             k_relayout2<T, RB><<<grid, dim3(32, 8), 0, s.stream>>>(s.tt[cur], cur, s.tt[want], d_);
-                        } else {
-                            constexpr int RB = sizeof(T) == 4 ? 256 : 128;   // (RB + 62) x 128 or 256 bytes of shared memory
-                            const dim3 grid(d_.kpad / 32, (d_.q + RB - 1) / RB, d_.ni);
-                            k_relayout3<T, RB><<<grid, dim3(32, 8), 0, s.stream>>>(s.tt[cur], cur, s.tt[want], d_);
                         }
                         s.st.launches += 1;
                         cur = want;

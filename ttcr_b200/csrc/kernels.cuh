@@ -137,37 +137,6 @@ __global__ void __launch_bounds__(256) k_relayout2(const T* __restrict__ src, in
     }
 }
 
-// L1 <-> L2 through shared memory: a block moves a band of RB destination rows of one 32-lane column.  The RB + 62 source
-// rows it needs (lane k reads the row shifted by nk-1-2k) are read as whole 128-byte row segments -- one request per row
-// instead of one per element as in k_relayout2, whose gathers keep the L1 busy with 32 sectors per warp load -- and the
-// sheared read happens in shared memory (row stride 32 words: lane = bank, conflict-free).
-// grid: (kpad/32, ceil(Q/RB), ni), block: (32, 8).
-template <typename T, int RB>
-__global__ void __launch_bounds__(256) k_relayout3(const T* __restrict__ src, int src_layout, T* __restrict__ dst, Dims d) {
-    __shared__ T tile[RB + 62][32];
-    const int k0 = blockIdx.x * 32, lane = threadIdx.x, k = k0 + lane;
-    const int i = blockIdx.z;
-    const int r0 = blockIdx.y * RB;
-    const size_t plane = (size_t)i * d.qs + GUARD;
-    // source row of destination row rd on lane k: rd -+ (nk-1-2k); the band's first source row belongs to lane k0 (dst L2)
-    // or lane k0+31 (dst L1)
-    const int sh0 = d.nk - 1 - 2 * k0;
-    const int rs0 = src_layout ? r0 + sh0 - 62 : r0 - sh0;
-    for (int y = threadIdx.y; y < RB + 62; y += 8) {
-        const int rs = rs0 + y;
-        if (rs >= 0 && rs < d.q) tile[y][lane] = src[(plane + rs) * d.kpad + k];
-    }
-    __syncthreads();
-    if (k >= d.nk) return;
-    for (int y = threadIdx.y; y < RB; y += 8) {
-        const int rd = r0 + y;
-        if (rd >= d.q) break;
-        const int j = src_layout ? rd - k : rd + k - (d.nk - 1);
-        // rs - rs0 = src L1 -> dst L2: y + 2 lane;  src L2 -> dst L1: y + 62 - 2 lane
-        if (j >= 0 && j < d.nj) dst[(plane + rd) * d.kpad + k] = tile[src_layout ? y + 62 - 2 * lane : y + 2 * lane][lane];
-    }
-}
-
 // 16-byte fill (n elements, n * sizeof(T) a multiple of 16)
 template <typename T>
 __global__ void k_fill16(T* __restrict__ p, size_t n, T v) {

@@ -1,0 +1,641 @@
+// Sweep kernel "MARCH4" (k_sweep_march4): the marching kernel of sweep_march.cuh with FOUR nodes per thread and step.
+//
+// k_sweep_march's step is one Godunov update deep with two independent updates per thread; a warp issues ~125 instructions
+// per step at one instruction per ~3.5 cycles (dependent fixed-latency chains, ILP 2), two warps per scheduler reach ~56 %
+// of the issue slots, and more warps per SM only lengthen the step.  This variant doubles the work of a
+// thread instead: a warp owns 4 planes x 32 lanes, thread (lu, lv) = lane lu*8 + lv the four lanes 4 lv .. 4 lv + 3 of plane lu,
+// so a step is still ONE update deep but carries four independent updates per thread (ILP 4) and ~1.5 instead of ~2 issued
+// instructions per node; operands arrive as LDS.128 (a quarter-warp reads 128 contiguous bytes: conflict-free whatever
+// the plane stride), results leave as one predicated STG.128.  A CTA is again WU x WV = 4 x 2 compute warps + two importers
+// + loader, one CTA per SM; the tile is 16 planes x 64 lanes, so a sweep has half as many tiles and V hops.
+//
+// Everything else -- sheared layouts, tickets in dependency order, TMA boxes skewed by the tensor map, tagged 8-byte words in
+// per-warp shared-memory rings and global mailboxes, importer warps, NaN fill instead of edge cases, the warp-uniform slow
+// variant for frozen nodes -- is k_sweep_march's; see there.  Same DAG, same arithmetic (update.cuh): bit-identical field.
+//   (u-1, m, v+e)   = result e of lane - 8 at the previous step      four SHFL     (lu == 0: ring words)
+//   (u, m-1, v+e-1) = e = 0: result 3 of lane - 1 (one SHFL; lv == 0: ring word);  e > 0: own previous result e - 1
+//   (u, m-1, v+e)   = own previous results
+//   (u, m+1, v+e), (u, m+1, v+e+1) = next old row (LDS.128) and the first lane of lane + 1's quad (LDS.32)
+//   (u+1, m, v+e), slowness          = two LDS.128
+#pragma once
+#include "sweep_march.cuh"
+
+namespace ttcrb200 {
+
+template <int WU, int WV, int NCH>
+struct March4Layout {
+    static constexpr int NW = WU * WV, PUT = 4 * WU, TW = 32 * WV, BW = TW + 4, C = 4, D = 32;
+    static constexpr int NT = (NW + 3) * 32;
+    static constexpr int ROWB = BW * 4, PSB = C * ROWB;                               // bytes per box row / per plane of a box
+    static constexpr int TBYTES = (PUT + 1) * PSB, SBYTES = PUT * PSB;                // bytes a box delivers
+    // the two mbarriers of a chunk slot live in the padding behind its T box
+    static constexpr int OFF_EMPTY = TBYTES, OFF_FULL = TBYTES + 8;
+    static constexpr int CHB_T = round128(TBYTES + 16), CHB_S = round128(SBYTES), CHB = CHB_T + CHB_S;
+    static constexpr int USLOT = 256, VSLOT = 32;                                     // 8 x {n0, tag, n1, tag, n2, tag, n3, tag} | 4 x {n3, tag}
+    static constexpr int URING = D * USLOT, VRING = D * VSLOT;
+    static constexpr int OFF_UR = NCH * CHB;
+    static constexpr int OFF_VR = OFF_UR + NW * URING;
+    static constexpr int OFF_PROG = OFF_VR + NW * VRING;                              // steps completed, per compute warp
+    static constexpr int OFF_CTL = OFF_PROG + (NW * 4 + 15) / 16 * 16;                // dead, tile
+    static constexpr int BYTES = OFF_CTL + 16;
+    static constexpr int BIG = 1 << 29;
+    static_assert(NCH * C < D, "word rings must outlast the box ring");
+    static_assert(PUT + 2 * C + 6 <= GUARD, "guard rows too few");
+    static_assert(TW % 32 == 0, "tiles are cut on kpad's granularity: no tile without a valid lane");
+    static_assert(BYTES <= 227 * 1024, "shared memory");
+};
+
+
+template <int WU, int WV, int NCH, bool RI, bool RJ, bool RK>
+struct March4Geom {
+    using L = March4Layout<WU, WV, NCH>;
+    // byte offsets inside a chunk slot, relative to the quad of traveltime words (u, m+1, v0 .. v3) of box row 0
+    static constexpr int DR = RJ ? -L::ROWB : L::ROWB;                 // next box row
+    static constexpr int DH = RK ? -4 : 16;                            // (u, m+1, v3+1)
+    static constexpr int DUP = RI ? -L::PSB : L::PSB;                  // (u+1, m, v)
+    static constexpr int DS = L::CHB_T + (RI ? -L::PSB : 0);           // slowness (u, m, v)
+    // vl: first lane (a multiple of 4) of the thread inside the tile.  With RK the quad sits mirrored in memory: v3 lowest.
+    __host__ __device__ static int thread_off(int pl, int vl) {
+        return (RI ? L::PUT - pl : pl) * L::PSB + (RK ? L::BW - 4 - vl : vl) * 4 + (RJ ? (L::C - 1) * L::ROWB : 0);
+    }
+    // box origins in tensor-map coordinates (x lane, y skewed row, z plane) of chunk c; `s` = 1 for the slowness box.
+    // Box row b holds, for plane pl, row m_first + b - pl of the traveltimes and m_first - 1 + b - pl of slowness.
+    __host__ __device__ static int box_x(const Dims& d, const MarchTile& t) { return RK ? d.kpad - L::BW - t.v0 : t.v0; }
+    __host__ __device__ static int box_z(const Dims& d, const MarchTile& t, int s) {
+        return RI ? d.ni - 1 - (t.u0 + L::PUT - s) : t.u0;
+    }
+    __host__ __device__ static int box_y(const SweepView& w, const Dims& d, const MarchTile& t, int c, int s) {
+        const int mf = t.m_first - s;
+        if (!RJ) return GUARD + mf + L::C * c + t.u0 + (RI ? 1 : 0);
+        return GUARD + (w.nm - 1) - mf - (L::C * c + L::C - 1) - t.u0 + d.ni - (RI ? 1 : 0);
+    }
+};
+
+
+// Cold path of a MARCH4 step: wait for the ring words of step `tgs` (both halves of the U quad): return values as march_wait_words
+static __device__ __noinline__ int march4_wait_words(unsigned rUi, unsigned rVi, unsigned tgs, unsigned a_dead, long long spin_cycles, unsigned spin_polls,
+                                                     unsigned sleep_ns) {
+    long long t0 = 0;
+    for (unsigned it = 1;; ++it) {
+        const uint4 xu0 = lds_u4(rUi), xu1 = lds_u4(rUi + 16);
+        const uint2 xv = lds_u2(rVi);
+        if (min(min(min(xu0.y, xu0.w), min(xu1.y, xu1.w)), xv.y) >= tgs) return 0;
+        if (it > spin_polls) __nanosleep(sleep_ns);
+        if ((it & 15u) == 0) {
+            if (lds_i(a_dead)) return 1;
+            if (t0 == 0) t0 = clock64();
+            else if (clock64() - t0 > spin_cycles) return 2;
+        }
+    }
+}
+
+template <int WU, int WV, int NCH, bool RI, bool RJ, bool RK>
+__global__ void __launch_bounds__((WU * WV + 3) * 32, (March4Layout<WU, WV, NCH>::BYTES <= 112 * 1024 ? 2 : 1))
+k_sweep_march4(const __grid_constant__ CUtensorMap tmT, const __grid_constant__ CUtensorMap tmS, MarchParams p_, MarchMail mail,
+              float* __restrict__ tt, const uint32_t* __restrict__ frozen, float dx) {
+    using L = March4Layout<WU, WV, NCH>;
+    using G = March4Geom<WU, WV, NCH, RI, RJ, RK>;
+    constexpr int NW = L::NW, PUT = L::PUT, TW = L::TW, C = L::C, D = L::D, BIG = L::BIG;
+    constexpr int USLOT = L::USLOT, VSLOT = L::VSLOT, URING = L::URING, VRING = L::VRING;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const SweepView& w = p_.w;
+    const float MAXV = FLT_MAX;
+    const unsigned sbase = (unsigned)pin((int)__cvta_generic_to_shared(smem_raw));
+    const unsigned a_ctl = sbase + L::OFF_CTL, a_dead = a_ctl, a_tile = a_ctl + 4;
+    const unsigned a_prog = sbase + L::OFF_PROG;
+    const unsigned a_ur = sbase + L::OFF_UR, a_vr = sbase + L::OFF_VR;
+    const unsigned serial = mail.serial;
+    const long long spin_cycles = p_.spin_cycles;
+    // Every warp sees the same sequence of chunks (nch per tile); fill k of the CTA goes to slot k % NCH.  Compute warps keep
+    // the parity of the "full" phase of the fill they wait for (cpar), the loader the round of the ring it is in (cpar).
+    unsigned cslot = 0, cpar = 0;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < NCH; ++i) {
+            mbar_init(sbase + i * L::CHB + L::OFF_FULL, 1);
+            mbar_init(sbase + i * L::CHB + L::OFF_EMPTY, NW);
+        }
+        fence_mbar_init();
+    }
+
+    for (;;) {
+        __syncthreads();   // everybody is done with the previous tile
+        if (threadIdx.x == 0) {
+            const int t = atomicAdd(&p_.ctrl[0], 1);
+            const int ab = *((volatile int*)&p_.ctrl[1]);
+            sts_i(a_tile, (ab || t >= p_.ntiles) ? -1 : t);
+            sts_i(a_dead, 0);
+        }
+        if (threadIdx.x < NW) sts_i(a_prog + 4 * threadIdx.x, 0);
+        __syncthreads();
+        const int ticket = lds_i(a_tile);
+        if (ticket < 0) break;
+        const int tile = p_.order[ticket];
+        const MarchTile T = march_tile<PUT, TW, C>(w, p_.nU, p_.nV, tile);
+        const int nA = T.nA;
+        // Word rings.  The words of step t live in slot (t - 1) % D and are valid when their tag is >= t (a slot only ever
+        // holds the tag of its step or of an older one).  Step 1 reads +MAX (the row before the tile's first row holds
+        // no node).  Words nobody will send -- U words of the first warp row of a tile without a tile above, V words of the
+        // first warp column of a tile without a tile to the left -- are +MAX with tag BIG in every slot.
+        for (unsigned o = threadIdx.x * 16; o < (unsigned)(NW * URING); o += L::NT * 16) {
+            const unsigned wr = o / URING, slot = (o % URING) / USLOT;
+            const unsigned tag = (wr < (unsigned)WV && !T.has_u) ? (unsigned)BIG : (slot == 0 ? 1u : 0u);
+            sts_u4(a_ur + o, __float_as_uint(MAXV), tag, __float_as_uint(MAXV), tag);
+        }
+        for (unsigned o = threadIdx.x * 16; o < (unsigned)(NW * VRING); o += L::NT * 16) {
+            const unsigned wr = o / VRING, slot = (o % VRING) / VSLOT;
+            const unsigned tag = (wr % WV == 0 && !T.has_v) ? (unsigned)BIG : (slot == 0 ? 1u : 0u);
+            sts_u4(a_vr + o, __float_as_uint(MAXV), tag, __float_as_uint(MAXV), tag);
+        }
+        __syncthreads();
+        if (p_.trace && threadIdx.x == 0) {
+            p_.trace[tile * 16 + 0] = gtime();
+            unsigned smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            p_.trace[tile * 16 + 7] = smid;
+        }
+
+        if (warp == NW || warp == NW + 1) {
+            // ================= importers: warp NW feeds the U words, warp NW + 1 the V words ==================================
+            // Mailboxes are indexed by the STEP of the tile that writes them (one word per lane / plane and step, also for
+            // the rows around its nodes, value +MAX):
+            //   U ring of warp (0, l/32), slot of step t, pair (l%32)/2  <- mail.u[tile U-1][step t + PUT - 1][lane l]
+            //   V ring of warp (pl/4, 0), slot of step t, word pl%4      <- mail.v[tile V-1][step t + dmf - 1][plane pl]
+            // and the steps after the last step of those tiles get +MAX.  A lane moves TWO words per access (16 bytes); the
+            // lanes of a warp are spread over S consecutive steps and every lane works on K steps at a time.  A round issues
+            // the polls of all K steps back to back and only then looks at what came back: a warp has six scoreboards, so
+            // polls that are issued and consumed one by one wait for each other (measured: 0.3 us per poll, and the importer
+            // paced every tile); a round costs ONE L2 round trip whatever K is.
+            constexpr int NPU = TW / 2, LU = NPU >= 32 ? 32 : NPU, SU = 32 / LU;       // pairs per step, lanes per step, steps per round and slot
+            constexpr int NPV = PUT / 2, LV = NPV > 8 ? 16 : 8, SV = 32 / LV;
+            static_assert(NPU <= 32 && NPV <= 16, "importer lane mapping");
+            const bool isU = warp == NW;
+            const int L_ = isU ? LU : LV, S = isU ? SU : SV;
+            const int h = lane / L_, j = lane % L_;
+            const bool act = isU ? (T.has_u != 0) : (T.has_v != 0 && j < NPV);
+            const int ja = act ? j : 0;
+            // last step with mailbox words; first word of step 0 for this lane; ring address of this lane's words; consumer progress
+            const int a_end = !act ? 0 : (isU ? nA - PUT + 1 : T.nA_left - T.dmf + 1);
+            const int stride = isU ? TW : PUT;
+            const unsigned long long* const base =
+                isU ? mail.u + ((size_t)(T.has_u ? tile - p_.nV : tile) * mail.rows + (PUT - 1)) * TW + 2 * ja
+                    : mail.v + ((size_t)(T.has_v ? tile - 1 : tile) * mail.rows + (T.dmf - 1)) * PUT + 2 * ja;
+            const unsigned wring = isU ? a_ur + (unsigned)(ja >> 4) * URING + (unsigned)(ja & 15) * 16 : a_vr + (unsigned)((ja >> 1) * WV) * VRING + (unsigned)(ja & 1) * 16;
+            const unsigned slotb = isU ? USLOT : VSLOT;
+            const unsigned pcons = a_prog + 4 * (isU ? (ja >> 4) : (ja >> 1) * WV);
+            constexpr int K = 6;
+            uint4 q[K];
+            int a[K];
+            bool have[K];
+#pragma unroll
+            for (int k = 0; k < K; ++k) { a[k] = act ? 2 + h + S * k : nA + 1; have[k] = false; q[k] = make_uint4(0, 0, 0, 0); }
+            long long t0 = 0;
+            unsigned idle = 0;
+            long long n_iter = 0, n_got = 0;
+            const long long ti0 = clock64();
+            for (;;) {
+                ++n_iter;
+#pragma unroll
+                for (int k = 0; k < K; ++k)
+                    if (!have[k] && a[k] <= a_end) q[k] = ld_mail2(base + (size_t)a[k] * stride);
+                const int lim = lds_i(pcons) + D;   // ring slot (a - 1) % D holds the words of step a - D until the consumer has passed it
+                int done = 1, got = 0;
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    if (a[k] <= nA) {
+                        const bool real = a[k] <= a_end;
+                        const bool ok = !real || (q[k].y == serial && q[k].w == serial);
+                        if (ok && a[k] <= lim) {
+                            const unsigned tag = (unsigned)a[k], mx = __float_as_uint(MAXV);
+                            sts_u4(wring + (unsigned)((a[k] - 1) & (D - 1)) * slotb, real ? q[k].x : mx, tag, real ? q[k].z : mx, tag);
+                            a[k] += S * K;
+                            have[k] = false;
+                            got = 1;
+                        } else {
+                            have[k] = ok;   // (words that wait for their ring slot are kept)
+                        }
+                        done &= a[k] > nA;
+                    }
+                }
+                n_got += got;
+                if (done) break;
+                if (got) { idle = 0; continue; }
+                if (idle >= 3) __nanosleep(p_.sleep_ns);   // (nothing to deliver for three round trips: the neighbours are far behind)
+                if ((++idle & 15u) == 0) {   // nothing moved for a while: is the march still alive?
+                    if (lds_i(a_dead)) break;
+                    if (idle == 16) t0 = clock64();
+                    else if (clock64() - t0 > spin_cycles) {
+                        if (atomicCAS(&p_.ctrl[1], 0, 31) == 0) { p_.ctrl[2] = tile; p_.ctrl[3] = a[0]; p_.ctrl[4] = a[1]; p_.ctrl[5] = warp; p_.ctrl[6] = lane; }
+                        sts_i(a_dead, 1);
+                        break;
+                    }
+                }
+            }
+            if (p_.trace && lane == 0) { p_.trace[tile * 16 + (isU ? 8 : 11)] = n_iter; p_.trace[tile * 16 + (isU ? 9 : 12)] = n_got; p_.trace[tile * 16 + (isU ? 10 : 13)] = clock64() - ti0; }
+            __syncwarp();
+        } else if (warp == NW + 2) {
+            // ================= loader ====================================================================================
+            // One thread.  Fill k of the CTA lives in slot k % NCH; it may be sent once every compute warp has arrived on the
+            // slot's "empty" barrier for fill k - NCH (the thread sleeps in try_wait: no polling).  Here cpar counts the
+            // rounds of the ring: round r >= 1 waits for the "empty" phase r - 1.
+            if (lane == 0) {
+                const int nch = T.nch;
+                const int xb = G::box_x(p_.d, T);
+                const int zT = G::box_z(p_.d, T, 0), zS = G::box_z(p_.d, T, 1);
+                const int yT0 = G::box_y(w, p_.d, T, 0, 0), yS0 = G::box_y(w, p_.d, T, 0, 1);
+                const int dyc = RJ ? -C : C;
+                for (int ci = 0; ci < nch; ++ci) {
+                    const unsigned slot = sbase + cslot * L::CHB;
+                    bool ok = true;
+                    if (cpar >= 1) {
+                        const long long t0 = clock64();
+                        while (!mbar_test(slot + L::OFF_EMPTY, (cpar - 1u) & 1u)) {
+                            if (lds_i(a_dead)) { ok = false; break; }
+                            if (clock64() - t0 > spin_cycles) {
+                                if (atomicCAS(&p_.ctrl[1], 0, 50) == 0) { p_.ctrl[2] = tile; p_.ctrl[3] = ci; p_.ctrl[4] = (int)cslot; p_.ctrl[5] = NW + 2; }
+                                sts_i(a_dead, 1);
+                                ok = false;
+                                break;
+                            }
+                        }
+                    }
+                    if (!ok) break;
+                    mbar_expect_tx(slot + L::OFF_FULL, L::TBYTES + L::SBYTES);
+                    tma_load_3d(slot, &tmT, xb, yT0 + ci * dyc, zT, slot + L::OFF_FULL);
+                    tma_load_3d(slot + L::CHB_T, &tmS, xb, yS0 + ci * dyc, zS, slot + L::OFF_FULL);
+                    if (p_.pf_chunks > 0 && ci + p_.pf_chunks < nch) {
+                        tma_prefetch_3d(&tmT, xb, yT0 + (ci + p_.pf_chunks) * dyc, zT);
+                        tma_prefetch_3d(&tmS, xb, yS0 + (ci + p_.pf_chunks) * dyc, zS);
+                    }
+                    if (++cslot == NCH) { cslot = 0; ++cpar; }
+                }
+            }
+        } else {
+            // ================= compute warps =============================================================================
+            const int lw = warp;
+            const int wu = lw / WV, wv = lw - wu * WV, lu = lane >> 3, lv = lane & 7;
+            const int pl = 4 * wu + lu, vl = 32 * wv + 4 * lv;
+            const int u = T.u0 + pl, vt = T.v0 + vl;
+            const int ulast = w.nu - 1;
+            // Lanes and planes beyond the arrays are filled with NaN by the TMA unit (the tensor maps ask for it): as an upwind
+            // or downwind neighbour a NaN drops out of the minima, as an old value it never lets `t < old` hold.
+            const bool ghost = vt >= p_.d.kpad || u > ulast;
+            const bool out_u_in = wu < WU - 1, out_v_in = wv < WV - 1;
+            const unsigned aUin = a_ur + (unsigned)lw * URING + lv * 32;   // pairs 2 lv, 2 lv + 1 of a slot of my U ring
+            const unsigned aVin = a_vr + (unsigned)lw * VRING + lu * 8;    // word lu of a slot of my V ring
+            constexpr unsigned OUT_U = WV * URING, OUT_V = VRING;          // the rings of the warp below / to the right
+            const unsigned a_myprog = (unsigned)pin((int)(a_prog + 4 * lw));
+            const unsigned toff = (unsigned)pin((int)G::thread_off(pl, vl));
+            // the thread's quad of step 1 (a row before the tile's first one), and the byte offset of the current step's quad from it
+            char* const pg0 = (char*)(tt + (w.base + (long long)min(u, ulast) * w.su + (long long)(T.m_first - 1 - pl) * w.sm + (long long)(RK ? vt + 3 : vt) * w.sv));
+            const int rowbytes = (int)w.sm * 4;
+            int poff = 0;
+            // ---- slow-path condition: frozen nodes (source box)
+            bool fzme = false;
+            int wz_lo = 1 << 28, wz_hi = -(1 << 28);
+            if (p_.fb.jhi >= p_.fb.jlo && u <= ulast) {
+                const int it = w.ri ? ulast - u : u;
+                bool kin = false;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int ve = vt + e;
+                    const int ko = ve - w.vlo, kt = w.rk ? p_.d.nk - 1 - ko : ko;
+                    kin = kin || (ve >= w.vlo && ve < w.vhi && kt >= p_.fb.klo && kt <= p_.fb.khi);
+                }
+                if (it >= p_.fb.ilo && it <= p_.fb.ihi && kin) {
+                    fzme = true;
+                    const int jol = RJ ? w.nj - 1 - p_.fb.jhi : p_.fb.jlo, joh = RJ ? w.nj - 1 - p_.fb.jlo : p_.fb.jhi;
+                    // oriented j = m_first + r - v + joff on local row r, which is updated at step t = r + 2 + pl
+                    wz_lo = jol - w.joff + vt - T.m_first + 2 + pl;
+                    wz_hi = joh - w.joff + vt + 3 - T.m_first + 2 + pl;
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                wz_lo = min(wz_lo, __shfl_xor_sync(0xffffffffu, wz_lo, o));
+                wz_hi = max(wz_hi, __shfl_xor_sync(0xffffffffu, wz_hi, o));
+            }
+            // lane roles, one bit each, in a register the compiler cannot rematerialise from %tid
+            enum : unsigned { F_L0 = 1, F_U0 = 2, F_V0 = 4, F_STU = 8, F_STV = 16, F_OMU = 32, F_OMV = 64, F_FZ = 512 };
+            const unsigned fl = (unsigned)pin((int)((lane == 0 ? F_L0 : 0u) | (lu == 0 ? F_U0 : 0u) | (lv == 0 ? F_V0 : 0u) | ((lu == 3 && out_u_in) ? F_STU : 0u) |
+                                                    ((lv == 7 && out_v_in) ? F_STV : 0u) | ((lu == 3 && !out_u_in && T.has_down) ? F_OMU : 0u) |
+                                                    ((lv == 7 && !out_v_in && T.has_right) ? F_OMV : 0u) |
+                                                    (fzme ? F_FZ : 0u)));
+            const bool mail_warp = __any_sync(0xffffffffu, (fl & (F_OMU | F_OMV)) != 0);
+            const float QNAN = __int_as_float(0x7fc00000);
+
+            int dead = 0;
+            auto give_up = [&](int why, int x, int a) {
+                if (atomicCAS(&p_.ctrl[1], 0, why) == 0) { p_.ctrl[2] = tile; p_.ctrl[3] = x; p_.ctrl[4] = a; p_.ctrl[5] = lw; p_.ctrl[6] = lane; }
+                sts_i(a_dead, 1);
+            };
+            auto wait_full = [&](unsigned a_full, unsigned par, int why) {
+                if (__builtin_expect(mbar_test(a_full, par), 1)) return;
+                const int st = march_wait_full(a_full, par, a_dead, spin_cycles);
+                if (st == 2) give_up(why, (int)cslot, (int)par);
+                if (st) dead = 1;
+            };
+            // ---- prologue: first chunk of the tile, operands of step 1
+            unsigned sb = sbase + cslot * L::CHB;   // chunk slot the current group reads
+            wait_full(sb + L::OFF_FULL, cpar, 40);
+            int deadw = __any_sync(0xffffffffu, dead);
+            unsigned rB = sb + toff;
+            const float ini = ghost ? 0.f : MAXV;
+            float p[4], o[4], j[4], up[4], s[4], hh;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) p[e] = o[e] = ini;
+            auto unpack = [&](float* d, const float4& a) {   // box order -> node order (mirrored lanes with RK)
+                d[0] = RK ? a.w : a.x; d[1] = RK ? a.z : a.y; d[2] = RK ? a.y : a.z; d[3] = RK ? a.x : a.w;
+            };
+            {
+                const float4 a = lds_f4(rB), b = lds_f4(rB + (unsigned)G::DUP), c = lds_f4(rB + (unsigned)G::DS);
+                hh = lds_f(rB + (unsigned)G::DH);
+                unpack(j, a); unpack(up, b); unpack(s, c);
+            }
+            float acc = 0.f;
+            if (p_.trace && threadIdx.x == 0) p_.trace[tile * 16 + 1] = gtime();
+
+            // Groups of C steps (tags t .. t+C-1) read chunk `sb`; groups in [ts0, ts1) may touch a frozen node and run the SLOW body; warps that feed a global mailbox run the MAILW bodies.
+            const unsigned t_end = (unsigned)nA + 1u;
+            unsigned ts0 = t_end, ts1 = t_end;
+            if (wz_hi >= wz_lo) {
+                ts0 = (unsigned)min(max(((wz_lo - 1) / C) * C + 1, 1), (int)t_end);
+                ts1 = (unsigned)min(max(((wz_hi - 1) / C + 1) * C + 1, 1), (int)t_end);
+            }
+            unsigned long long* mu = mail.u + ((size_t)tile * mail.rows + 1) * TW + vl;    // [tile][step][lane]
+            unsigned long long* mv = mail.v + ((size_t)tile * mail.rows + 1) * PUT + pl;   // [tile][step][plane]
+            unsigned t = 1;
+            unsigned so = 0;                  // byte offset of the group's first slot in a U ring (V ring: so * VSLOT / USLOT)
+            unsigned gU = aUin, gV = aVin;
+
+            // One march step: ring words at rUi / rVi must carry a tag >= tgs, outputs go to rUo / rVo with tag tgs + 1, the next
+            // step's operands are at `ao`.
+            auto step = [&](const int r, const unsigned tgs, const unsigned rUi, const unsigned rVi, const unsigned rUo, const unsigned rVo, const unsigned ao,
+                            auto slow_c, auto mail_c) {
+                constexpr bool SLOW = decltype(slow_c)::value != 0;
+                (void)mail_c;
+                // ---- (1) everything this step reads from shared memory
+                uint4 xu0 = lds_u4(rUi), xu1 = lds_u4(rUi + 16);
+                uint2 xv = lds_u2(rVi);
+                const float4 nj = lds_f4(ao), nup = lds_f4(ao + (unsigned)G::DUP), ns = lds_f4(ao + (unsigned)G::DS);
+                const float nh = lds_f(ao + (unsigned)G::DH);
+                // ---- (2) the upwind neighbours inside the patch
+                float um[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) um[e] = __shfl_up_sync(0xffffffffu, p[e], 8);
+                float km0 = __shfl_up_sync(0xffffffffu, p[3], 1);
+                // ---- (3) the one branch: words not there yet
+                if (__builtin_expect(__any_sync(0xffffffffu, min(min(min(xu0.y, xu0.w), min(xu1.y, xu1.w)), xv.y) < tgs), 0)) {
+                    const int st = march4_wait_words(rUi, rVi, tgs, a_dead, spin_cycles, p_.spin_polls, p_.sleep_ns);
+                    if (st == 2) give_up(41, (int)tgs, (int)min(xu0.y, xv.y));
+                    if (st) dead = 1;
+                    xu0 = lds_u4(rUi); xu1 = lds_u4(rUi + 16); xv = lds_u2(rVi);
+                }
+                if (SLOW) {
+                    if (fl & F_FZ) {   // (the quad shares a mask word: e is a multiple of 4)
+                        const long long e = (long long)((float*)(pg0 + poff) - tt);
+                        const unsigned bits = frozen[e >> 5] >> (e & 31);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                            if (bits & (1u << (RK ? 3 - q : q))) s[q] = QNAN;
+                    }
+                }
+                if (fl & F_U0) {
+                    um[0] = __uint_as_float(xu0.x); um[1] = __uint_as_float(xu0.z);
+                    um[2] = __uint_as_float(xu1.x); um[3] = __uint_as_float(xu1.z);
+                }
+                if (fl & F_V0) km0 = __uint_as_float(xv.x);
+                // ---- (4) the four updates: node e takes (m-1, v-1) from node e-1's previous result, (m+1, v+1) from node e+1's old row
+                float n[4];
+                n[0] = fminf(godunov(tmin(km0, j[1]), tmin(p[0], j[0]), tmin(um[0], up[0]), s[0] * dx), o[0]);
+                n[1] = fminf(godunov(tmin(p[0], j[2]), tmin(p[1], j[1]), tmin(um[1], up[1]), s[1] * dx), o[1]);
+                n[2] = fminf(godunov(tmin(p[1], j[3]), tmin(p[2], j[2]), tmin(um[2], up[2]), s[2] * dx), o[2]);
+                n[3] = fminf(godunov(tmin(p[2], hh), tmin(p[3], j[3]), tmin(um[3], up[3]), s[3] * dx), o[3]);   // (NaN -> old: slots that are no node, frozen nodes)
+                // ---- (5) hand-off: warp below / to the right (shared rings), tiles U+1 / V+1 (global mailboxes)
+                sts_u4_ifu(rUo, __float_as_uint(n[0]), tgs + 1, __float_as_uint(n[1]), tgs + 1, fl & F_STU);
+                sts_u4_ifu(rUo + 16, __float_as_uint(n[2]), tgs + 1, __float_as_uint(n[3]), tgs + 1, fl & F_STU);
+                sts_u2_ifu(rVo, __float_as_uint(n[3]), tgs + 1, fl & F_STV);
+                if (mail_warp) {   // (warp-uniform; a second copy of the loop for these warps would not fit the 32 KB instruction cache)
+                    st_mail2_if(mu + r * TW, serial, n[0], n[1], (int)(fl & F_OMU));   // (mu, mv: the group's first step)
+                    st_mail2_if(mu + r * TW + 2, serial, n[2], n[3], (int)(fl & F_OMU));
+                    st_mail_if(mv + r * PUT, serial, n[3], (int)(fl & F_OMV));
+                }
+                // ---- (6) result, change sum, rotate the operands
+                stg_f4_stream_if((float*)(pg0 + poff), RK ? n[3] : n[0], RK ? n[2] : n[1], RK ? n[1] : n[2], RK ? n[0] : n[3],
+                                 (n[0] < o[0] || n[1] < o[1] || n[2] < o[2] || n[3] < o[3]) ? 1 : 0);
+                poff += rowbytes;
+                acc += ((o[0] - n[0]) + (o[1] - n[1])) + ((o[2] - n[2]) + (o[3] - n[3]));
+#pragma unroll
+                for (int e = 0; e < 4; ++e) { p[e] = n[e]; o[e] = j[e]; }
+                unpack(j, nj); unpack(up, nup); unpack(s, ns);
+                hh = nh;
+            };
+            auto group = [&](auto slow_c, auto mail_c) {
+                // chunk slot of the next group (and the parity of its "full" phase: it flips when the ring wraps)
+                unsigned nslot = cslot + 1, npar = cpar;
+                if (nslot == NCH) { nslot = 0; npar ^= 1u; }
+                const unsigned sbn = sbase + nslot * L::CHB;
+                const unsigned so_n = (so + C * USLOT) & (unsigned)(URING - 1);
+                const unsigned gUn = aUin + so_n, gVn = aVin + so_n / (unsigned)(USLOT / VSLOT);
+#pragma unroll
+                for (int r = 0; r < C - 1; ++r)
+                    step(r, t + r, gU + r * USLOT, gV + r * VSLOT, gU + OUT_U + (r + 1) * USLOT, gV + OUT_V + (r + 1) * VSLOT,
+                         rB + (unsigned)((r + 1) * G::DR), slow_c, mail_c);
+                wait_full(sbn + L::OFF_FULL, npar, 42);   // the chunk the last step of the group takes the next operands from
+                step(C - 1, t + C - 1, gU + (C - 1) * USLOT, gV + (C - 1) * VSLOT, gUn + OUT_U, gVn + OUT_V, sbn + toff, slow_c, mail_c);
+                mu += C * TW; mv += C * PUT;
+                // every lane has read the group's words and the chunk's last row (its values were used by the update above)
+                __syncwarp();
+                mbar_arrive_ifu(sb + L::OFF_EMPTY, fl & F_L0);
+                t += C;
+                sts_i_ifu(a_myprog, (int)t - 1, fl & F_L0);
+                sb = sbn; rB = sbn + toff; cslot = nslot; cpar = npar;
+                so = so_n; gU = gUn; gV = gVn;
+                deadw = __any_sync(0xffffffffu, dead);
+            };
+            auto march = [&](auto mail_c) {
+#pragma unroll 1
+                for (int seg = 0; seg < 3; ++seg) {
+                    const unsigned e = seg == 0 ? ts0 : (seg == 1 ? ts1 : t_end);
+                    if (seg == 1) {
+                        while (t < e && !deadw) group(IntC<1>(), mail_c);
+                    } else {
+                        while (t < e && !deadw) group(IntC<0>(), mail_c);
+                    }
+                }
+            };
+            march(IntC<0>());
+            // the last chunk (only its first row was read, by the prefetch of the last step) goes back to the loader, too
+            if (!deadw) {
+                __syncwarp();
+                mbar_arrive_ifu(sb + L::OFF_EMPTY, fl & F_L0);
+                if (++cslot == NCH) { cslot = 0; cpar ^= 1u; }
+            }
+            sts_i_ifu(a_myprog, BIG, fl & F_L0);   // release an importer still waiting for this warp
+            double dacc = ghost ? 0.0 : (double)acc;   // (NaN - NaN in the ghosts)
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) dacc += __shfl_xor_sync(0xffffffffu, dacc, o);
+            if (lane == 0) p_.partial[(size_t)tile * NW + lw] = dacc;
+            if (p_.trace && lane == 0) {
+                if (lw == 0) p_.trace[tile * 16 + 5] = gtime();
+            }
+        }
+    }
+}
+
+// ---- host side ---------------------------------------------------------------------------------------------------------
+template <int WU, int WV, int NCH>
+inline int march4_launch(TileState& s, MarchState& ms, const TileOptions& o, int sm_count, const SweepView& w, const Dims& d, float* tt,
+                        const float* slo, const uint32_t* frozen, const FrozenBox& fb, float dx, double* d_change, cudaStream_t st) {
+    using L = March4Layout<WU, WV, NCH>;
+    constexpr int PUT = L::PUT, TW = L::TW, NW = L::NW;
+    MarchParams p;
+    p.w = w; p.d = d; p.fb = fb;
+    p.nV = (d.kpad + TW - 1) / TW;
+    p.nU = (w.nu + PUT - 1) / PUT;
+    p.ntiles = p.nU * p.nV;
+    p.spin_cycles = o.spin_limit << 9;
+    static const int pf_env = getenv("TTCR_B200_PF") ? atoi(getenv("TTCR_B200_PF")) : 0;
+    p.pf_chunks = pf_env;
+    static const int spin_env = getenv("TTCR_B200_SPIN") ? atoi(getenv("TTCR_B200_SPIN")) : 24;
+    static const int sleep_env = getenv("TTCR_B200_SLEEP") ? atoi(getenv("TTCR_B200_SLEEP")) : 400;
+    p.spin_polls = (unsigned)spin_env; p.sleep_ns = (unsigned)sleep_env;
+    p.ctrl = s.d_ctrl;
+    const char* trace_path = getenv("TTCR_B200_TRACE");
+    if (trace_path && ms.trace_cap < p.ntiles) {
+        cudaFree(ms.d_trace);
+        ms.d_trace = nullptr;
+        TCK(cudaMalloc(&ms.d_trace, (size_t)p.ntiles * 16 * sizeof(long long)));
+        ms.trace_cap = p.ntiles;
+    }
+    p.trace = trace_path ? ms.d_trace : nullptr;
+    const int rows = d.nj + TW + PUT + 2 * L::C + 8;
+    if (!ms.d_mbu || ms.mb_tiles < p.ntiles || ms.mb_rows != rows || ms.mb_tw != TW || ms.mb_put != PUT) {
+        TCK(cudaStreamSynchronize(st));
+        cudaFree(ms.d_mbu); cudaFree(ms.d_mbv); cudaFree(ms.d_partial); cudaFree(ms.d_order);
+        ms.d_mbu = ms.d_mbv = nullptr; ms.d_partial = nullptr; ms.d_order = nullptr;
+        ms.mb_rows = rows; ms.mb_tiles = p.ntiles; ms.mb_tw = TW; ms.mb_put = PUT;
+        const size_t nu = (size_t)ms.mb_tiles * ms.mb_rows * TW, nv = (size_t)ms.mb_tiles * ms.mb_rows * PUT;
+        TCK(cudaMalloc(&ms.d_mbu, nu * 8));
+        TCK(cudaMalloc(&ms.d_mbv, nv * 8));
+        TCK(cudaMalloc(&ms.d_partial, (size_t)p.ntiles * NW * sizeof(double)));
+        TCK(cudaMalloc(&ms.d_order, (size_t)p.ntiles * sizeof(int)));
+        TCK(cudaMemsetAsync(ms.d_mbu, 0, nu * 8, st));
+        TCK(cudaMemsetAsync(ms.d_mbv, 0, nv * 8, st));
+        ms.serial = 0;
+        ms.order_key = -1;
+    }
+    MarchMail mail;
+    mail.u = ms.d_mbu; mail.v = ms.d_mbv; mail.rows = ms.mb_rows;
+    mail.serial = ++ms.serial;
+    if (mail.serial == 0) {   // wrapped: clear the tags once every 2^32 sweeps
+        TCK(cudaMemsetAsync(ms.d_mbu, 0, (size_t)ms.mb_tiles * ms.mb_rows * TW * 8, st));
+        TCK(cudaMemsetAsync(ms.d_mbv, 0, (size_t)ms.mb_tiles * ms.mb_rows * PUT * 8, st));
+        mail.serial = ms.serial = 1;
+    }
+    p.order = ms.d_order; p.partial = ms.d_partial;
+    const int key = 7400000 + PUT * 10000 + TW * 40 + w.vlo;
+    if (ms.order_key != key || ms.ntiles != p.ntiles) {
+        // ticket order: a linear extension of (U-1,V) < (U,V), (U,V-1) < (U,V), sorted by the step at which a tile can start
+        std::vector<std::pair<long long, int>> k(p.ntiles);
+        static const int lag_env = getenv("TTCR_B200_LAG_U") ? atoi(getenv("TTCR_B200_LAG_U")) : 0;
+        const long long lag_u = lag_env > 0 ? lag_env : PUT + 2;
+        for (int U = 0; U < p.nU; ++U)
+            for (int V = 0; V < p.nV; ++V) {
+                const int va = std::max(V * TW, w.vlo);
+                k[U * p.nV + V] = {U * lag_u + (long long)(va - w.joff) + V, U * p.nV + V};
+            }
+        std::stable_sort(k.begin(), k.end());
+        std::vector<int> order(p.ntiles);
+        for (int i = 0; i < p.ntiles; ++i) order[i] = k[i].second;
+        TCK(cudaMemcpyAsync(ms.d_order, order.data(), p.ntiles * sizeof(int), cudaMemcpyHostToDevice, st));
+        TCK(cudaStreamSynchronize(st));
+        ms.order_key = key;
+        ms.ntiles = p.ntiles;
+    }
+    const bool minus = (w.ri != 0) == (w.rj != 0);
+    auto get_map = [&](const void* a, int bp) -> CUtensorMap {
+        const std::vector<long long> kk = {(long long)(size_t)a, minus, L::BW, bp, d.kpad, d.qs, d.ni};
+        for (auto& e : ms.maps)
+            if (e.first == kk) return e.second;
+        if (ms.maps.size() > 64) ms.maps.clear();
+        ms.maps.push_back({kk, make_skew_map(a, d, minus, L::BW, L::C, bp, true)});
+        return ms.maps.back().second;
+    };
+    const CUtensorMap tmT = get_map(tt, PUT + 1);
+    const CUtensorMap tmS = get_map(slo, PUT);
+    TCK(cudaMemsetAsync(s.d_ctrl, 0, sizeof(int), st));
+    const int variant = (w.ri ? 1 : 0) | (w.rj ? 2 : 0) | (w.rk ? 4 : 0);
+    auto run = [&](auto kern) {
+        int occ = 0;
+        for (auto& e : ms.occ)
+            if (e.first == (const void*)kern) occ = e.second;
+        if (!occ) {   // once per kernel instance and state (= slot, hence device)
+            TCK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::BYTES));
+            TCK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, L::NT, L::BYTES));
+            if (occ < 1) throw std::runtime_error("march kernel does not fit on an SM");
+            ms.occ.push_back({(const void*)kern, occ});
+        }
+        int per_sm = occ;
+        if (o.ctas_per_sm > 0) per_sm = std::min(per_sm, o.ctas_per_sm);
+        int grid = std::min(p.ntiles, per_sm * sm_count);
+        if (o.max_ctas > 0) grid = std::min(grid, o.max_ctas);
+        kern<<<grid, L::NT, L::BYTES, st>>>(tmT, tmS, p, mail, tt, frozen, dx);
+    };
+    switch (variant) {
+        case 0: run(k_sweep_march4<WU, WV, NCH, false, false, false>); break;
+        case 1: run(k_sweep_march4<WU, WV, NCH, true, false, false>); break;
+        case 2: run(k_sweep_march4<WU, WV, NCH, false, true, false>); break;
+        case 3: run(k_sweep_march4<WU, WV, NCH, true, true, false>); break;
+        case 4: run(k_sweep_march4<WU, WV, NCH, false, false, true>); break;
+        case 5: run(k_sweep_march4<WU, WV, NCH, true, false, true>); break;
+        case 6: run(k_sweep_march4<WU, WV, NCH, false, true, true>); break;
+        default: run(k_sweep_march4<WU, WV, NCH, true, true, true>); break;
+    }
+    k_sum_partials<<<1, 256, 0, st>>>(ms.d_partial, p.ntiles * NW, d_change);
+    TCK(cudaMemcpyAsync(s.h_abort, s.d_ctrl + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+    TCK(cudaGetLastError());
+    if (trace_path) {
+        std::vector<long long> h((size_t)p.ntiles * 16);
+        TCK(cudaStreamSynchronize(st));
+        TCK(cudaMemcpy(h.data(), ms.d_trace, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+        FILE* f = fopen(trace_path, "ab");
+        if (f) {
+            const int hdr[4] = {p.ntiles, p.nU, p.nV, PUT + 1000 * 16};   // (record length in the thousands)
+            fwrite(hdr, sizeof(int), 4, f);
+            fwrite(h.data(), sizeof(long long), h.size(), f);
+            fclose(f);
+        }
+    }
+    return 2;
+}
+
+template <typename T>
+inline int march4_sweep(TileState&, MarchState&, const TileOptions&, int, const SweepView&, const Dims&, T*, const T*, const uint32_t*,
+                        const FrozenBox&, T, double*, cudaStream_t) {
+    throw std::runtime_error("march kernel: fp32 only");
+}
+#if defined(TTCR_B200_SPLIT_BUILD) && !defined(TTCR_B200_MARCH4_DEFINE)
+template <>
+int march4_sweep<float>(TileState& s, MarchState& ms, const TileOptions& o, int sm_count, const SweepView& w, const Dims& d, float* tt,
+                        const float* slo, const uint32_t* frozen, const FrozenBox& fb, float dx, double* d_change, cudaStream_t st);   // defined in march4_inst.cu
+#else
+#ifdef TTCR_B200_MARCH4_DEFINE
+#define TTCR_B200_MARCH4_DEFINE_LINKAGE
+#else
+#define TTCR_B200_MARCH4_DEFINE_LINKAGE inline
+#endif
+template <>
+TTCR_B200_MARCH4_DEFINE_LINKAGE int march4_sweep<float>(TileState& s, MarchState& ms, const TileOptions& o, int sm_count, const SweepView& w, const Dims& d,
+                                                        float* tt, const float* slo, const uint32_t* frozen, const FrozenBox& fb, float dx,
+                                                        double* d_change, cudaStream_t st) {
+    // <warps along u, warps along v, chunk slots of the box ring>; tile = 4 WU planes x 32 WV lanes
+    if (o.warps == 4) return march4_launch<4, 1, 6>(s, ms, o, sm_count, w, d, tt, slo, frozen, fb, dx, d_change, st);   // 16 planes x 32 lanes, one warp per scheduler
+    if (o.rows == 2) return march4_launch<8, 1, 4>(s, ms, o, sm_count, w, d, tt, slo, frozen, fb, dx, d_change, st);     // 32 planes x 32 lanes
+    return march4_launch<4, 2, 4>(s, ms, o, sm_count, w, d, tt, slo, frozen, fb, dx, d_change, st);
+}
+#endif
+
+}  // namespace ttcrb200

@@ -54,6 +54,7 @@ struct TileOptions {
     int depth = 8;         // register queue depth (rows of loads in flight): 4 or 8
     long long spin_limit = 1ll << 22;   // polls before a wait is declared dead
     int max_ctas = 0;      // k_sweep_march: cap on the grid size (0 = none); tests use it to make every CTA run several tiles
+    int nodes = 0;         // k_sweep_march: nodes per thread and step: 2 (sweep_march.cuh, tiles of 16 x 32), 4 (sweep_march4.cuh, 16 x 64), 0 = by grid size
 };
 
 struct TileState {
