@@ -475,7 +475,8 @@ k_sweep_march(const __grid_constant__ CUtensorMap tmT, const __grid_constant__ C
             // step's operands are at `ao`.
             auto step = [&](const int r, const unsigned tgs, const unsigned rUi, const unsigned rVi, const unsigned rUo, const unsigned rVo, const unsigned ao,
                             auto slow_c, auto mail_c) {
-                constexpr bool SLOW = decltype(slow_c)::value != 0, MAILW = decltype(mail_c)::value != 0;
+                constexpr bool SLOW = decltype(slow_c)::value != 0;
+                (void)mail_c;
                 // ---- (1) everything this step reads from shared memory
                 uint4 xu = lds_u4(rUi);
                 uint2 xv = lds_u2(rVi);
@@ -509,7 +510,7 @@ k_sweep_march(const __grid_constant__ CUtensorMap tmT, const __grid_constant__ C
                 // ---- (5) hand-off: warp below / to the right (shared rings), tiles U+1 / V+1 (global mailboxes)
                 sts_u4_ifu(rUo, __float_as_uint(n0), tgs + 1, __float_as_uint(n1), tgs + 1, fl & F_STU);
                 sts_u2_ifu(rVo, __float_as_uint(n1), tgs + 1, fl & F_STV);
-                if (MAILW) {
+                if (mail_warp) {   // (warp-uniform; one copy of the loop instead of one per kind of warp: instruction cache)
                     st_mail2_if(mu + r * TW, serial, n0, n1, (int)(fl & F_OMU));   // (mu, mv: the group's first step)
                     st_mail_if(mv + r * PUT, serial, n1, (int)(fl & F_OMV));
                 }
@@ -536,7 +537,7 @@ k_sweep_march(const __grid_constant__ CUtensorMap tmT, const __grid_constant__ C
                          rB + (unsigned)((r + 1) * G::DR), slow_c, mail_c);
                 wait_full(sbn + L::OFF_FULL, npar, 42);   // the chunk the last step of the group takes the next operands from
                 step(C - 1, t + C - 1, gU + (C - 1) * USLOT, gV + (C - 1) * VSLOT, gUn + OUT_U, gVn + OUT_V, sbn + toff, slow_c, mail_c);
-                if (decltype(mail_c)::value) { mu += C * TW; mv += C * PUT; }
+                mu += C * TW; mv += C * PUT;
                 // every lane has read the group's words and the chunk's last row (its values were used by the update above)
                 __syncwarp();
                 mbar_arrive_ifu(sb + L::OFF_EMPTY, fl & F_L0);
@@ -557,7 +558,7 @@ k_sweep_march(const __grid_constant__ CUtensorMap tmT, const __grid_constant__ C
                     }
                 }
             };
-            if (mail_warp) march(IntC<1>()); else march(IntC<0>());
+            march(IntC<0>());
             // the last chunk (only its first row was read, by the prefetch of the last step) goes back to the loader, too
             if (!deadw) {
                 __syncwarp();
