@@ -27,10 +27,14 @@ def _model(nx, nz, seed, rough=True):
     return (0.4 + 0.3 * np.sin(0.11 * X) * np.cos(0.07 * Z) + (0.2 * rng.uniform(0, 1, (nx, nz)) if rough else 0.0))
 
 
+@pytest.mark.parametrize("cluster", [0, 1])
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
 @pytest.mark.parametrize("case", sorted(CASES))
-def test_2d_against_oracle(oracle, case, dtype):
+def test_2d_against_oracle(oracle, case, dtype, cluster, monkeypatch):
+    """cluster = 0: one CTA per source (k2d_solve<T, false>); 1: one cluster of 8 CTAs per source (k2d_solve<T, true>), which the
+    library itself only picks for grids wider than 1024 nodes"""
     from ttcr_b200 import Grid2d
+    monkeypatch.setenv("TTCR_B200_2D_CLUSTER", str(cluster))
     nx, nz, dx, dz, weno, rot, src, t0 = CASES[case]
     x, z = np.arange(nx) * dx, np.arange(nz) * dz
     # fp64: a rough model and eps = 1e-15 (every iteration is compared bit for bit); fp32: the WENO iteration does not settle

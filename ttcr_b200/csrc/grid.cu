@@ -158,7 +158,7 @@ class Grid final : public GridBase {
             for (int l = 0; l < 2; ++l) { free_field(s.tt[l]); cudaFree(s.mask[l]); }
             for (auto e : s.sweep_ev) cudaEventDestroy(e);
             cudaFree(s.d_change); cudaFreeHost(s.h_change);
-            cudaFree(s.d_fb); cudaFree(s.d_bar);
+            cudaFree(s.d_fb); cudaFree(s.d_bar); cudaFree(s.d_ppart);
             for (auto& a : s.pgraph)
                 for (auto& b : a)
                     if (b.exec) cudaGraphExecDestroy(b.exec);
@@ -466,6 +466,8 @@ class Grid final : public GridBase {
         MarchWState marchw;
         ttcr_b200_stats st{};
         unsigned* d_bar = nullptr;           // arrival counter of k_sweep_planes_coop's grid barrier
+        double* d_ppart = nullptr;           // per-block sums of the plane kernels' decreases (one slot per block and plane)
+        size_t ppart_cap = 0;
         FrozenBox* d_fb = nullptr;           // the source's frozen box, for k_sweep_plane (launch arguments stay source independent)
         struct PlaneGraph { cudaGraphExec_t exec = nullptr; bool pdl = false; };
         PlaneGraph pgraph[8][2];             // captured plane launches of a direction: [dir][first order | WENO]
@@ -499,6 +501,18 @@ class Grid final : public GridBase {
             CK(cudaMalloc(&lin_[l], d_.nodes() * sizeof(T)));
             bytes_ += d_.nodes() * sizeof(T);
         }
+    }
+
+    void ensure_ppart(Slot& s, size_t n) {
+        if (n <= s.ppart_cap) return;
+        CK(cudaStreamSynchronize(s.stream));
+        for (auto& a : s.pgraph)          // (captured graphs hold the old pointer)
+            for (auto& b : a)
+                if (b.exec) { cudaGraphExecDestroy(b.exec); b.exec = nullptr; }
+        cudaFree(s.d_ppart);
+        s.d_ppart = nullptr;
+        CK(cudaMalloc(&s.d_ppart, n * sizeof(double)));
+        s.ppart_cap = n;
     }
 
     void ensure_pts(Slot& s, size_t n) {
@@ -601,32 +615,42 @@ class Grid final : public GridBase {
             int grid = std::max(1, std::min(max_blocks, per_sm * sm_count_));
             if (grid > 1 && grid < max_blocks && grid % 2 == 0) --grid;
             CK(cudaMemsetAsync(s.d_bar, 0, sizeof(unsigned), s.stream));
+            ensure_ppart(s, (size_t)grid);
             SweepView wv = w;
             Dims dv = d_;
             const T* slo = slo_[w.layout];
             const uint32_t* mask = s.mask[w.layout];
             const FrozenBox* fbp = s.d_fb;
             T dx = g_.dx;
-            double* chg = s.d_change;
+            double* chg = s.d_ppart;
             unsigned* bar = s.d_bar;
             void* args[] = {&wv, &dv, &tt, &slo, &mask, &fbp, &dx, &chg, &bar};
             const void* fn = weno_stage ? (const void*)k_sweep_planes_coop<T, true> : (const void*)k_sweep_planes_coop<T, false>;
             CK(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(32, 8), args, 0, s.stream));
             (void)np;
-            s.st.launches += 1; s.st.sweep_launches += 1;
+            k_sum_partials<<<1, 256, 0, s.stream>>>(s.d_ppart, grid, s.d_change);
+            s.st.launches += 2; s.st.sweep_launches += 1;
             return;
         }
         // One launch per wavefront plane (the OpenCL design, Grid3Drn_OpenCL.h:839-848).  Launch bound: the np launches of
         // a direction are captured once per slot into a CUDA graph (their arguments do not depend on the source) and
         // replayed, optionally chained by programmatic dependent launch so that plane p+1 is resident when p drains.
         const int np = w.nu + w.nm - 1;
+        // one slot of s.d_ppart per block and plane (offsets do not depend on the source or the direction: they are part of the
+        // captured graph); the buffer is sized once per slot, before any capture
+        size_t nparts = 0;
+        for (int p = 0; p < np; ++p) {
+            const int u_lo = std::max(0, p - w.nm + 1), u_hi = std::min(w.nu - 1, p);
+            nparts += (size_t)(d_.kpad / 32) * ((u_hi - u_lo + 1 + 7) / 8);
+        }
+        ensure_ppart(s, nparts);
         auto launch_all = [&]() {
             const dim3 block(32, 8);
             const T* slo = slo_[w.layout];
             const uint32_t* mask = s.mask[w.layout];
             const FrozenBox* fbp = s.d_fb;
             T dx = g_.dx;
-            double* chg = s.d_change;
+            double* chg = s.d_ppart;
             cudaLaunchAttribute at[1];
             at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
             at[0].val.programmaticStreamSerializationAllowed = 1;
@@ -643,7 +667,9 @@ class Grid final : public GridBase {
                     CK(cudaLaunchKernelEx(&cfg, k_sweep_plane<T, true>, w, d_, tt, slo, mask, fbp, p, u_lo, u_hi, dx, chg));
                 else
                     CK(cudaLaunchKernelEx(&cfg, k_sweep_plane<T, false>, w, d_, tt, slo, mask, fbp, p, u_lo, u_hi, dx, chg));
+                chg += (size_t)cfg.gridDim.x * cfg.gridDim.y;
             }
+            k_sum_partials<<<1, 256, 0, s.stream>>>(s.d_ppart, (int)nparts, s.d_change);
         };
         if (plane_graph_) {
             auto& pg = s.pgraph[dir][weno_stage ? 1 : 0];
@@ -668,7 +694,7 @@ class Grid final : public GridBase {
         } else {
             launch_all();
         }
-        s.st.launches += np; s.st.sweep_launches += np;
+        s.st.launches += np + 1; s.st.sweep_launches += np;
     }
 
     int plane_kernel() const {
@@ -947,7 +973,26 @@ public:
             const size_t nb = std::min(per, ns - n0);
             p.tt = d_tt_ + first_slot * N_;
             p.frozen = d_frozen_ + first_slot * N_;
-            k2d_solve<T><<<(unsigned)nb, 1024, 0, st_>>>(p, (int)n0);
+            // wide grids: a cluster of CTAs per source (grid2d.cuh); narrow ones: one CTA (a wavefront fits its threads and
+            // its L1, and more sources run at a time)
+            const int cl_env = getenv("TTCR_B200_2D_CLUSTER") ? atoi(getenv("TTCR_B200_2D_CLUSTER")) : -1;   // (read per call: the tests run both kernels)
+            const bool use_cluster = cl_env >= 0 ? cl_env != 0 : std::min(ncx_, ncz_) + 1 > 1024;   // (measured: 1001^2 0.74 s with one CTA, 0.84 s with a cluster; 2001^2 3.13 s / 1.99 s)
+            if (use_cluster) {
+                cudaLaunchConfig_t cfg{};
+                static const int cs_env = getenv("TTCR_B200_2D_CLUSTER_SIZE") ? atoi(getenv("TTCR_B200_2D_CLUSTER_SIZE")) : K2D_CLUSTER;
+                static const int bs_env = getenv("TTCR_B200_2D_BLOCK") ? atoi(getenv("TTCR_B200_2D_BLOCK")) : 256;
+                const int cs = std::max(1, std::min(cs_env, K2D_CLUSTER));
+                cfg.gridDim = dim3((unsigned)nb * cs);
+                cfg.blockDim = dim3(std::max(32, std::min(bs_env, 1024)));
+                cfg.stream = st_;
+                cudaLaunchAttribute at[1];
+                at[0].id = cudaLaunchAttributeClusterDimension;
+                at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+                cfg.attrs = at; cfg.numAttrs = 1;
+                CK(cudaLaunchKernelEx(&cfg, k2d_solve<T, true>, p, (int)n0));
+            } else {
+                k2d_solve<T, false><<<(unsigned)nb, 1024, 0, st_>>>(p, (int)n0);
+            }
             for (size_t b = 0; b < nb; ++b) {
                 const size_t n = n0 + b, m = rxo[n + 1] - rxo[n];
                 if (m) k2d_interp<T><<<(unsigned)((m + 127) / 128), 128, 0, st_>>>(p, d_tt_ + (first_slot + b) * N_, brx.as<T>() + 2 * rxo[n], (int)m,

@@ -18,6 +18,8 @@
 // -fmad=false); T = float evaluates the same expressions in float (the reference's float build promotes through its double
 // literals; tolerance 1e-4, tests/).
 #pragma once
+#include <cooperative_groups.h>
+
 #include "update.cuh"
 
 namespace ttcrb200 {
@@ -39,20 +41,27 @@ struct P2 {
     int* err;              // [source]: 1 = Tx outside the grid
 };
 
+// A traveltime read.  CG: the field is shared by the CTAs of a cluster (k2d_solve<T, true>): the L1 of an SM is not coherent
+// with the stores of the other SMs, so the read goes to L2 (ld.global.cg); stores write through anyway.
+template <bool CG, typename T>
+__device__ __forceinline__ T ld2(const T* p) {
+    if (CG) return __ldcg(p);
+    return *p;
+}
 // first-order one-sided minimum along one axis (Grid2Drn.h:924-943)
-template <typename T>
+template <bool CG, typename T>
 __device__ __forceinline__ T ax1_2d(const T* tt, size_t n, int q, int nc, size_t st) {
-    if (q == 0) return tt[n + st];
-    if (q == nc) return tt[n - st];
-    const T a = tt[n - st], t = tt[n + st];
+    if (q == 0) return ld2<CG>(tt + n + st);
+    if (q == nc) return ld2<CG>(tt + n - st);
+    const T a = ld2<CG>(tt + n - st), t = ld2<CG>(tt + n + st);
     return a < t ? a : t;
 }
 // per-axis WENO estimate: the branch order of Grid2Drn.h:1080-1190 is the one of axis_weno (update.cuh)
-template <typename T>
+template <bool CG, typename T>
 __device__ __forceinline__ T axw_2d(const T* tt, size_t n, int q, int nc, size_t st, T d) {
-    const T vm2 = q >= 2 ? tt[n - 2 * st] : T(0), vm1 = q >= 1 ? tt[n - st] : T(0);
-    const T vp1 = q <= nc - 1 ? tt[n + st] : T(0), vp2 = q <= nc - 2 ? tt[n + 2 * st] : T(0);
-    return axis_weno<T>(vm2, vm1, tt[n], vp1, vp2, q, nc, d);
+    const T vm2 = q >= 2 ? ld2<CG>(tt + n - 2 * st) : T(0), vm1 = q >= 1 ? ld2<CG>(tt + n - st) : T(0);
+    const T vp1 = q <= nc - 1 ? ld2<CG>(tt + n + st) : T(0), vp2 = q <= nc - 2 ? ld2<CG>(tt + n + 2 * st) : T(0);
+    return axis_weno<T>(vm2, vm1, ld2<CG>(tt + n), vp1, vp2, q, nc, d);
 }
 // the two local solvers: square cells (Grid2Drn.h:945-953) and dx != dz (:1041-1057); return the new value (or the old one)
 template <typename T>
@@ -81,22 +90,22 @@ __device__ __forceinline__ T solve_xz_2d(T old, T a, T b, T s, T dx, T dz) {
 }
 
 // kind: 0 update_node, 1 update_node45, 2 update_node_xz, 3 update_node_weno3, 4 update_node_weno3_xz.  Returns old - new.
-template <typename T>
+template <bool CG, typename T>
 __device__ __forceinline__ T update_2d(const P2<T>& p, T* tt, int i, int j, int kind) {
     const size_t st = (size_t)p.ncz + 1, n = (size_t)i * st + j;
     const int ncx = p.ncx, ncz = p.ncz;
-    const T old = tt[n];
+    const T old = ld2<CG>(tt + n);
     T a, b, t, nw;
     switch (kind) {
         case 0:
-            a = ax1_2d(tt, n, i, ncx, st);
-            b = ax1_2d(tt, n, j, ncz, 1);
+            a = ax1_2d<CG>(tt, n, i, ncx, st);
+            b = ax1_2d<CG>(tt, n, j, ncz, 1);
             nw = solve_sq_2d(old, a, b, p.s[n] * p.dx);
             break;
         case 1: {   // stencil rotated by pi/4 (Grid2Drn.h:957-1015): +MAX off the grid
             const T M = Lim<T>::max();
-            const T pp = (i != ncx && j != ncz) ? tt[n + st + 1] : M, mm = (i != 0 && j != 0) ? tt[n - st - 1] : M;
-            const T pm = (i != ncx && j != 0) ? tt[n + st - 1] : M, mp = (i != 0 && j != ncz) ? tt[n - st + 1] : M;
+            const T pp = (i != ncx && j != ncz) ? ld2<CG>(tt + n + st + 1) : M, mm = (i != 0 && j != 0) ? ld2<CG>(tt + n - st - 1) : M;
+            const T pm = (i != ncx && j != 0) ? ld2<CG>(tt + n + st - 1) : M, mp = (i != 0 && j != ncz) ? ld2<CG>(tt + n - st + 1) : M;
             if (i == 0) { a = pp; b = pm; }
             else if (i == ncx) { a = mm; b = mp; }
             else { a = pp; t = mm; a = a < t ? a : t; b = pm; t = mp; b = b < t ? b : t; }
@@ -104,18 +113,18 @@ __device__ __forceinline__ T update_2d(const P2<T>& p, T* tt, int i, int j, int 
             break;
         }
         case 2:
-            a = ax1_2d(tt, n, i, ncx, st);
-            b = ax1_2d(tt, n, j, ncz, 1);
+            a = ax1_2d<CG>(tt, n, i, ncx, st);
+            b = ax1_2d<CG>(tt, n, j, ncz, 1);
             nw = solve_xz_2d(old, a, b, p.s[n], p.dx, p.dz);
             break;
         case 3:
-            a = axw_2d(tt, n, i, ncx, st, p.dx);
-            b = axw_2d(tt, n, j, ncz, 1, p.dx);   // (sic: dx on both axes, the scheme requires dx == dz)
+            a = axw_2d<CG>(tt, n, i, ncx, st, p.dx);
+            b = axw_2d<CG>(tt, n, j, ncz, 1, p.dx);   // (sic: dx on both axes, the scheme requires dx == dz)
             nw = solve_sq_2d(old, a, b, p.s[n] * p.dx);
             break;
         default:
-            a = axw_2d(tt, n, i, ncx, st, p.dx);
-            b = axw_2d(tt, n, j, ncz, 1, p.dz);
+            a = axw_2d<CG>(tt, n, i, ncx, st, p.dx);
+            b = axw_2d<CG>(tt, n, j, ncz, 1, p.dz);
             nw = solve_xz_2d(old, a, b, p.s[n], p.dx, p.dz);
     }
     if (nw < old) { tt[n] = nw; return old - nw; }
@@ -172,37 +181,68 @@ __device__ void init_2d(const P2<T>& p, T* tt, unsigned char* frozen, const T* t
     }
 }
 
-// One CTA = one source, start to finish.
-template <typename T>
+// One CTA = one source, start to finish (CL = false, 1024 threads), or -- wide grids -- one CLUSTER of K2D_CLUSTER CTAs of 256
+// threads per source (CL = true): the nodes of a wavefront are dealt over the cluster's threads, the CTA barrier becomes the
+// hardware cluster barrier (barrier.cluster, release / acquire), traveltimes are read through L2.  With one CTA a wavefront
+// of a 2001 x 2001 grid costs 4.6 us -- every node of a diagonal lies in a different 128-byte line, and ~22000 sector requests
+// per diagonal go through ONE SM's L1 -- with eight SMs sharing them it is bound by the L2 round trip and the barrier.
+constexpr int K2D_CLUSTER = 8;
+
+template <typename T, bool CL>
 __global__ void __launch_bounds__(1024, 1) k2d_solve(P2<T> p, int first_source) {
+    namespace cg = cooperative_groups;
     __shared__ double red[32];
+    __shared__ double cred[K2D_CLUSTER];   // (rank 0's copy collects the CTAs' sums)
     __shared__ int go;
-    const int b = blockIdx.x, src = first_source + b;
+    __shared__ int fbox[4];                // bounding box of the nodes initFSM may freeze: the frozen bytes are only read inside
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = CL ? (int)cluster.block_rank() : 0, ncta = CL ? (int)cluster.num_blocks() : 1;   // (<= K2D_CLUSTER)
+    const int b = (int)blockIdx.x / ncta, src = first_source + b;
     const size_t N = (size_t)(p.ncx + 1) * (p.ncz + 1);
     T* tt = p.tt + (size_t)b * N;
     unsigned char* frozen = p.frozen + (size_t)b * N;
     const T* tx = p.tx + (size_t)src * p.ntx_max * 2;
     const T* t0 = p.t0 + (size_t)src * p.ntx_max;
     const int ntx = p.ntx[src];
-    const int tid = threadIdx.x, nth = blockDim.x;
+    const int ltid = threadIdx.x;
+    const int tid = rank * blockDim.x + ltid, nth = ncta * blockDim.x;   // the thread's place among all threads of the source
     const int ncx = p.ncx, ncz = p.ncz;
+    auto sync_all = [&]() {
+        if (CL) cluster.sync(); else __syncthreads();
+    };
 
-    if (tid == 0) {   // checkPts (Grid2Drn.h:333-342)
+    if (ltid == 0) {   // checkPts (Grid2Drn.h:333-342); every CTA of a cluster comes to the same verdict
         const T xmax = p.xmin + ncx * p.dx, zmax = p.zmin + ncz * p.dz;
         int bad = 0;
         for (int n = 0; n < ntx; ++n)
             if (tx[2 * n] < p.xmin || tx[2 * n] > xmax || tx[2 * n + 1] < p.zmin || tx[2 * n + 1] > zmax) bad = 1;
-        p.err[src] = bad;
+        if (rank == 0) p.err[src] = bad;
         go = !bad;
+        // initFSM freezes the (2 npts + 1)^2 nodes around an on-node Tx point and the (2 npts)^2 around the cell of an off-node
+        // one (Grid2Drn.h:1360-1419); one node of margin for the rounding of the cell index
+        const int np = p.weno ? 2 : 1;
+        int ilo = 1 << 30, ihi = -1, jlo = 1 << 30, jhi = -1;
+        for (int n = 0; n < ntx; ++n) {
+            const int ci = (int)floor(((double)tx[2 * n] - (double)p.xmin) / (double)p.dx), cj = (int)floor(((double)tx[2 * n + 1] - (double)p.zmin) / (double)p.dz);
+            ilo = min(ilo, ci - np - 1); ihi = max(ihi, ci + np + 2);
+            jlo = min(jlo, cj - np - 1); jhi = max(jhi, cj + np + 2);
+        }
+        fbox[0] = ilo; fbox[1] = ihi; fbox[2] = jlo; fbox[3] = jhi;
     }
     __syncthreads();
     if (!go) return;
     for (size_t n = tid; n < N; n += nth) { tt[n] = Lim<T>::max(); frozen[n] = 0; }
-    __syncthreads();
+    sync_all();
     if (tid == 0) init_2d(p, tt, frozen, tx, t0, ntx, p.weno ? 2 : 1);
-    __syncthreads();
+    sync_all();
 
     const bool square = p.dx == p.dz;
+    const int f_ilo = fbox[0], f_ihi = fbox[1], f_jlo = fbox[2], f_jhi = fbox[3];
+    auto is_frozen = [&](int i, int j) -> bool {   // (no load, and no second round trip to L2 before the update's loads, outside the box)
+        if (i < f_ilo || i > f_ihi || j < f_jlo || j > f_jhi) return false;
+        const size_t n = (size_t)i * (ncz + 1) + j;
+        return CL ? __ldcg(frozen + n) != 0 : frozen[n] != 0;
+    };
     auto sweeps = [&](int kind) -> double {   // the four passes (i up, j up), (i down, j up), (i down, j down), (i up, j down)
         double acc = 0.0;
         for (int d = 0; d < 4; ++d) {
@@ -211,8 +251,8 @@ __global__ void __launch_bounds__(1024, 1) k2d_solve(P2<T> p, int first_source) 
                 for (int ii = 0; ii <= ncx; ++ii) {
                     const int i = iu ? ii : ncx - ii;
                     for (int j = tid; j <= ncz; j += nth)
-                        if (!frozen[(size_t)i * (ncz + 1) + j]) acc += (double)update_2d(p, tt, i, j, 1);
-                    __syncthreads();
+                        if (!is_frozen(i, j)) acc += (double)update_2d<CL>(p, tt, i, j, 1);
+                    sync_all();
                 }
             } else {
                 for (int ds = 0; ds <= ncx + ncz; ++ds) {
@@ -220,9 +260,9 @@ __global__ void __launch_bounds__(1024, 1) k2d_solve(P2<T> p, int first_source) 
                     for (int ii = lo + tid; ii <= hi; ii += nth) {
                         const int jj = ds - ii;
                         const int i = iu ? ii : ncx - ii, j = ju ? jj : ncz - jj;
-                        if (!frozen[(size_t)i * (ncz + 1) + j]) acc += (double)update_2d(p, tt, i, j, kind);
+                        if (!is_frozen(i, j)) acc += (double)update_2d<CL>(p, tt, i, j, kind);
                     }
-                    __syncthreads();
+                    sync_all();
                 }
             }
         }
@@ -231,17 +271,24 @@ __global__ void __launch_bounds__(1024, 1) k2d_solve(P2<T> p, int first_source) 
     auto converged = [&](double acc) -> bool {   // L1 change of the iteration = sum of the decreases (tt only decreases)
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-        if ((tid & 31) == 0) red[tid >> 5] = acc;
+        if ((ltid & 31) == 0) red[ltid >> 5] = acc;
         __syncthreads();
-        if (tid == 0) {
+        if (ltid == 0) {
             double c = 0.0;
-            for (int w = 0; w < (nth + 31) / 32; ++w) c += red[w];
+            for (int w = 0; w < ((int)blockDim.x + 31) / 32; ++w) c += red[w];
+            if (CL) *cluster.map_shared_rank(&cred[rank], 0) = c;   // fixed order: warps of a CTA, then CTAs by rank
+            else cred[0] = c;
+        }
+        sync_all();
+        if (ltid == 0) {
+            double c = 0.0;
+            for (int r = 0; r < ncta; ++r) c += CL ? *cluster.map_shared_rank(&cred[r], 0) : cred[r];
             const T change = c > (double)Lim<T>::max() ? Lim<T>::max() : (T)c;
             go = change >= p.eps_total;
         }
         __syncthreads();
         const bool r = !go;
-        __syncthreads();
+        sync_all();   // (rank 0's sums have been read by everybody before anybody starts the next iteration)
         return r;
     };
     int niter = 0, niterw = 0;

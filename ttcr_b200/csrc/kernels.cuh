@@ -407,10 +407,25 @@ __device__ __forceinline__ double plane_node(const SweepView& w, const Dims& d, 
     return delta;
 }
 
+// sum of a (32, 8) block's per-thread values, warps in order, into *out
+__device__ __forceinline__ void block_partial(double v, double* out) {
+    __shared__ double sh[8];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (threadIdx.x == 0) sh[threadIdx.y] = v;
+    __syncthreads();
+    if (threadIdx.x == 0 && threadIdx.y == 0) {
+        double a = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) a += sh[w];
+        *out = a;
+    }
+}
+
 template <typename T, bool WENO>
 __global__ void __launch_bounds__(256) k_sweep_plane(SweepView w, Dims d, T* __restrict__ tt, const T* __restrict__ slo,
                                                      const uint32_t* __restrict__ frozen, const FrozenBox* __restrict__ fbp, int p,
-                                                     int u_lo, int u_hi, T dx, double* __restrict__ change) {
+                                                     int u_lo, int u_hi, T dx, double* __restrict__ partial) {
     // Programmatic dependent launch (grid.cu launches the planes of a sweep with programmatic stream serialisation):
     // let plane p+1 be scheduled now, and touch memory only when plane p-1 has completed and flushed.  Both are no-ops
     // in a plain launch.  The frozen box sits in device memory so that the launch arguments of a plane do not depend
@@ -421,10 +436,11 @@ __global__ void __launch_bounds__(256) k_sweep_plane(SweepView w, Dims d, T* __r
     const int v = blockIdx.x * 32 + threadIdx.x;
     const int u = u_lo + blockIdx.y * 8 + threadIdx.y;
     double delta = plane_node<T, WENO>(w, d, tt, slo, frozen, fb, p, u, u_hi, v, dx);
-    // block reduction of the L1 change (Grid3Drnfs.h:144-150; tt only ever decreases, so the
-    // per-sweep decreases telescope to sum |times - tt| of the iteration)
-    for (int o = 16; o > 0; o >>= 1) delta += __shfl_xor_sync(0xffffffffu, delta, o);
-    if (threadIdx.x == 0 && delta != 0.0) atomicAdd(change, delta);
+    // block reduction of the L1 change (Grid3Drnfs.h:144-150; tt only ever decreases, so the per-sweep decreases telescope to
+    // sum |times - tt| of the iteration).  Every block writes its sum to its own slot of `partial` (the plane's slice of the
+    // sweep's buffer); k_sum_partials adds the slots in a fixed order, so the iteration count does not depend on the order in
+    // which blocks happen to finish (an atomicAdd of doubles would).
+    block_partial(delta, partial + (size_t)blockIdx.y * gridDim.x + blockIdx.x);
 }
 
 // All wavefront planes of a directional sweep in ONE cooperative launch: the grid walks the planes and meets at a
@@ -436,7 +452,7 @@ __global__ void __launch_bounds__(256) k_sweep_plane(SweepView w, Dims d, T* __r
 template <typename T, bool WENO>
 __global__ void __launch_bounds__(256) k_sweep_planes_coop(SweepView w, Dims d, T* __restrict__ tt, const T* __restrict__ slo,
                                                            const uint32_t* __restrict__ frozen, const FrozenBox* __restrict__ fbp,
-                                                           T dx, double* __restrict__ change, unsigned* __restrict__ bar) {
+                                                           T dx, double* __restrict__ partial, unsigned* __restrict__ bar) {
     const FrozenBox fb = *fbp;
     const int np = w.nu + w.nm - 1;
     const int vb = d.kpad / 32;
@@ -464,8 +480,7 @@ __global__ void __launch_bounds__(256) k_sweep_planes_coop(SweepView w, Dims d, 
             __syncthreads();
         }
     }
-    for (int o = 16; o > 0; o >>= 1) delta += __shfl_xor_sync(0xffffffffu, delta, o);
-    if (threadIdx.x == 0 && delta != 0.0) atomicAdd(change, delta);
+    block_partial(delta, partial + blockIdx.x);   // (one slot per CTA, summed in CTA order by k_sum_partials)
 }
 
 }  // namespace ttcrb200
