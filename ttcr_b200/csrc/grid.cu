@@ -171,7 +171,7 @@ class Grid final : public GridBase {
             cudaStreamDestroy(s.stream);
         }
         for (int l = 0; l < 2; ++l) free_field(slo_[l]);
-        cudaFree(lin_[0]); cudaFree(lin_[1]);
+        cudaFree(lin_);
         if (copy_st_) {
             cudaStreamDestroy(copy_st_);
             for (auto& e : copy_ev_) cudaEventDestroy(e);
@@ -210,6 +210,7 @@ class Grid final : public GridBase {
         std::lock_guard<std::mutex> lk(lin_mu_);
         ensure_lin();
         cudaStream_t st = slots_[0].stream;
+        T* const stage = staging(slots_[0]);
         // A large node model in numpy order coming from the host: the x planes are contiguous in both the source and the
         // sheared layouts, so the model is copied in chunks of planes on a copy stream and every chunk is imported (into
         // both layouts) while the next one is still on the bus.  The copy is the longer leg; only the last import shows.
@@ -225,24 +226,26 @@ class Grid final : public GridBase {
             const size_t plane = (size_t)d_.nj * d_.nk;
             for (int c = 0; c < NCHUNK; ++c) {
                 const int i0 = (int)((long long)d_.ni * c / NCHUNK), i1 = (int)((long long)d_.ni * (c + 1) / NCHUNK);
-                CK(cudaMemcpyAsync(lin_[0] + i0 * plane, (const T*)s + i0 * plane, (size_t)(i1 - i0) * plane * sizeof(T), kind, copy_st_));
+                CK(cudaMemcpyAsync(stage + i0 * plane, (const T*)s + i0 * plane, (size_t)(i1 - i0) * plane * sizeof(T), kind, copy_st_));
                 CK(cudaEventRecord(copy_ev_[c], copy_st_));
                 CK(cudaStreamWaitEvent(st, copy_ev_[c], 0));
                 const size_t ne = (size_t)(i1 - i0) * d_.qs * d_.kpad;
-                for (int l = 0; l < 2; ++l) k_import<T><<<nblocks(ne), 256, 0, st>>>(lin_[0], order, slo_[l], l, d_, i0, i1);
+                for (int l = 0; l < 2; ++l) k_import<T><<<nblocks(ne), 256, 0, st>>>(stage, order, slo_[l], l, d_, i0, i1);
             }
+            release_staging(slots_[0], st);
             CK(cudaGetLastError());
             CK(cudaStreamSynchronize(st));
             have_slowness_ = true;
             return;
         }
-        CK(cudaMemcpyAsync(lin_[0], s, n * sizeof(T), kind, st));
-        const T* nodes = lin_[0];
+        CK(cudaMemcpyAsync(stage, s, n * sizeof(T), kind, st));
+        const T* nodes = stage;
         if (cell_) {
-            k_cell_to_node<T><<<nblocks(d_.nodes()), 256, 0, st>>>(lin_[0], lin_[1], order, g_.ncx, g_.ncy, g_.ncz);
-            nodes = lin_[1];
+            k_cell_to_node<T><<<nblocks(d_.nodes()), 256, 0, st>>>(stage, lin_, order, g_.ncx, g_.ncy, g_.ncz);
+            nodes = lin_;
         }
         for (int l = 0; l < 2; ++l) k_import<T><<<nblocks(d_.elems()), 256, 0, st>>>(nodes, order, slo_[l], l, d_);
+        release_staging(slots_[0], st);
         CK(cudaGetLastError());
         CK(cudaStreamSynchronize(st));
         have_slowness_ = true;
@@ -252,11 +255,12 @@ class Grid final : public GridBase {
         CK(cudaSetDevice(dev_));
         if (order != 0 && order != 1) throw Err(TTCR_B200_ERR_INVALID, "bad order");
         std::lock_guard<std::mutex> lk(lin_mu_);
-        ensure_lin();
         cudaStream_t st = slots_[0].stream;
-        k_export<T><<<nblocks(d_.nodes()), 256, 0, st>>>(slo_[0], 0, lin_[0], order, d_);
+        T* const stage = staging(slots_[0]);
+        k_export<T><<<nblocks(d_.nodes()), 256, 0, st>>>(slo_[0], 0, stage, order, d_);
         CK(cudaGetLastError());
-        CK(cudaMemcpyAsync(out, lin_[0], d_.nodes() * sizeof(T), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(out, stage, d_.nodes() * sizeof(T), cudaMemcpyDeviceToHost, st));
+        release_staging(slots_[0], st);
         CK(cudaStreamSynchronize(st));
     }
 
@@ -264,11 +268,11 @@ class Grid final : public GridBase {
         CK(cudaSetDevice(dev_));
         Slot& s = slot_at(slot);
         if (order != 0 && order != 1) throw Err(TTCR_B200_ERR_INVALID, "bad order");
-        std::lock_guard<std::mutex> lk(lin_mu_);
-        ensure_lin();
-        k_export<T><<<nblocks(d_.nodes()), 256, 0, s.stream>>>(s.tt[0], 0, lin_[0], order, d_);
+        T* const stage = staging(s);   // (the slot's own scratch: no lock, slots export concurrently)
+        k_export<T><<<nblocks(d_.nodes()), 256, 0, s.stream>>>(s.tt[0], 0, stage, order, d_);
         CK(cudaGetLastError());
-        CK(cudaMemcpyAsync(out, lin_[0], d_.nodes() * sizeof(T), cudaMemcpyDeviceToHost, s.stream));
+        CK(cudaMemcpyAsync(out, stage, d_.nodes() * sizeof(T), cudaMemcpyDeviceToHost, s.stream));
+        release_staging(s, s.stream);
         CK(cudaStreamSynchronize(s.stream));
     }
 
@@ -495,12 +499,19 @@ class Grid final : public GridBase {
         return slots_[slot];
     }
 
-    void ensure_lin() {   // lin_[1] holds the averaged node model of a cell grid; node grids never need it
-        for (int l = 0; l < (cell_ ? 2 : 1); ++l) {
-            if (lin_[l]) continue;
-            CK(cudaMalloc(&lin_[l], d_.nodes() * sizeof(T)));
-            bytes_ += d_.nodes() * sizeof(T);
-        }
+    // Linear staging (a model or a field in host order, on its way in or out).  Between solves the L2-layout traveltime array
+    // of a slot is scratch -- a solve starts in L1 and k_relayout2 rewrites every node of L2 before the first sweep that reads
+    // it -- so its first nodes() elements serve as the staging buffer (it has elems() > 2 nodes() of them) instead of a
+    // separate allocation (0.5 GB at 512^3); release_staging() restores the +MAX the non-node slots of that range must hold.
+    T* staging(Slot& s) { return s.tt[1]; }
+    void release_staging(Slot& s, cudaStream_t st) {
+        const size_t n = (d_.nodes() + 3) / 4 * 4;   // (elems() is a multiple of 32)
+        k_fill16<T><<<nblocks(n / (16 / sizeof(T)), 256, 148 * 32), 256, 0, st>>>(s.tt[1], n, Lim<T>::max());
+    }
+    void ensure_lin() {   // the averaged node model of a cell grid; node grids never need it
+        if (!cell_ || lin_) return;
+        CK(cudaMalloc(&lin_, d_.nodes() * sizeof(T)));
+        bytes_ += d_.nodes() * sizeof(T);
     }
 
     void ensure_ppart(Slot& s, size_t n) {
@@ -852,7 +863,7 @@ class Grid final : public GridBase {
     int kernel_ = TTCR_B200_KERNEL_AUTO;
     TileOptions tile_opt_{};
     T* slo_[2] = {nullptr, nullptr};   // node slowness in layouts L1, L2
-    T* lin_[2] = {nullptr, nullptr};   // linear staging buffers (host order)
+    T* lin_ = nullptr;   // cell grids: the averaged node model in host order (the other staging buffer is a slot's idle array)
     std::mutex lin_mu_;
     std::vector<Slot> slots_;
     size_t bytes_ = 0;

@@ -36,6 +36,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <stdexcept>
@@ -581,10 +582,14 @@ inline int tile_launch(TileState& s, const TileOptions& o, int sm_count, const S
     }
     TCK(cudaMemsetAsync(s.d_flags, 0, p.ntiles * sizeof(int), st));
     TCK(cudaMemsetAsync(s.d_ctrl, 0, sizeof(int), st));   // ticket counter only; the abort flag is sticky
-    static int occ_cache = 0;   // per instantiation
-    if (!occ_cache) {
-        TCK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_cache, k_sweep_tile<T, NW, R, D>, (NW + 2) * 32, 0));
-        if (occ_cache < 1) throw std::runtime_error("tile kernel does not fit on an SM");
+    // per instantiation; a pure query (static shared memory, no per-device function attribute), so every device of a box and
+    // every slot thread computes the same value: the atomic only makes the concurrent first use well defined
+    static std::atomic<int> occ_cache{0};
+    if (!occ_cache.load(std::memory_order_relaxed)) {
+        int q = 0;
+        TCK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, k_sweep_tile<T, NW, R, D>, (NW + 2) * 32, 0));
+        if (q < 1) throw std::runtime_error("tile kernel does not fit on an SM");
+        occ_cache.store(q, std::memory_order_relaxed);
     }
     int occ = occ_cache;
     if (o.ctas_per_sm > 0) occ = std::min(occ, o.ctas_per_sm);
