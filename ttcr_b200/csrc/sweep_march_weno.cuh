@@ -399,7 +399,7 @@ k_sweep_march_weno(const __grid_constant__ CUtensorMap tmT, const __grid_constan
             };
 
             // One march step: ring words at rUi / rVi must carry a tag >= tgs, outputs go to rUo / rVo with tag tgs + 1, the next
-            // step's operands are at `ao`.  ONE copy of this body exists in the kernel (the group loop below is not unrolled and
+            // step's operands are at `ao`.  TWO copies of this body exist in the kernel (the group loop below is unrolled by two and
             // the frozen-node and mailbox cases are run-time predicates): a step is ~500 instructions, and every copy more is
             // 8 KB that eight warps at eight different places of the loop pull through a 32 KB instruction cache.
             auto step = [&](const unsigned tgs, const unsigned rUi, const unsigned rVi, const unsigned rUo, const unsigned rVo, const unsigned ao,
@@ -477,7 +477,7 @@ k_sweep_march_weno(const __grid_constant__ CUtensorMap tmT, const __grid_constan
                 const unsigned so_n = (so + C * USLOT) & (unsigned)(URING - 1);
                 const unsigned gUn = aUin + so_n, gVn = aVin + (so_n >> 2);
                 unsigned aU = gU, aV = gV, ao = rB;
-#pragma unroll 1
+#pragma unroll 2   // (two copies of the step: half of the register moves of the rolled loop, 18 KB of hot code; measured 933 -> 887 ms per 512^3 solve, four copies 876 ms)
                 for (int r = 0; r < C; ++r) {
                     const bool last = r == C - 1;
                     if (last) wait_full(sbn + L::OFF_FULL, npar, 42);   // the chunk the last step takes the next operands from
