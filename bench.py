@@ -19,6 +19,8 @@ With N > 1 (torchrun, one rank per GPU) every rank solves its own source of the 
 source-parallel).  The device-resident arm has no collective in its timed region (the model is resident); the e2e arm
 is raytrace_sharded(): the model sits in pinned memory on rank 0 only, is uploaded once and broadcast over NCCL, the
 receiver times are all-gathered -- every step, inside the timed region.
+detail.default_arguments (rank 0): the reference's default arguments (fp64, weno=1) at 256^3, weno=1 at 512^3 fp32, and BASELINE.json
+configs[4]'s size (1024^3 fp32, one source) with its own roofline fraction.
 detail.config4 (every N): BASELINE.json configs[3], 511^3 cells -> Grid3Drcfs averaging, 64 sources sharded over the
 ranks through raytrace_sharded (strong scaling; model on rank 0, broadcast + all-gather inside its wall-clock time).
 --impl reference times the reference's own CPU implementation on rank 0: 1 thread for 1 source; for --gpus N > 1 the N
@@ -333,6 +335,24 @@ def default_path_side(local_rank):
                    "avg_sweep_ms": per_sweep_ms,
                    "roofline_frac": BYTES_PER_NODE_SWEEP * float(n) ** 3 / (per_sweep_ms * 1e-3) / 1e9 / peak,
                    "kernel": "k_sweep_march_weno (WENO stage), k_sweep_march (first-order stage)"}
+    g.close()
+    # BASELINE.json configs[4] size: 1024^3 nodes fp32, one source at -1/4 L of the centre, first order (k_sweep_march4: the
+    # marching kernel with four nodes per thread, which the library picks for grids of ~700^3 and more)
+    n = 1024
+    x, s = gradient_model(n, np.float32)
+    g = Grid3d(x, x, x, cell_slowness=0, tt_from_rp=0, eps=1e-5, maxit=50, weno=0, dtype=np.float32, device=local_rank)
+    g.set_slowness(s)
+    del s
+    dxn = float(x[1] - x[0])
+    src5 = np.round(np.array([[5.0, 5.0, 5.0]]) / dxn) * dxn
+    g.solve(src5)
+    st = g.solve(src5)
+    per_sweep_ms = st["sweep_ms"] / max(st["sweeps"], 1)
+    out["config5_1024"] = {"workload": "1024^3 gradient model, one source on a node near (5, 5, 5), fp32, first order (BASELINE.json configs[4] size)",
+                           "solve_ms": st["solve_ms"], "niter": st["niter"], "sweeps": st["sweeps"],
+                           "value": float(n) ** 3 * st["sweeps"] / (st["solve_ms"] * 1e-3) / 1e6, "avg_sweep_ms": per_sweep_ms,
+                           "roofline_frac": BYTES_PER_NODE_SWEEP * float(n) ** 3 / (per_sweep_ms * 1e-3) / 1e9 / peak,
+                           "device_bytes": g.device_bytes(), "kernel": "k_sweep_march4 (four nodes per thread)"}
     g.close()
     return out
 
