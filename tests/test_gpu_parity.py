@@ -138,6 +138,26 @@ def test_plane_and_tile_kernels_agree_bitwise():
         assert out[0][1] == o[1]
 
 
+@pytest.mark.parametrize("kernel", [1, 6, 2, 7, 74])
+def test_change_sum_is_reproducible(kernel):
+    """The L1 change that decides `change >= eps * N` (Grid3Drnfs.h:144-150) is reduced in a fixed order by every sweep kernel
+    (per-block / per-tile partial sums, k_sum_partials): the same solve twice gives the same sum bit for bit, hence the same
+    iteration count.  (Round 1's plane kernels added doubles with atomicAdd in whatever order the blocks finished.)"""
+    from ttcr_b200 import Grid3d
+    n = 56
+    x, s = _model(n, 21)
+    src = np.array([[x[9], x[30], x[41]]])
+    g = Grid3d(x, x, x, cell_slowness=0, tt_from_rp=False, weno=0, dtype=np.float32, eps=1e-9, maxit=3)
+    set_kernel(g, kernel)
+    g.set_slowness(s)
+    seen = set()
+    for _ in range(4):
+        g.raytrace(src, src)
+        st = g.get_stats()
+        seen.add((st["last_change"], st["niter"]))
+    assert len(seen) == 1, seen
+
+
 def test_homogeneous_analytic_config2_scaled():
     """config 2 (homogeneous, centre source, t = s*dist), scaled to 128^3 for test time"""
     from ttcr_b200 import Grid3d
