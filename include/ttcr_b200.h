@@ -146,7 +146,8 @@ int ttcr_b200_get_niter(ttcr_b200_grid* g, size_t slot, int* niter, int* niterw)
 
 /* Replaces: Grid3D::setTraveltimeFromRaypath / setUsePool (Grid3D.h:287,302-309) and tuning knobs.
  * keys: "tt_from_rp" (0/1), "kernel" (TTCR_B200_KERNEL_*), "tile_rows" (flag chunk, rows),
- *       "ctas_per_sm", "march_nodes" (k_sweep_march: 2 or 4 nodes per thread and step, 0 = by grid size), "weno_kernel"
+ *       "ctas_per_sm", "march_nodes" (k_sweep_march: 2 or 4 nodes per thread and step, 0 = by grid size), "tile_warps" (compute warps per
+ *       tile, 0 = by grid size), "weno_kernel"
  *       (kernel of the WENO stage), "max_ctas" (cap on a marching kernel's grid), "plane_graph" / "plane_pdl" (0/1: replay the plane-per-launch sweeps of the WENO stage from a
  *       captured CUDA graph / chain them by programmatic dependent launch), "use_pool" (accepted, ignored). */
 int ttcr_b200_set_option(ttcr_b200_grid* g, const char* key, double value);

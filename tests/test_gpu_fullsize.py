@@ -53,19 +53,22 @@ def test_config3_512_gradient_properties():
     x, s = _gradient(n)
     src = np.array([[0.0, 0.0, 0.0]])
     fields = []
-    for kernel, nodes in ((7, 2), (7, 4), (2, 0)):                 # k_sweep_march, k_sweep_march4, k_sweep_tile
+    # k_sweep_march (8 compute warps: what the library picks at this size), k_sweep_march4 (grids of 1024^3 and more),
+    # k_sweep_march with 12 compute warps (grids around 768^3), k_sweep_tile
+    for kernel, nodes, warps in ((7, 2, 8), (7, 4, 8), (7, 2, 12), (2, 0, 8)):
         g = Grid3d(x, x, x, cell_slowness=0, tt_from_rp=False, weno=0, dtype=np.float32)
         g.set_option("kernel", kernel)
         g.set_option("march_nodes", nodes)
+        g.set_option("tile_warps", warps)
         g.raytrace(src, src, s)
         fields.append(g.get_grid_traveltimes())
         assert g.get_niter() == (2, 0)
-        if kernel == 7 and nodes == 2:
+        if kernel == 7 and nodes == 2 and warps == 8:
             g.raytrace(src, src)                                   # idempotence: same call, same field
             assert np.array_equal(g.get_grid_traveltimes(), fields[0])
         del g
-    assert np.array_equal(fields[0], fields[1])                    # independently written marching kernels, bit for bit
-    assert np.array_equal(fields[0], fields[2])
+    for f in fields[1:]:
+        assert np.array_equal(fields[0], f)                        # independently written marching kernels, bit for bit
     f = fields[0]
     assert np.all(np.isfinite(f)) and f[0, 0, 0] == 0.0
     exact = _gradient_exact(x, src[0])

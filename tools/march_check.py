@@ -113,10 +113,10 @@ def timing(sizes, combos=None):
         g = Grid3d(x, x, x, cell_slowness=0, tt_from_rp=False, weno=0, dtype=np.float32)
         g.set_slowness(s)
         print(f"--- {n}^3 device bytes {g.device_bytes() / 2**30:.2f} GiB", flush=True)
-        combos_n = combos or [dict(kernel=MARCH, march_nodes=4), dict(kernel=MARCH, march_nodes=2)]
+        combos_n = combos or [dict(kernel=MARCH), dict(kernel=MARCH, march_nodes=4), dict(kernel=MARCH, march_nodes=2), dict(kernel=MARCH, march_nodes=2, tile_warps=12)]   # (the first: the library's own choice)
         for src in ([0.0, 0.0, 0.0],):
             for c in combos_n:
-                g.set_option("tile_warps", 8); g.set_option("tile_urows", 1); g.set_option("ctas_per_sm", 0); g.set_option("tile_depth", 8); g.set_option("march_nodes", 0)
+                g.set_option("tile_warps", 0); g.set_option("tile_urows", 1); g.set_option("ctas_per_sm", 0); g.set_option("tile_depth", 8); g.set_option("march_nodes", 0)
                 for k, v in c.items():
                     g.set_option(k, v)
                 best = None

@@ -429,7 +429,10 @@ class Grid final : public GridBase {
             kernel_ = (int)v;
         } else if (key == "tile_rows") tile_opt_.chunk = std::max(1, (int)v);
         else if (key == "ctas_per_sm") tile_opt_.ctas_per_sm = std::max(0, (int)v);
-        else if (key == "tile_warps") tile_opt_.warps = std::max(1, std::min(16, (int)v));
+        else if (key == "tile_warps") {   // 0: back to the choice by grid size
+            warps_set_ = v != 0;
+            tile_opt_.warps = warps_set_ ? std::max(1, std::min(16, (int)v)) : 8;
+        }
         else if (key == "tile_urows") tile_opt_.rows = std::max(1, std::min(4, (int)v));
         else if (key == "tile_depth") tile_opt_.depth = (int)v;
         else if (key == "spin_limit") tile_opt_.spin_limit = (long long)v;
@@ -589,16 +592,21 @@ class Grid final : public GridBase {
         // its chain of dependent steps (512^3: 3.5 tiles per SM) the two-node kernel wins (0.69 against 0.80 ms), where it is
         // bound by the SMs' throughput the four-node kernel does (measured cross-over between 640^3 and 768^3; 1024^3: 3.39
         // against 3.77 ms).
+        // In between (768^3: 1152 tiles) the two-node kernel with 12 compute warps (tiles of 24 planes x 32 lanes) is the fastest:
+        // 1.60 ms against 1.70 (four nodes) and 1.75 (two nodes, 8 warps); at 512^3 it ties with 8 warps, at 896^3 (1568 tiles) and
+        // 1024^3 it is 2 % behind the four-node kernel.
         const long long tiles2 = (long long)((w.nu + 15) / 16) * (d_.kpad / 32);
-        const int nodes = tile_opt_.nodes ? tile_opt_.nodes : (tiles2 >= 1000 ? 4 : 2);
+        const int nodes = tile_opt_.nodes ? tile_opt_.nodes : (tiles2 >= 1400 ? 4 : 2);
+        TileOptions topt = tile_opt_;
+        if (!warps_set_ && !tile_opt_.nodes && tiles2 >= 1000 && tiles2 < 1400) topt.warps = 12;
         if (kernel == TTCR_B200_KERNEL_MARCH && nodes == 4) {
-            const int nl = march4_sweep<T>(s.tile, s.march4, tile_opt_, sm_count_, w, d_, tt, slo_[w.layout], s.mask[w.layout], fb,
+            const int nl = march4_sweep<T>(s.tile, s.march4, topt, sm_count_, w, d_, tt, slo_[w.layout], s.mask[w.layout], fb,
                                           g_.dx, s.d_change, s.stream);
             s.st.launches += nl; s.st.sweep_launches += nl;
             return;
         }
         if (kernel == TTCR_B200_KERNEL_MARCH) {
-            const int nl = march_sweep<T>(s.tile, s.march, tile_opt_, sm_count_, w, d_, tt, slo_[w.layout], s.mask[w.layout], fb,
+            const int nl = march_sweep<T>(s.tile, s.march, topt, sm_count_, w, d_, tt, slo_[w.layout], s.mask[w.layout], fb,
                                          g_.dx, s.d_change, s.stream);
             s.st.launches += nl; s.st.sweep_launches += nl;
             return;
@@ -862,6 +870,7 @@ class Grid final : public GridBase {
     int dev_ = 0, sm_count_ = 148;
     int kernel_ = TTCR_B200_KERNEL_AUTO;
     TileOptions tile_opt_{};
+    bool warps_set_ = false;   // "tile_warps" given: no choice by grid size
     T* slo_[2] = {nullptr, nullptr};   // node slowness in layouts L1, L2
     T* lin_ = nullptr;   // cell grids: the averaged node model in host order (the other staging buffer is a slot's idle array)
     std::mutex lin_mu_;
