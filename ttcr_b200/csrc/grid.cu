@@ -795,7 +795,7 @@ class Grid final : public GridBase {
                             const dim3 grid((d_.nk + 31) / 32, (d_.nj + 31) / 32, d_.ni);
                             k_relayout<T><<<grid, dim3(32, 8), 0, s.stream>>>(s.tt[cur], cur, s.tt[want], d_);
                         } else {
-                            constexpr int RB = 128;
+                            constexpr int RB = 64;   // (measured at 512^3: 64 rows per block 12.35 ms per solve, 32: 12.49, 128: 12.45-12.51, 256: 12.59)
                             const dim3 grid(d_.kpad / 32, (d_.q + RB - 1) / RB, d_.ni);
                             k_relayout2<T, RB><<<grid, dim3(32, 8), 0, s.stream>>>(s.tt[cur], cur, s.tt[want], d_);
                         }

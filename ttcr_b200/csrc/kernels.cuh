@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(256) k_relayout2(const T* __restrict__ src, in
     if (k >= d.nk) return;
     const int shift = d.nk - 1 - 2 * k;                 // L2 row = L1 row + shift
     const size_t plane = (size_t)i * d.qs + GUARD;
-#pragma unroll 4
+#pragma unroll 8
     for (int y = threadIdx.y; y < RB; y += 8) {
         const int rd = r0 + y;                           // destination row
         if (rd >= d.q) break;
