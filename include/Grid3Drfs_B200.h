@@ -88,6 +88,51 @@ public:
         }
     }
 
+    // Grid3D::raytrace(Tx, t0, Rx, traveltimes, m_data, threadNo) (Grid3D.h:150-155, :743-780) and
+    // (.., r_data, m_data, threadNo) (:143-148, :646-690): the sensitivity matrix M of Grid3Drn::getRaypath.  The library walks
+    // the raw terms with the raypaths (the reference's two overloads differ, raypath.cuh: m_terms = 1 / 2); here they are
+    // merged like the reference merges them (m_data[nm].v += m.v in order of appearance, Grid3Drn.h:1612-1623).
+    void raytrace(const std::vector<sxyz<T1>>& Tx, const std::vector<T1>& t0, const std::vector<sxyz<T1>>& Rx,
+                  std::vector<T1>& traveltimes, std::vector<std::vector<sijv<T1>>>& m_data, const size_t threadNo = 0) const override {
+        std::vector<std::vector<sxyz<T1>>> r_data;
+        raytrace_m(Tx, t0, Rx, traveltimes, r_data, m_data, threadNo, 1);
+    }
+    void raytrace(const std::vector<sxyz<T1>>& Tx, const std::vector<T1>& t0, const std::vector<sxyz<T1>>& Rx,
+                  std::vector<T1>& traveltimes, std::vector<std::vector<sxyz<T1>>>& r_data,
+                  std::vector<std::vector<sijv<T1>>>& m_data, const size_t threadNo = 0) const override {
+        raytrace_m(Tx, t0, Rx, traveltimes, r_data, m_data, threadNo, 2);
+    }
+    void raytrace_m(const std::vector<sxyz<T1>>& Tx, const std::vector<T1>& t0, const std::vector<sxyz<T1>>& Rx,
+                    std::vector<T1>& traveltimes, std::vector<std::vector<sxyz<T1>>>& r_data,
+                    std::vector<std::vector<sijv<T1>>>& m_data, const size_t threadNo, const int mode) const {
+        // (the option is per grid: like the reference's own M overloads, not meant to run concurrently with other calls)
+        check(ttcr_b200_set_option(h, "m_terms", mode));
+        try {
+            raytrace(Tx, t0, Rx, traveltimes, r_data, threadNo);
+        } catch (...) {
+            ttcr_b200_set_option(h, "m_terms", 0);
+            throw;
+        }
+        check(ttcr_b200_set_option(h, "m_terms", 0));
+        size_t total = 0;
+        for (const auto& r : r_data) total += r.size();
+        std::vector<unsigned long long> node(8 * total);
+        std::vector<T1> val(8 * total);
+        check(ttcr_b200_get_m_terms(h, threadNo, node.data(), val.data()));
+        m_data.assign(Rx.size(), std::vector<sijv<T1>>());
+        size_t o = 0;
+        for (size_t n = 0; n < Rx.size(); ++n) {
+            for (size_t k = 8; k < 8 * r_data[n].size(); ++k) {   // (the receiver, point 0, closes no segment)
+                const size_t j = node[o + k];
+                bool found = false;
+                for (auto& m : m_data[n])
+                    if (m.j == j) { m.v += val[o + k]; found = true; break; }
+                if (!found) m_data[n].push_back(sijv<T1>(n, j, val[o + k]));
+            }
+            o += 8 * r_data[n].size();
+        }
+    }
+
     // Grid3D::raytrace(vector<vector<sxyz>>&, ...) (Grid3D.h:172-175, :810-853) is NOT virtual: called
     // through a Grid3D*, the reference's own fan-out (ctpl pool / std::thread blocks) runs and calls the
     // single-source override above concurrently with distinct threadNo, which the library supports (one

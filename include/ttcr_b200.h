@@ -126,6 +126,15 @@ int ttcr_b200_raytrace_rays(ttcr_b200_grid* g, const void* tx_xyz, const void* t
                             size_t nrx, void* tt_out, size_t* ray_npts, size_t slot);
 int ttcr_b200_get_rays(ttcr_b200_grid* g, size_t slot, void* xyz_out);
 
+/* Replaces: the m_data overloads of Grid3D::raytrace (Grid3D.h:85-95, :146-154, :187-194, :646-690, :743-780), i.e.
+ * Grid3Drn::getRaypath with m_data (Grid3Drn.h:1500-1801, :2144-2448): the sensitivity matrix M of node-slowness grids.
+ * With option "m_terms" = 1 (as the overload with m_data only) or 2 (as the overload with r_data and m_data: the reference's two
+ * overloads differ, see raypath.cuh), ttcr_b200_raytrace_rays also walks the M terms; this call returns them RAW: 8 (column, value)
+ * pairs per ray point, ray after ray, in the order the reference produces them (the 8 pairs of a ray's first point are zero:
+ * the receiver closes no segment).  node_out / value_out: 8 * sum(ray_npts) elements.  The reference then merges the terms
+ * of equal column of a ray in order of appearance (m_data[nm].v += m.v); so does the caller (ttcr_b200/rgrid.py). */
+int ttcr_b200_get_m_terms(ttcr_b200_grid* g, size_t slot, unsigned long long* node_out, void* value_out);
+
 /* Replaces: Grid3D::raytrace(vector<vector<sxyz>>&Tx, vector<vector<T>>&t0, vector<vector<sxyz>>&Rx,
  * vector<vector<T>>&tt) (Grid3D.h:172-175, :810-853).  Source s owns Tx points
  * [tx_off[s], tx_off[s+1]) and receivers [rx_off[s], rx_off[s+1]); tt_out is indexed like rx.
@@ -147,7 +156,7 @@ int ttcr_b200_get_niter(ttcr_b200_grid* g, size_t slot, int* niter, int* niterw)
 /* Replaces: Grid3D::setTraveltimeFromRaypath / setUsePool (Grid3D.h:287,302-309) and tuning knobs.
  * keys: "tt_from_rp" (0/1), "kernel" (TTCR_B200_KERNEL_*), "tile_rows" (flag chunk, rows),
  *       "ctas_per_sm", "march_nodes" (k_sweep_march: 2 or 4 nodes per thread and step, 0 = by grid size), "tile_warps" (compute warps per
- *       tile, 0 = by grid size), "weno_kernel"
+ *       tile, 0 = by grid size), "m_terms" (0/1/2: ttcr_b200_raytrace_rays also produces the raw terms of the matrix M), "weno_kernel"
  *       (kernel of the WENO stage), "max_ctas" (cap on a marching kernel's grid), "plane_graph" / "plane_pdl" (0/1: replay the plane-per-launch sweeps of the WENO stage from a
  *       captured CUDA graph / chain them by programmatic dependent launch), "use_pool" (accepted, ignored). */
 int ttcr_b200_set_option(ttcr_b200_grid* g, const char* key, double value);

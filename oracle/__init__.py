@@ -74,6 +74,9 @@ def _load_ref():
         if hasattr(lib, "ttcr_ref_raytrace_rays"):
             lib.ttcr_ref_raytrace_rays.argtypes = [C.c_void_p, dp, dp, C.c_size_t, dp, C.c_size_t, dp, C.c_size_t, C.c_void_p, dp,
                                                    C.c_size_t]
+        if hasattr(lib, "ttcr_ref_raytrace_m"):
+            lib.ttcr_ref_raytrace_m.argtypes = [C.c_void_p, dp, dp, C.c_size_t, dp, C.c_size_t, dp, C.c_size_t, C.c_void_p, C.c_void_p, dp,
+                                                C.c_size_t, C.c_int]
         lib.ttcr_ref_get_niter.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
         _ref = lib
     return _ref
@@ -152,6 +155,21 @@ class RefGrid:
                                                    thread_no, npts.ctypes.data, _dp(xyz), cap))
         assert npts.max(initial=0) <= cap
         return tt, [xyz[i, :int(n)].copy() for i, n in enumerate(npts)]
+
+    def raytrace_m(self, tx, t0, rx, thread_no=0, cap=65536, with_rays=False):
+        """Grid3D::raytrace(..., m_data, threadNo) (Grid3D.h:743-780) or, with_rays, (..., r_data, m_data, threadNo) (:646-690):
+        returns (tt at rx, list of (columns uint64, values) per receiver, in the order the reference leaves them in m_data)"""
+        tx = np.ascontiguousarray(tx, dtype=np.float64).reshape(-1, 3)
+        t0 = np.ascontiguousarray(np.broadcast_to(np.asarray(t0, dtype=np.float64), (tx.shape[0],)))
+        rx = np.ascontiguousarray(rx, dtype=np.float64).reshape(-1, 3)
+        tt = np.empty(rx.shape[0])
+        nnz = np.zeros(rx.shape[0], dtype=np.uintp)
+        col = np.zeros((rx.shape[0], cap), dtype=np.uint64)
+        val = np.zeros((rx.shape[0], cap))
+        self._chk(self._lib.ttcr_ref_raytrace_m(self._h, _dp(tx), _dp(t0), tx.shape[0], _dp(rx), rx.shape[0], _dp(tt), thread_no,
+                                                nnz.ctypes.data, col.ctypes.data, _dp(val), cap, int(bool(with_rays))))
+        assert nnz.max(initial=0) <= cap
+        return tt, [(col[i, :int(n)].copy(), val[i, :int(n)].copy()) for i, n in enumerate(nnz)]
 
     def raytrace_multi(self, tx, t0, rx):
         """one Tx point per source; same receivers for all; the reference's own thread fan-out."""

@@ -6,7 +6,7 @@
 // (ttcr/Grid3D.h:810-853) with nThreads = 2 and usePool off, so that the reference's own std::thread fan-out calls
 // raytrace(..., threadNo = 0 / 1) of the adapter concurrently: two slots of one ttcr_b200 grid.  Receiver traveltimes and the
 // fields of both thread slots must be bit-identical in double (node and cell slowness, first order and WENO), and within
-// 1e-4 in float.  Compiled from /root/reference's headers by `make -C oracle adapter-run` into oracle/_ref/adapter_run (which
+// 1e-4 in float; the matrices M of the two m_data overloads bit-identical in double.  Compiled from /root/reference's headers by `make -C oracle adapter-run` into oracle/_ref/adapter_run (which
 // travels to the GPU box); tests/test_gpu_parity.py::test_cxx_adapter_linked_and_run executes it.  No reference source is copied.
 #include <cmath>
 #include <cstdint>
@@ -101,6 +101,45 @@ static int run(bool weno, const char* name) {
     return bad;
 }
 
+// The two M overloads (Grid3D.h:143-155; node slowness only): columns, values and their order, bit for bit in double.  A smooth
+// model: the reference's raypath walk has no guard against cycling, and on the random model of run() it does not terminate.
+static int run_m() {
+    using T = double;
+    const uint32_t nc = 24;
+    const T dx = T(0.5);
+    std::unique_ptr<ttcr::Grid3D<T, uint32_t>> ref(new ttcr::Grid3Drnfs<T, uint32_t>(nc, nc, nc, dx, T(0), T(0), T(0), T(1e-15), 20, true, true, false, 1, false));
+    std::unique_ptr<ttcr::Grid3D<T, uint32_t>> gpu(
+        new ttcr::Grid3Drfs_B200<T, uint32_t, false>(nc, nc, nc, dx, T(0), T(0), T(0), T(1e-15), 20, true, true, false, 1, false));
+    std::vector<T> s((size_t)(nc + 1) * (nc + 1) * (nc + 1));
+    for (uint32_t k = 0, n = 0; k <= nc; ++k)
+        for (uint32_t j = 0; j <= nc; ++j)
+            for (uint32_t i = 0; i <= nc; ++i, ++n)
+                s[n] = (1.0 + 0.3 * std::sin(0.7 * i * dx) * std::cos(0.9 * j * dx)) / (1.0 + 0.1 * k * dx);
+    ref->setSlowness(s);
+    gpu->setSlowness(s);
+    std::vector<ttcr::sxyz<T>> Tx{ttcr::sxyz<T>(3.3, 7.1, 8.9)}, Rx{ttcr::sxyz<T>(10.2, 1.7, 2.9), ttcr::sxyz<T>(2.5, 3.5, 1.0), ttcr::sxyz<T>(6.0, 6.0, 11.5)};
+    std::vector<T> t0{0.25};
+    int bad = 0;
+    for (int with_rays = 0; with_rays < 2; ++with_rays) {
+        std::vector<T> ta, tb;
+        std::vector<std::vector<ttcr::sxyz<T>>> ra, rb;
+        std::vector<std::vector<ttcr::sijv<T>>> ma, mb;
+        if (with_rays) { ref->raytrace(Tx, t0, Rx, ta, ra, ma, 0); gpu->raytrace(Tx, t0, Rx, tb, rb, mb, 0); }
+        else { ref->raytrace(Tx, t0, Rx, ta, ma, 0); gpu->raytrace(Tx, t0, Rx, tb, mb, 0); }
+        int mbad = ma.size() != mb.size() || ta.size() != tb.size() || std::memcmp(ta.data(), tb.data(), ta.size() * sizeof(T)) != 0;
+        size_t nnz = 0;
+        for (size_t n = 0; !mbad && n < ma.size(); ++n) {
+            mbad |= ma[n].size() != mb[n].size();
+            for (size_t k = 0; !mbad && k < ma[n].size(); ++k)
+                mbad |= ma[n][k].i != mb[n][k].i || ma[n][k].j != mb[n][k].j || std::memcmp(&ma[n][k].v, &mb[n][k].v, sizeof(T)) != 0;
+            nnz += ma[n].size();
+        }
+        if (mbad || nnz == 0) ++bad;
+        std::printf("%-28s %s  %zu entries\n", with_rays ? "M (r_data, m_data) <double>" : "M (m_data) <double>", (mbad || nnz == 0) ? "MISMATCH" : "ok", nnz);
+    }
+    return bad;
+}
+
 int main() {
     int bad = 0;
     try {
@@ -110,6 +149,7 @@ int main() {
         bad += run<double, true>(true, "Grid3Drcfs<double> weno");
         bad += run<float, false>(false, "Grid3Drnfs<float> fo");
         bad += run<float, true>(false, "Grid3Drcfs<float> fo");
+        bad += run_m();
     } catch (const std::exception& e) {
         std::printf("exception: %s\n", e.what());
         return 2;

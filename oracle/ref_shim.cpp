@@ -44,6 +44,8 @@ struct Base {
                                 const double* rx, size_t nrx, double* tt) = 0;
     virtual void raytrace_rays(const double* tx, const double* t0, size_t ntx, const double* rx, size_t nrx, double* tt,
                                size_t th, size_t* npts, double* xyz, size_t cap) = 0;
+    virtual void raytrace_m(const double* tx, const double* t0, size_t ntx, const double* rx, size_t nrx, double* tt, size_t th,
+                            size_t* nnz, unsigned long long* col, double* val, size_t cap, int with_rays) = 0;
     virtual void get_tt(double* out, size_t th) = 0;
     virtual void niter(int* a, int* b) = 0;
     virtual size_t nnodes() = 0;
@@ -99,6 +101,29 @@ struct Impl : Base {
                 xyz[3 * (cap * i + k)] = double(r_data[i][k].x);
                 xyz[3 * (cap * i + k) + 1] = double(r_data[i][k].y);
                 xyz[3 * (cap * i + k) + 2] = double(r_data[i][k].z);
+            }
+        }
+    }
+    // Grid3D::raytrace(Tx,t0,Rx,traveltimes,m_data,threadNo) (Grid3D.h:743-780) or -- with_rays -- the overload with r_data and
+    // m_data (:646-690; the two walk the M terms differently): receiver n gets nnz[n] (column, value) pairs of the matrix M in
+    // the order the reference leaves them in m_data[n], the first `cap` of them stored at cap * n
+    void raytrace_m(const double* tx, const double* t0, size_t ntx, const double* rx, size_t nrx, double* tt, size_t th,
+                    size_t* nnz, unsigned long long* col, double* val, size_t cap, int with_rays) override {
+        std::vector<ttcr::sxyz<T>> Tx, Rx;
+        pts(tx, ntx, Tx);
+        pts(rx, nrx, Rx);
+        std::vector<T> vt0(ntx), vtt(nrx);
+        for (size_t i = 0; i < ntx; ++i) vt0[i] = T(t0[i]);
+        std::vector<std::vector<ttcr::sijv<T>>> m_data;
+        std::vector<std::vector<ttcr::sxyz<T>>> r_data;
+        if (with_rays) base().raytrace(Tx, vt0, Rx, vtt, r_data, m_data, th);
+        else base().raytrace(Tx, vt0, Rx, vtt, m_data, th);
+        for (size_t i = 0; i < nrx; ++i) {
+            tt[i] = double(vtt[i]);
+            nnz[i] = m_data[i].size();
+            for (size_t k = 0; k < m_data[i].size() && k < cap; ++k) {
+                col[cap * i + k] = m_data[i][k].j;
+                val[cap * i + k] = double(m_data[i][k].v);
             }
         }
     }
@@ -218,6 +243,10 @@ int ttcr_ref_raytrace(void* h, const double* tx, const double* t0, size_t ntx, c
 int ttcr_ref_raytrace_rays(void* h, const double* tx, const double* t0, size_t ntx, const double* rx, size_t nrx, double* tt,
                            size_t thread_no, size_t* npts, double* xyz, size_t cap) {
     return guard([&] { static_cast<Base*>(h)->raytrace_rays(tx, t0, ntx, rx, nrx, tt, thread_no, npts, xyz, cap); });
+}
+int ttcr_ref_raytrace_m(void* h, const double* tx, const double* t0, size_t ntx, const double* rx, size_t nrx, double* tt,
+                        size_t thread_no, size_t* nnz, unsigned long long* col, double* val, size_t cap, int with_rays) {
+    return guard([&] { static_cast<Base*>(h)->raytrace_m(tx, t0, ntx, rx, nrx, tt, thread_no, nnz, col, val, cap, with_rays); });
 }
 int ttcr_ref_raytrace_multi(void* h, size_t nsrc, const double* tx, const double* t0,
                             const double* rx, size_t nrx, double* tt, double* seconds) {

@@ -204,8 +204,11 @@ def test_errors_match_reference_behaviour():
         g.raytrace(np.array([[9.5, 0, 0]]), np.array([[1.0, 1, 1]]))
     with pytest.raises(ValueError, match="Thread number"):
         g.get_grid_traveltimes(3)
-    with pytest.raises(NotImplementedError):
-        g.raytrace(np.array([[1.0, 1, 1]]), np.array([[2.0, 2, 2]]), compute_M=True)
+    with pytest.raises(ValueError, match="mutually exclusive"):      # rgrid.pyx:907-908
+        g.raytrace(np.array([[1.0, 1, 1]]), np.array([[2.0, 2, 2]]), compute_M=True, compute_L=True)
+    gc = Grid3d(x[:5], x[:5], x[:5], cell_slowness=1, tt_from_rp=False)
+    with pytest.raises(NotImplementedError):                         # rgrid.pyx:910-911: M is defined for node slowness only
+        gc.raytrace(np.array([[1.0, 1, 1]]), np.array([[2.0, 2, 2]]), compute_M=True)
     g3 = Grid3d(x, x, x, cell_slowness=0, tt_from_rp=False)
     with pytest.raises(RuntimeError, match="slowness"):
         g3.raytrace(np.array([[1.0, 1, 1]]), np.array([[2.0, 2, 2]]))
@@ -291,6 +294,57 @@ def test_raypaths_vs_oracle(oracle, dtype):
         t1, r1 = g.raytrace(src[i:i + 1], rcv[i:i + 1], return_rays=True)
         assert tt[i] == t1[0] and np.array_equal(rays[i], r1[0])
         assert np.array_equal(rays[i][-1], src[i].astype(dtype).astype(np.float64))
+
+
+@pytest.mark.parametrize("with_rays", [False, True])
+@pytest.mark.parametrize("dtype,interp_vel", [(np.float64, False), (np.float64, True), (np.float32, False)])
+def test_compute_M_vs_reference(oracle, dtype, interp_vel, with_rays):
+    """compute_M=True: the sensitivity matrices M of Grid3D::raytrace(.., m_data) and (.., r_data, m_data) (Grid3D.h:646-690,
+    :743-780; Grid3Drn::getRaypath with m_data, Grid3Drn.h:1500-1801, :2144-2448) against the UNMODIFIED reference run live
+    (oracle/_ref).  The reference's two overloads differ (the first gives the terms of the walk's steps ds = 0, the second
+    the leg to the plane in front of Tx); both are reproduced: in double the columns, the values (signed zeros included)
+    and their order are identical; in float (the two solvers' float fields differ by rounding) the row sums agree."""
+    if not oracle.have_ref():
+        pytest.skip("oracle/_ref (the reference built from /root/reference) is not available")
+    import scipy.sparse as sp
+    from ttcr_b200 import Grid3d
+    n = 25
+    x = np.linspace(0.0, 12.0, n)
+    X, Y, Z = np.meshgrid(x, x, x, indexing="ij")
+    s = ((1 + 0.3 * np.sin(0.7 * X) * np.cos(0.9 * Y)) / (1 + 0.1 * Z)).astype(dtype)
+    dx = float(x.astype(dtype)[1] - x.astype(dtype)[0])
+    rng = np.random.default_rng(5)
+    src = np.array([[3.3, 7.1, 8.9]])
+    rcv = np.vstack([rng.uniform(1.0, 11.0, (12, 3)), [[x[5], x[7], 3.3], [x[10], x[11], x[12]], src[0]]])
+    g = Grid3d(x, x, x, cell_slowness=0, tt_from_rp=True, interp_vel=interp_vel, weno=1, eps=1e-15, maxit=20, dtype=dtype)
+    out = g.raytrace(src, rcv, s, compute_M=True, return_rays=with_rays)
+    tt, M = out[0], out[-1]
+    assert len(M) == 1 and sp.isspmatrix_csr(M[0]) and M[0].shape == (rcv.shape[0], n ** 3)
+    ref = oracle.RefGrid(n - 1, n - 1, n - 1, dx, eps=1e-15, maxit=20, weno=True, dtype=dtype, tt_from_rp=True, interp_vel=interp_vel)
+    ref.set_slowness(oracle.to_cxx(s))
+    tref, mref = ref.raytrace_m(src.astype(dtype), 0.0, rcv.astype(dtype), with_rays=with_rays)
+    if dtype == np.float64:
+        assert np.array_equal(tt, tref)
+    else:
+        assert np.allclose(tt, tref, rtol=1e-4)
+    nz = 0
+    for i, (col, val) in enumerate(mref):
+        order = np.argsort(col.astype(np.int64), kind="stable")      # rgrid.pyx:1176-1183 emits a row by ascending column
+        a, b = M[0].indptr[i], M[0].indptr[i + 1]
+        if dtype == np.float64:
+            assert np.array_equal(M[0].indices[a:b], col.astype(np.int64)[order])
+            assert np.array_equal(M[0].data[a:b], val[order])
+            assert np.array_equal(np.signbit(M[0].data[a:b]), np.signbit(val[order]))
+        else:
+            # the float reference walks ITS float field, the device its own (they differ by ~1e-6): a ray may cross a cell
+            # corner on the other side, so columns are not compared; the row sums (- sum of s^2 ds, the weights of a
+            # segment add up to one) are
+            assert np.isclose(M[0].data[a:b].sum(), val.sum(), rtol=2e-3, atol=1e-6)
+        nz += int(np.count_nonzero(val))
+    if dtype == np.float64:
+        assert M[0].indptr[-1] == sum(c.size for c, _ in mref)
+    assert mref[-1][0].size == 0 and M[0].indptr[-1] == M[0].indptr[-2]   # the receiver on the source: no ray, no terms
+    assert nz > 0
 
 
 @pytest.mark.parametrize("n_threads", [1, 2, 3])

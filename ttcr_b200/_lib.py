@@ -23,7 +23,7 @@ SYMBOLS = (
     "ttcr_b200_create", "ttcr_b200_destroy", "ttcr_b200_last_error", "ttcr_b200_set_slowness",
     "ttcr_b200_set_slowness_device", "ttcr_b200_set_slowness_device_planes", "ttcr_b200_get_tt_device", "ttcr_b200_get_slowness", "ttcr_b200_raytrace", "ttcr_b200_raytrace_multi", "ttcr_b200_get_tt",
     "ttcr_b200_get_niter", "ttcr_b200_set_option", "ttcr_b200_n_slots", "ttcr_b200_solve",
-    "ttcr_b200_get_stats", "ttcr_b200_device_bytes", "ttcr_b200_version", "ttcr_b200_raytrace_rays", "ttcr_b200_get_rays",
+    "ttcr_b200_get_stats", "ttcr_b200_device_bytes", "ttcr_b200_version", "ttcr_b200_raytrace_rays", "ttcr_b200_get_rays", "ttcr_b200_get_m_terms",
     "ttcr_b200_create2d", "ttcr_b200_destroy2d", "ttcr_b200_set_slowness2d", "ttcr_b200_get_slowness2d", "ttcr_b200_raytrace2d",
     "ttcr_b200_raytrace2d_multi", "ttcr_b200_get_tt2d", "ttcr_b200_get_niter2d", "ttcr_b200_last_solve_ms2d",
 )
@@ -71,6 +71,7 @@ def load() -> C.CDLL:
     lib.ttcr_b200_raytrace.argtypes = [vp, vp, vp, sz, vp, sz, vp, sz]
     lib.ttcr_b200_raytrace_rays.argtypes = [vp, vp, vp, sz, vp, sz, vp, vp, sz]
     lib.ttcr_b200_get_rays.argtypes = [vp, sz, vp]
+    lib.ttcr_b200_get_m_terms.argtypes = [vp, sz, vp, vp]
     lib.ttcr_b200_raytrace_multi.argtypes = [vp, sz, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.ttcr_b200_get_tt.argtypes = [vp, vp, sz, i32]
     lib.ttcr_b200_get_niter.argtypes = [vp, sz, C.POINTER(i32), C.POINTER(i32)]

@@ -83,6 +83,7 @@ struct GridBase {
     virtual void raytrace_rays(const void* tx, const void* t0, size_t ntx, const void* rx, size_t nrx, void* tt, size_t* npts,
                                size_t slot) = 0;
     virtual void get_rays(size_t slot, void* xyz) = 0;
+    virtual void get_m_terms(size_t slot, unsigned long long* node, void* value) = 0;
     virtual void get_tt(void* out, size_t slot, int order) = 0;
     virtual void stats(size_t slot, ttcr_b200_stats* out) = 0;
     virtual void set_option(const std::string& key, double v) = 0;
@@ -310,6 +311,18 @@ class Grid final : public GridBase {
         if (!s.rays.empty()) std::memcpy(xyz, s.rays.data(), s.rays.size() * sizeof(T));
     }
 
+    // The raw terms of the matrix M of the last raytrace_rays call made with option "m_terms" = 1 (Grid3Drn::getRaypath with
+    // m_data, Grid3Drn.h:1500-1801): 8 (column, value) pairs per ray point, ray after ray, in the order the reference produces
+    // them; the 8 pairs of every ray's FIRST point (the receiver closes no segment) are zero.  8 * sum(ray_npts) elements each.
+    void get_m_terms(size_t slot, unsigned long long* node, void* value) override {
+        Slot& s = slot_at(slot);
+        if (s.m_node.size() != 8 * (s.rays.size() / 3)) throw Err(TTCR_B200_ERR_LOGIC, "no M terms: set option m_terms = 1 before raytrace_rays");
+        if (!s.m_node.empty()) {
+            std::memcpy(node, s.m_node.data(), s.m_node.size() * sizeof(unsigned long long));
+            std::memcpy(value, s.m_val.data(), s.m_val.size() * sizeof(T));
+        }
+    }
+
     void raytrace_impl(const void* tx, const void* t0, size_t ntx, const void* rx, size_t nrx, void* tt, size_t slot, size_t* npts) {
         CK(cudaSetDevice(dev_));
         Slot& s = slot_at(slot);
@@ -324,6 +337,7 @@ class Grid final : public GridBase {
         ensure_pts(s, 4 * ntx + 5 * nrx);   // Tx, t0 | Rx, traveltimes, status (before the solve: it uploads Tx into this buffer)
         solve_device(s, vtx, vt0);
         s.rays.clear();
+        s.m_node.clear(); s.m_val.clear();
         if (nrx) {
             T* const h_rx = s.h_pts + 4 * ntx;
             T* const d_rx = s.d_pts + 4 * ntx;
@@ -331,7 +345,7 @@ class Grid final : public GridBase {
             CK(cudaMemcpyAsync(d_rx, h_rx, 3 * nrx * sizeof(T), cudaMemcpyHostToDevice, s.stream));
             T* d_out = d_rx + 3 * nrx;
             const unsigned rp_blocks = (unsigned)((nrx + 63) / 64);
-            ScratchBuf b_rn, b_off, b_xyz;
+            ScratchBuf b_rn, b_off, b_xyz, b_mn, b_mv;
             if (want_rays) {   // counts and offsets of the ray points
                 b_rn.alloc(nrx * sizeof(int), s.stream);
                 b_off.alloc(nrx * sizeof(unsigned long long), s.stream);
@@ -341,7 +355,7 @@ class Grid final : public GridBase {
             if (walk) {
                 // Grid3D.h:493-501 with tt_from_rp: traveltimes integrated along the raypaths (raypath.cuh)
                 k_tt_from_rp<T><<<rp_blocks, 64, 0, s.stream>>>(g_, d_, s.tt[0], slo_[0], s.d_pts, s.d_pts + 3 * ntx, (int)ntx, d_rx, (int)nrx,
-                                                                d_out, d_out + nrx, d_rn, nullptr, nullptr, intvel_);
+                                                                d_out, d_out + nrx, d_rn, nullptr, nullptr, intvel_, want_rays ? m_terms_ : 0);
             } else {
                 k_interp<T><<<(unsigned)((nrx + 127) / 128), 128, 0, s.stream>>>(g_, d_, s.tt[0], d_rx, (int)nrx, d_out);
             }
@@ -373,11 +387,26 @@ class Grid final : public GridBase {
                 b_xyz.alloc(3 * total * sizeof(T), s.stream);
                 T* const d_xyz = b_xyz.as<T>();
                 CK(cudaMemcpyAsync(d_off, off.data(), nrx * sizeof(unsigned long long), cudaMemcpyHostToDevice, s.stream));
+                unsigned long long* d_mn = nullptr;
+                T* d_mv = nullptr;
+                if (m_terms_) {   // (cell grids: the reference defines M for node slowness only, rgrid.pyx:910-911)
+                    if (cell_) throw Err(TTCR_B200_ERR_INVALID, "M terms are defined for node slowness only");
+                    b_mn.alloc(8 * total * sizeof(unsigned long long), s.stream);
+                    b_mv.alloc(8 * total * sizeof(T), s.stream);
+                    d_mn = b_mn.as<unsigned long long>(); d_mv = b_mv.as<T>();
+                    CK(cudaMemsetAsync(d_mn, 0, 8 * total * sizeof(unsigned long long), s.stream));
+                    CK(cudaMemsetAsync(d_mv, 0, 8 * total * sizeof(T), s.stream));
+                }
                 k_tt_from_rp<T><<<rp_blocks, 64, 0, s.stream>>>(g_, d_, s.tt[0], slo_[0], s.d_pts, s.d_pts + 3 * ntx, (int)ntx, d_rx, (int)nrx,
-                                                                d_out, d_out + nrx, d_rn, d_off, d_xyz, intvel_);
+                                                                d_out, d_out + nrx, d_rn, d_off, d_xyz, intvel_, m_terms_, d_mn, d_mv);
                 CK(cudaGetLastError());
                 s.rays.resize(3 * total);
                 CK(cudaMemcpyAsync(s.rays.data(), d_xyz, 3 * total * sizeof(T), cudaMemcpyDeviceToHost, s.stream));
+                if (m_terms_) {
+                    s.m_node.resize(8 * total); s.m_val.resize(8 * total);
+                    CK(cudaMemcpyAsync(s.m_node.data(), d_mn, 8 * total * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s.stream));
+                    CK(cudaMemcpyAsync(s.m_val.data(), d_mv, 8 * total * sizeof(T), cudaMemcpyDeviceToHost, s.stream));
+                }
                 CK(cudaStreamSynchronize(s.stream));
                 if (translate_)   // Grid3D.h:578-584: r_data += origin
                     for (size_t n = 0; n < s.rays.size(); n += 3) { s.rays[n] += origin_[0]; s.rays[n + 1] += origin_[1]; s.rays[n + 2] += origin_[2]; }
@@ -449,6 +478,10 @@ class Grid final : public GridBase {
             weno_kernel_ = (int)v;
         }
         else if (key == "plane_pdl") plane_pdl_ = v != 0;
+        else if (key == "m_terms") {
+            if (v != 0 && v != 1 && v != 2) throw Err(TTCR_B200_ERR_INVALID, "m_terms: 0, 1 (as the m_data overload) or 2 (as the r_data + m_data overload)");
+            m_terms_ = (int)v;
+        }
         else if (key == "use_pool") {}
         else if (key == "maxit") maxit_ = (int)v;
         else throw Err(TTCR_B200_ERR_INVALID, "unknown option '" + key + "'");
@@ -479,6 +512,8 @@ class Grid final : public GridBase {
         struct PlaneGraph { cudaGraphExec_t exec = nullptr; bool pdl = false; };
         PlaneGraph pgraph[8][2];             // captured plane launches of a direction: [dir][first order | WENO]
         std::vector<T> rays;                 // points of the last raytrace_rays call, ray after ray (x,y,z)
+        std::vector<unsigned long long> m_node;   // raw M terms of that call (option m_terms): 8 per ray point
+        std::vector<T> m_val;
         std::vector<cudaEvent_t> sweep_ev;   // pairs of events around the directional sweeps
         size_t sweep_ev_used = 0;
     };
@@ -857,6 +892,7 @@ class Grid final : public GridBase {
     int maxit_;
     bool weno_, ttrp_, cell_, translate_, intvel_;
     bool have_slowness_ = false;
+    int m_terms_ = 0;   // raytrace_rays also produces the raw terms of the matrix M (get_m_terms): 1 / 2 = which overload
     cudaStream_t copy_st_ = nullptr;   // H2D leg of the pipelined model import
     cudaEvent_t copy_ev_[9] = {};
     // plane-per-launch sweeps (WENO stage, small grids): replay a captured graph / chain the planes by PDL
@@ -1163,6 +1199,11 @@ int ttcr_b200_raytrace_rays(ttcr_b200_grid* g, const void* tx, const void* t0, s
         size_t dummy = 0;
         g->impl->raytrace_rays(tx, t0, ntx, rx, nrx, tt, ray_npts ? ray_npts : &dummy, slot);
     });
+}
+
+int ttcr_b200_get_m_terms(ttcr_b200_grid* g, size_t slot, unsigned long long* node_out, void* value_out) {
+    if (!g) return TTCR_B200_ERR_INVALID;
+    return guard([&] { g->impl->get_m_terms(slot, node_out, value_out); });
 }
 
 int ttcr_b200_get_rays(ttcr_b200_grid* g, size_t slot, void* xyz_out) {

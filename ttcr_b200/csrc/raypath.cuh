@@ -176,12 +176,48 @@ __device__ __forceinline__ T rp_dist(T ax, T ay, T az, T bx, T by, T bz) {
     return rp_sqrt((ax - bx) * (ax - bx) + (ay - by) * (ay - by) + (az - bz) * (az - bz));
 }
 
+// The eight terms one ray segment adds to the matrix M (Grid3Drn::getRaypath with m_data, Grid3Drn.h:1590-1626, :1676-1709,
+// :1718-1751, :1760-1793): -s^2 ds times the trilinear weight of each node of the cell around the segment's mid point, with
+// the reference's arithmetic -- T variables, the "1. -" and the product of the three factors in double, node positions
+// iv*dx WITHOUT the grid's origin, column index (kv nny + jv) nnx + iv.  Raw terms: the reference merges the terms of equal
+// column in order of appearance; the host does that (ttcr_b200/rgrid.py).
+template <typename T>
+__device__ void rp_m_terms(const Geom<T>& g, const Dims& d, const T* __restrict__ s_l1, T ax, T ay, T az, T bx, T by, T bz, bool interp_vel,
+                           unsigned long long* __restrict__ node, T* __restrict__ val) {
+    const T dx = g.dx;
+    const T mx = T(0.5) * (ax + bx), my = T(0.5) * (ay + by), mz = T(0.5) * (az + bz);   // mid_pt = 0.5 * (a + b)
+    T s = rp_slow_at(g, d, s_l1, mx, my, mz, interp_vel);
+    s *= s;
+    const T ds = rp_dist(ax, ay, az, bx, by, bz);
+    const unsigned long long ix = (unsigned long long)((mx - g.xmin) / dx), iy = (unsigned long long)((my - g.ymin) / dx),
+                             iz = (unsigned long long)((mz - g.zmin) / dx);
+    const unsigned long long nnx = (unsigned long long)d.ni, nny = (unsigned long long)d.nj;
+    int e = 0;
+    for (unsigned long long ii = 0; ii < 2; ++ii)
+        for (unsigned long long jj = 0; jj < 2; ++jj)
+            for (unsigned long long kk = 0; kk < 2; ++kk) {
+                const unsigned long long iv = ix + ii, jv = iy + jj, kv = iz + kk;
+                const T dvdv = T((1. - (double)(rp_abs(mx - T(iv) * dx) / dx)) * (1. - (double)(rp_abs(my - T(jv) * dx) / dx)) *
+                                 (1. - (double)(rp_abs(mz - T(kv) * dx) / dx)));
+                node[e] = (kv * nny + jv) * nnx + iv;
+                val[e] = -s * ds * dvdv;
+                ++e;
+            }
+}
+
 // status: 0 ok, 1 the ray left the grid (the reference throws), 2 it did not reach a source
 template <typename T>
 __global__ void k_tt_from_rp(Geom<T> g, Dims d, const T* __restrict__ tt_l1, const T* __restrict__ s_l1, const T* __restrict__ tx,
                              const T* __restrict__ t0, int ntx, const T* __restrict__ rx, int nrx, T* __restrict__ out,
                              T* __restrict__ status, int* __restrict__ ray_n, const unsigned long long* __restrict__ ray_off,
-                             T* __restrict__ ray_xyz, bool interp_vel) {
+                             T* __restrict__ ray_xyz, bool interp_vel, int m_mode = 0, unsigned long long* __restrict__ m_node = nullptr,
+                             T* __restrict__ m_val = nullptr) {
+    // m_mode: the reference's two getRaypath overloads with m_data differ (both are reproduced as they are):
+    //   1 = m_data only (Grid3Drn.h:1500-1801): a walk step sets prev_pt = curr_pt BEFORE its M terms, so the terms of the
+    //       steps carry ds = 0 (their columns still enter the matrix, with value -0); the last legs are right
+    //   2 = r_data and m_data (:2144-2448): the steps are right (prev_pt = r_data.back() before the push); on the leg to the
+    //       plane in front of Tx the point is pushed first, so THAT leg carries ds = 0
+    //   both return tt = 0 (not t0) for a receiver that coincides with a Tx point
     // ray_n != nullptr: the points of the raypath are wanted too (Grid3Drn::getRaypath, Grid3Drn.h:1339-1500: the same walk
     // with r_data.push_back).  First launch with ray_xyz == nullptr counts them, the second one (ray_off = exclusive prefix
     // sum of the counts) stores them.
@@ -193,6 +229,11 @@ __global__ void k_tt_from_rp(Geom<T> g, Dims d, const T* __restrict__ tt_l1, con
         if (rp) { rp[3 * npt] = x; rp[3 * npt + 1] = y; rp[3 * npt + 2] = z; }
         ++npt;
     };
+    // m_node != nullptr (store pass only): the 8 raw M terms of the segment that ENDS at the point about to be pushed go to
+    // slot 8 * (ray_off[r] + its index); every point but the receiver closes exactly one segment
+    auto mterms = [&](T ax, T ay, T az, T bx, T by, T bz) {
+        if (m_mode && m_node && rp) rp_m_terms(g, d, s_l1, ax, ay, az, bx, by, bz, interp_vel, m_node + 8 * (ray_off[r] + npt), m_val + 8 * (ray_off[r] + npt));
+    };
     const T dx = g.dx;
     const T k1 = 1. / 24., k2 = 9. / 8.;
     const T maxDist = rp_sqrt(dx * dx + dx * dx + dx * dx);
@@ -200,7 +241,7 @@ __global__ void k_tt_from_rp(Geom<T> g, Dims d, const T* __restrict__ tt_l1, con
     push(Rx, Ry, Rz);
     for (int ns = 0; ns < ntx; ++ns)
         if (Rx == tx[3 * ns] && Ry == tx[3 * ns + 1] && Rz == tx[3 * ns + 2]) {
-            out[r] = t0[ns];
+            out[r] = m_mode ? T(0) : t0[ns];
             status[r] = T(0);
             if (ray_n) ray_n[r] = npt;
             return;
@@ -234,7 +275,9 @@ __global__ void k_tt_from_rp(Geom<T> g, Dims d, const T* __restrict__ tt_l1, con
         s2 = rp_slow_at(g, d, s_l1, cx, cy, cz, interp_vel);
         ttr += 0.5 * (s1 + s2) * rp_dist(px, py, pz, cx, cy, cz);
         s1 = s2;
+        if (m_mode == 2) mterms(cx, cy, cz, px, py, pz);
         px = cx; py = cy; pz = cz;
+        if (m_mode == 1) mterms(cx, cy, cz, px, py, pz);   // (sic: prev_pt = curr_pt already, Grid3Drn.h:1587-1594)
         push(cx, cy, cz);
         // close enough to one of the Tx points?  (the reference does not leave this loop early)
         for (int ns = 0; ns < ntx; ++ns) {
@@ -245,14 +288,18 @@ __global__ void k_tt_from_rp(Geom<T> g, Dims d, const T* __restrict__ tt_l1, con
                 if (rp_dist(cx, cy, cz, px, py, pz) > dist || (cx == Tx && cy == Ty && cz == Tz)) {
                     s2 = rp_slow_at(g, d, s_l1, Tx, Ty, Tz, interp_vel);
                     ttr += t0[ns] + 0.5 * (s1 + s2) * rp_dist(px, py, pz, Tx, Ty, Tz);
+                    mterms(Tx, Ty, Tz, px, py, pz);
                     push(Tx, Ty, Tz);
                 } else {
                     s2 = rp_slow_at(g, d, s_l1, cx, cy, cz, interp_vel);
                     ttr += 0.5 * (s1 + s2) * rp_dist(px, py, pz, cx, cy, cz);
+                    if (m_mode == 2) mterms(cx, cy, cz, cx, cy, cz);   // (sic: pushed first, prev_pt = r_data.back(), :2357-2366)
+                    else mterms(cx, cy, cz, px, py, pz);
                     push(cx, cy, cz);
                     s1 = s2;
                     s2 = rp_slow_at(g, d, s_l1, Tx, Ty, Tz, interp_vel);
                     ttr += t0[ns] + 0.5 * (s1 + s2) * rp_dist(cx, cy, cz, Tx, Ty, Tz);
+                    mterms(Tx, Ty, Tz, cx, cy, cz);
                     push(Tx, Ty, Tz);
                 }
                 reached = true;

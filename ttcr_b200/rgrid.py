@@ -20,8 +20,8 @@ Differences, all deliberate:
   ttcr/Grid3Drn.h:1103-1243) runs on the device, one thread per receiver, bit-identical to the reference.
 * ``return_rays=True`` returns the raypaths of ``Grid3Drn::getRaypath`` (ttcr/Grid3Drn.h:1339-1500), walked on the
   device (two passes: count, then store), bit-identical to the reference.
-* ``compute_L`` / ``compute_M`` raise ``NotImplementedError`` (for the FSM the reference itself rejects
-  ``compute_L``, rgrid.pyx:915-916; M matrices belong to the post-solve stages).
+* ``compute_L`` raises ``NotImplementedError`` (for the FSM the reference itself rejects it, rgrid.pyx:915-916);
+  ``compute_M`` returns the reference's matrices M (raw terms from the device's raypath walk, merged on the host).
 """
 from __future__ import annotations
 
@@ -283,9 +283,6 @@ class _Grid3d:
             raise NotImplementedError("compute_L defined only for grids with slowness defined for cells")
         if compute_L:
             raise NotImplementedError("compute_L defined for the FSM")   # rgrid.pyx:915-916
-        if compute_M:
-            raise NotImplementedError("M matrices are a post-solve stage outside the B200 FSM path")
-
         evID = None
         if source.shape[1] == 5:
             src = source[:, 2:5]
@@ -343,6 +340,27 @@ class _Grid3d:
                 iRx.append(ii); vRx.append(rcv[ii, :])
 
         tt = np.zeros((rcv.shape[0],), dtype=self.dtype)
+        if compute_M:
+            # rgrid.pyx:1057-1060, :1162-1186: one csr matrix (receivers of the event x nodes) per event; the raw terms come
+            # from the device's raypath walk (Grid3Drn::getRaypath with m_data), merged here as the reference merges them
+            import scipy.sparse as sp
+            if thread_no is not None:
+                assert nTx == 1
+            slot = 0 if thread_no is None else int(thread_no)
+            rays = [None] * rcv.shape[0]
+            M = []
+            nn = self.get_number_of_nodes()
+            for n in range(nTx):
+                t, r, m = self._raytrace_one(vTx[n], vt0[n], vRx[n], slot, rays=True, m_terms=2 if return_rays else 1)
+                tt[iRx[n]] = t
+                for i, ir in enumerate(iRx[n]):
+                    rays[int(ir)] = r[i]
+                indptr = np.zeros(len(m) + 1, dtype=np.int64)
+                indptr[1:] = np.cumsum([c.size for c, _ in m])
+                indices = np.concatenate([c for c, _ in m]) if m else np.zeros(0, dtype=np.int64)
+                val = np.concatenate([v for _, v in m]) if m else np.zeros(0)
+                M.append(sp.csr_matrix((val.astype(np.float64), indices.astype(np.int64), indptr), shape=(len(m), nn)))
+            return (tt, rays, M) if return_rays else (tt, M)
         if return_rays:
             # rgrid.pyx:1072-1084, :1110-1121: one array (npts, 3) per receiver, in the order of rcv.  Sources run one
             # after the other on one slot (the walk is a few microseconds per receiver next to the solve).
@@ -403,20 +421,53 @@ class _Grid3d:
                                                          nw.ctypes.data))
         return out.reshape(n, m), np.column_stack([ni, nw]).astype(np.int64)
 
-    def _raytrace_one(self, tx, t0, rx, slot, rays=False):
+    @staticmethod
+    def _merge_m_terms(node, val):
+        """One ray's raw M terms -> (columns ascending, values): terms of equal column are added in order of appearance
+        (``m_data[nm].v += m.v``, Grid3Drn.h:1612-1623), rows are emitted by ascending column (rgrid.pyx:1176-1183)."""
+        first = {}
+        cols, vals = [], []
+        for j, v in zip(node.tolist(), val):
+            k = first.get(j)
+            if k is None:
+                first[j] = len(cols)
+                cols.append(j)
+                vals.append(v)
+            else:
+                vals[k] = vals[k] + v          # (numpy scalar of the grid's dtype: the reference adds in T)
+        order = np.argsort(np.asarray(cols, dtype=np.int64), kind="stable")
+        return np.asarray(cols, dtype=np.int64)[order], np.asarray(vals, dtype=val.dtype)[order]
+
+    def _raytrace_one(self, tx, t0, rx, slot, rays=False, m_terms=False):
         tx = np.ascontiguousarray(tx, dtype=self.dtype)
         t0 = np.ascontiguousarray(t0, dtype=self.dtype)
         rx = np.ascontiguousarray(rx, dtype=self.dtype)
         out = np.empty(rx.shape[0], dtype=self.dtype)
         if rays:
             npts = np.zeros(rx.shape[0], dtype=np.uintp)
-            self._chk(self._lib.ttcr_b200_raytrace_rays(self._h, tx.ctypes.data, t0.ctypes.data, tx.shape[0], rx.ctypes.data,
-                                                        rx.shape[0], out.ctypes.data, npts.ctypes.data, slot))
+            if m_terms:
+                self.set_option("m_terms", int(m_terms))   # 1: as Grid3D::raytrace(.., m_data), 2: as (.., r_data, m_data)
+            try:
+                self._chk(self._lib.ttcr_b200_raytrace_rays(self._h, tx.ctypes.data, t0.ctypes.data, tx.shape[0], rx.ctypes.data,
+                                                            rx.shape[0], out.ctypes.data, npts.ctypes.data, slot))
+            finally:
+                if m_terms:
+                    self.set_option("m_terms", 0)
             xyz = np.empty((int(npts.sum()), 3), dtype=self.dtype)
             self._chk(self._lib.ttcr_b200_get_rays(self._h, slot, xyz.ctypes.data))
             ends = np.cumsum(npts).astype(np.int64)
             # the reference hands back float64 arrays whatever the grid's dtype (rgrid.pyx:1076: np.empty((n, 3)))
-            return out, [xyz[int(e - n):int(e)].astype(np.float64) for n, e in zip(npts, ends)]
+            paths = [xyz[int(e - n):int(e)].astype(np.float64) for n, e in zip(npts, ends)]
+            if not m_terms:
+                return out, paths
+            node = np.zeros(8 * int(npts.sum()), dtype=np.uint64)
+            val = np.zeros(8 * int(npts.sum()), dtype=self.dtype)
+            self._chk(self._lib.ttcr_b200_get_m_terms(self._h, slot, node.ctypes.data, val.ctypes.data))
+            m = []
+            for n, e in zip(npts, ends):   # (the 8 slots of a ray's first point, the receiver, hold no term)
+                a, b = 8 * (int(e) - int(n) + 1), 8 * int(e)
+                m.append(self._merge_m_terms(node[a:b], val[a:b]) if b > a else (np.zeros(0, dtype=np.int64), np.zeros(0, dtype=self.dtype)))
+            return out, paths, m
         self._chk(self._lib.ttcr_b200_raytrace(self._h, tx.ctypes.data, t0.ctypes.data, tx.shape[0], rx.ctypes.data,
                                                rx.shape[0], out.ctypes.data, slot))
         return out
